@@ -1,0 +1,240 @@
+/*
+ * siftcuda.h — C ABI of libsiftcuda.so, the B200 (sm_100a) SIFT detect + describe engine.
+ *
+ * This header is the drop-in seam for the hot path of lukevanin/SIFTMetal. In the reference the
+ * seam is the C module `MetalShaders` (Sources/MetalShaders/module.modulemap:1-4, umbrella
+ * Sources/MetalShaders/include/MetalShaders.h:6-11) whose POD structs cross between the Swift
+ * host (Sources/SIFTMetal/SIFT/{SIFT,SIFTOctave,DifferenceOfGaussians}.swift) and the Metal
+ * kernels (Sources/MetalShaders/Metal/ *.metal). Here the whole per-frame pipeline lives behind
+ * the entry points below, so the Swift (or C++/Python) host only marshals pixels in and
+ * keypoints / descriptors out. Every declaration cites the reference interface it replaces.
+ *
+ * Plain C, plain pointers and sizes. No torch types. No CPU fallback: every compute entry point
+ * returns SIFT_ERR_NO_DEVICE / SIFT_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef SIFTCUDA_H
+#define SIFTCUDA_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIFTCUDA_ABI_VERSION 1
+
+/* DifferenceOfGaussians.Configuration (DifferenceOfGaussians.swift:23-51): 7 octaves, 3 scales
+ * per octave, hence 6 Gaussian + 5 DoG slices per octave (:80-81). Fixed, as in the reference. */
+#define SIFT_NUM_OCTAVES 7
+#define SIFT_SCALES_PER_OCTAVE 3
+#define SIFT_NUM_GAUSSIANS 6
+#define SIFT_NUM_DOGS 5
+/* include/SIFTOrientation.h:12, include/SIFTDescriptor.h:14-16 */
+#define SIFT_ORIENTATION_HISTOGRAM_BINS 36
+#define SIFT_DESCRIPTOR_HISTOGRAM_WIDTH 4
+#define SIFT_DESCRIPTOR_ORIENTATION_BINS 8
+#define SIFT_DESCRIPTOR_FEATURE_COUNT 128
+/* include/ConvolutionSeries.h:13 */
+#define SIFT_CONVOLUTION_WEIGHTS_LENGTH 32
+
+/* ---- status codes (the reference aborts via try!/precondition/fatalError; we return) ------- */
+enum {
+    SIFT_OK = 0,
+    SIFT_ERR_INVALID_ARGUMENT = 1, /* null pointer, bad size, batch larger than max_batch        */
+    SIFT_ERR_NO_DEVICE = 2,        /* no CUDA device / not an sm_100 part                          */
+    SIFT_ERR_CUDA = 3,             /* a CUDA runtime call failed (see sift_last_error_string)      */
+    SIFT_ERR_CAPACITY = 4,         /* a device list overflowed its capacity; results truncated —  */
+                                   /* replaces the precondition crash of Buffer.swift:35-39        */
+    SIFT_ERR_NOT_DETECTED = 5,     /* sift_describe before sift_detect (SIFTOctave.swift:354,459)  */
+    SIFT_ERR_OUT_OF_MEMORY = 6
+};
+
+/* ---- configuration ---------------------------------------------------------------------------
+ * SIFT.Configuration (SIFT.swift:57-103). In the reference only `inputSize` can be set and the
+ * thresholds are literals at the call sites (SIFTOctave.swift:217-226, :296-300, :396-401);
+ * sift_config_default() fills exactly those literals. */
+typedef struct SiftConfig {
+    int32_t width;                  /* inputSize.width  (pixels of the BGRA8 input)               */
+    int32_t height;                 /* inputSize.height                                           */
+    int32_t max_batch;              /* frames resident per call; 1 = the reference's behaviour    */
+    float   dog_threshold;          /* 0.0133  (SIFTOctave.swift:218)                             */
+    float   edge_threshold;         /* 10.0    (SIFTOctave.swift:224)                             */
+    int32_t max_interpolation_iterations; /* 5 (SIFTOctave.swift:219)                             */
+    float   max_offset;             /* 0.6     (SIFTOctave.swift:220)                             */
+    int32_t image_border;           /* 5       (SIFTInterpolate.metal:182)                        */
+    float   lambda_orientation;     /* 1.5     (SIFTOctave.swift:298)                             */
+    float   orientation_threshold;  /* 0.8     (SIFTOctave.swift:299)                             */
+    int32_t orientation_smoothing_iterations; /* 6 (SIFTOrientation.metal:167)                    */
+    /* Per-frame list capacities. The reference hard-codes 4096/4096/2048 per octave and aborts
+     * beyond (SIFTOctave.swift:22-26); 0 = size from the image.                   */
+    int32_t max_candidates_per_frame;
+    int32_t max_keypoints_per_frame;
+    int32_t max_descriptors_per_frame;
+    int32_t flags;                  /* SIFT_FLAG_*                                                */
+} SiftConfig;
+
+#define SIFT_FLAG_KEEP_PYRAMID 1    /* keep all Gaussian planes for sift_debug_download           */
+
+/* ---- result PODs -------------------------------------------------------------------------- */
+
+/* SIFTKeypoint (SIFTKeypoint.swift:11-35), field for field; SIMD2 members flattened. It is what
+ * SIFTOctave.interpolateKeypoints builds from SIFTInterpolateOutputKeypoint
+ * (include/SIFTInterpolate.h:34-46, SIFTOctave.swift:257-286). 44 bytes. */
+typedef struct SiftKeypoint {
+    int32_t octave;
+    int32_t scale;
+    float   subScale;
+    int32_t scaledX, scaledY;         /* scaledCoordinate                                         */
+    float   absoluteX, absoluteY;     /* absoluteCoordinate (input-image pixels)                  */
+    float   normalizedX, normalizedY; /* normalizedCoordinate                                     */
+    float   sigma;
+    float   value;
+} SiftKeypoint;
+
+/* SIFTDescriptorResult (include/SIFTDescriptor.h:37-42) with the 128 features packed to bytes
+ * (they are 0…255 by construction, SIFTDescriptor.metal:41-49) — 136 bytes instead of 524.
+ * `keypoint` indexes the frame's keypoint array (octave-major, as returned by the same call). */
+typedef struct SiftDescriptor {
+    int32_t keypoint;
+    float   theta;
+    uint8_t features[SIFT_DESCRIPTOR_FEATURE_COUNT];
+} SiftDescriptor;
+
+/* Result of a batch call. All arrays are context-owned pinned host memory, valid until the next
+ * call on the same context. Keypoints / descriptors are concatenated frame-major, octave-major,
+ * in canonical order (scale, y, x of the originating extremum; orientation bin ascending). */
+typedef struct SiftBatchResult {
+    int32_t n_frames;
+    const int32_t* keypoint_counts;     /* [n_frames][SIFT_NUM_OCTAVES]                           */
+    const int32_t* descriptor_counts;   /* [n_frames][SIFT_NUM_OCTAVES]                           */
+    const int32_t* candidate_counts;    /* [n_frames][SIFT_NUM_OCTAVES] raw 25-neighbour extrema  */
+                                        /* above the 0.8·C_DoG pre-threshold                      */
+    const SiftKeypoint*   keypoints;
+    const SiftDescriptor* descriptors;
+    int64_t total_keypoints;
+    int64_t total_descriptors;
+} SiftBatchResult;
+
+/* Geometry and schedule of one context: DifferenceOfGaussians.init (:233-344) restated. */
+typedef struct SiftInfo {
+    int32_t width, height, max_batch;
+    int32_t octave_width[SIFT_NUM_OCTAVES];
+    int32_t octave_height[SIFT_NUM_OCTAVES];
+    int32_t octave_pitch[SIFT_NUM_OCTAVES];          /* floats per row in device memory           */
+    float   octave_delta[SIFT_NUM_OCTAVES];
+    float   sigmas[SIFT_NUM_OCTAVES][SIFT_NUM_GAUSSIANS];
+    float   seed_sigma;
+    int32_t seed_taps;
+    float   seed_weights[SIFT_CONVOLUTION_WEIGHTS_LENGTH];
+    float   rho[SIFT_NUM_GAUSSIANS - 1];
+    int32_t taps[SIFT_NUM_GAUSSIANS - 1];
+    float   weights[SIFT_NUM_GAUSSIANS - 1][SIFT_CONVOLUTION_WEIGHTS_LENGTH];
+    int32_t max_candidates_per_frame, max_keypoints_per_frame, max_descriptors_per_frame;
+    int64_t device_bytes;                            /* HBM held by the context                   */
+    int32_t sm_count;
+} SiftInfo;
+
+/* Per-stage device times of the last sift_batch_execute, from CUDA events recorded on the
+ * context's own stream (replaces measure(name:) of Utilities/Performance.swift:12-20). ms. */
+#define SIFT_STAGE_SEED 0
+#define SIFT_STAGE_PYRAMID 1     /* blur + DoG + gradient, all octaves                            */
+#define SIFT_STAGE_EXTREMA 2
+#define SIFT_STAGE_REFINE 3
+#define SIFT_STAGE_ORIENTATION 4
+#define SIFT_STAGE_DESCRIPTOR 5
+#define SIFT_STAGE_COUNT 6
+typedef struct SiftTimings {
+    float total_ms;                      /* first launch → last kernel                           */
+    float stage_ms[SIFT_STAGE_COUNT];    /* valid when stage timing was enabled                   */
+    float blur_octave0_ms;               /* the dominant kernel: 5 octave-0 blur launches, summed */
+    int32_t blur_octave0_launches;
+    int32_t kernel_launches;             /* kernels launched by the last execute                  */
+    int32_t stage_timing_enabled;
+} SiftTimings;
+
+typedef struct SiftContext SiftContext;
+
+/* ---- lifetime ----------------------------------------------------------------------------- */
+
+/* Fills the literals the reference uses. Replaces SIFT.Configuration.init(inputSize:)
+ * (SIFT.swift:100-102). */
+int sift_config_default(SiftConfig* config, int32_t width, int32_t height);
+
+/* Replaces SIFT.init(device:configuration:) (SIFT.swift:112-143): allocates every device plane
+ * and list once, computes the Gaussian tap tables on the host in float
+ * (GaussianKernel.swift:20-43, GaussianSeriesKernel.swift:27-51). `device` is a CUDA ordinal
+ * (was: MTLDevice). */
+int sift_create(const SiftConfig* config, int device, SiftContext** out_context);
+void sift_destroy(SiftContext* context);
+int sift_get_info(const SiftContext* context, SiftInfo* out_info);
+
+/* ---- the reference's two entry points ------------------------------------------------------- */
+
+/* Replaces SIFT.getKeypoints(_:) (SIFT.swift:147-152). `bgra8` is a host pointer to
+ * height rows of `pitch_bytes` bytes of BGRA8 pixels (was: a bgra8Unorm MTLTexture,
+ * ConvertSRGBToGrayscaleKernel.swift:34). On return *out_keypoints points at
+ * sum(counts_per_octave) keypoints grouped by octave; the Gaussian-gradient planes stay on the
+ * device for a following sift_describe, exactly like the reference's gradientTextures
+ * (SIFTOctave.swift:354,459). */
+int sift_detect(SiftContext* context, const void* bgra8, int32_t pitch_bytes,
+                const SiftKeypoint** out_keypoints, int32_t counts_per_octave[SIFT_NUM_OCTAVES]);
+
+/* Replaces SIFT.getDescriptors(keypointOctaves:) (SIFT.swift:207-238): orientation assignment
+ * (SIFTOctave.swift:290-382) then one descriptor per (keypoint, orientation)
+ * (SIFTOctave.swift:384-492). `keypoints` are caller-supplied (they may have been filtered),
+ * grouped by octave with `counts_per_octave`; SiftDescriptor.keypoint indexes that array. */
+int sift_describe(SiftContext* context, const SiftKeypoint* keypoints,
+                  const int32_t counts_per_octave[SIFT_NUM_OCTAVES],
+                  const SiftDescriptor** out_descriptors,
+                  int32_t descriptor_counts_per_octave[SIFT_NUM_OCTAVES]);
+
+/* ---- batch path (frames are independent units; they shard across GPUs by context) --------- */
+
+/* getKeypoints + getDescriptors for n ≤ max_batch frames in one go, no host round trip between
+ * the two. images[i] is a host BGRA8 frame. */
+int sift_detect_and_describe_batch(SiftContext* context, const void* const* images, int32_t n,
+                                   int32_t pitch_bytes, SiftBatchResult* out_result);
+
+/* The same, split so that device-resident inputs can be timed apart from PCIe:
+ *   upload (H2D into the context's input arena)  or  set_device_input (caller's device memory,
+ *   n frames `frame_stride_bytes` apart — not copied, must stay valid until execute returns),
+ *   execute (every kernel of the path; returns after the stream drained; SIFT_ERR_CAPACITY if a
+ *   list overflowed), download (D2H of counts, keypoints, descriptors). */
+int sift_batch_upload(SiftContext* context, const void* const* images, int32_t n,
+                      int32_t pitch_bytes);
+int sift_batch_set_device_input(SiftContext* context, const void* device_bgra8, int32_t n,
+                                int32_t pitch_bytes, int64_t frame_stride_bytes);
+int sift_batch_execute(SiftContext* context);
+int sift_batch_download(SiftContext* context, SiftBatchResult* out_result);
+
+/* ---- diagnostics -------------------------------------------------------------------------- */
+
+const char* sift_status_string(int status);
+const char* sift_last_error_string(const SiftContext* context);
+int sift_set_stage_timing(SiftContext* context, int32_t enabled);
+int sift_last_timings(const SiftContext* context, SiftTimings* out_timings);
+
+/* Debug taps into the pyramid of the last execute. `what`: */
+#define SIFT_PLANE_GRAY 0        /* luminosity, W×H            (slice, octave ignored)             */
+#define SIFT_PLANE_SEED 1        /* blurred 2× seed = octave 0 Gaussian slice 0                    */
+#define SIFT_PLANE_GAUSSIAN 2    /* slice 0…5 (needs SIFT_FLAG_KEEP_PYRAMID for slice 5)           */
+#define SIFT_PLANE_DOG 3         /* slice 0…4                                                      */
+#define SIFT_PLANE_GRADIENT 4    /* slice 1…3, interleaved (orientation, magnitude), 2 floats/px   */
+int sift_debug_download(SiftContext* context, int32_t what, int32_t frame, int32_t octave,
+                        int32_t slice, float* dst, int64_t dst_floats);
+
+/* Raw candidates (x, y, scale triples = SIFTExtremaResult, include/SIFTExtrema.h:14-18) of one
+ * frame and octave of the last execute, canonical order. Returns the count (or <0: -status). */
+int64_t sift_debug_candidates(SiftContext* context, int32_t frame, int32_t octave,
+                              int32_t* dst_xyz, int64_t dst_capacity_triples);
+
+/* Evaluates the engine's device math primitives on n inputs (parity tests against the oracle's
+ * restatement): op 0 expf(a) · 1 atan2f(a, b) · 2 sinf(a) · 3 cosf(a) · 4 exp2f(a). */
+int sift_debug_math(int device, int32_t op, const float* a, const float* b, float* out,
+                    int64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIFTCUDA_H */
