@@ -1,0 +1,734 @@
+// capi.cu — context lifetime, per-call orchestration and the extern "C" surface of
+// include/siftcuda.h. Host stages restated here (each cites the reference):
+//   DifferenceOfGaussians.init / Octave.init   (DifferenceOfGaussians.swift:233-344, :69-147)
+//   GaussianKernel / GaussianSeriesKernel taps (GaussianKernel.swift:20-43, GaussianSeriesKernel.swift:27-51)
+//   SIFT.getKeypoints / getDescriptors         (SIFT.swift:147-238)
+// One context = one device, one stream; every call is synchronous at return. There is no CPU
+// path: without a usable sm_100 device every compute entry point fails.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace sift;
+
+struct SiftContext {
+    SiftConfig cfg{};
+    int device = 0;
+    int smCount = 0;
+    cudaStream_t stream = nullptr;
+    SiftInfo info{};
+    EngineParams P{};
+    Taps seedTaps{};
+    int seedNtaps = 0;
+    Taps taps[kGaussians - 1]{};
+    int ntaps[kGaussians - 1]{};
+
+    int B = 1;       // max_batch
+    int nSegs = 0;   // B * 7
+    int capCand = 0, capKp = 0, capDesc = 0;  // totals over the batch
+
+    // device memory
+    std::vector<void*> allocations;
+    int64_t deviceBytes = 0;
+    uint8_t* dInput = nullptr;
+    float* dGray = nullptr;
+    float* dScaled = nullptr;
+    int pitch2 = 0;
+    uint32_t* dMask = nullptr;
+    int* dBlockSums = nullptr;
+    Candidate* dCands = nullptr;
+    SiftKeypoint* dKpTmp = nullptr;
+    uint32_t* dFlagWords = nullptr;
+    SiftKeypoint* dKps = nullptr;
+    int* dKpSeg = nullptr;
+    int* dSegStarts = nullptr;  // [3][nSegs + 1]: candidates, keypoints, descriptors
+    int* dNOri = nullptr;
+    float* dOriTmp = nullptr;
+    int* dOriOffset = nullptr;
+    SiftDescriptor* dDesc = nullptr;
+    Counters* dCounters = nullptr;
+
+    // pinned host memory
+    Counters* hCounters = nullptr;
+    int* hSegStarts = nullptr;
+    SiftKeypoint* hKps = nullptr;
+    SiftDescriptor* hDesc = nullptr;
+    int* hKpSeg = nullptr;
+    std::vector<int32_t> kpCounts, descCounts, candCounts;
+
+    // current input
+    const uint8_t* curInput = nullptr;
+    int curPitch = 0;
+    int64_t curFrameStride = 0;
+    int curFrames = 0;
+    bool executed = false;   // pyramid + gradients of curFrames frames are on the device
+    bool described = false;
+
+    // timing
+    bool stageTiming = true;
+    cudaEvent_t ev[SIFT_STAGE_COUNT + 1]{};
+    cudaEvent_t evBlur0[2]{};
+    SiftTimings timings{};
+    int launches = 0;
+
+    std::string lastError;
+};
+
+namespace {
+
+int fail(SiftContext* c, int status, const char* what, cudaError_t e = cudaSuccess) {
+    if (c) {
+        char buf[512];
+        if (e != cudaSuccess)
+            snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+        else
+            snprintf(buf, sizeof buf, "%s", what);
+        c->lastError = buf;
+    }
+    return status;
+}
+
+#define CTX_TRY(c, expr)                                                   \
+    do {                                                                   \
+        cudaError_t _e = (expr);                                           \
+        if (_e != cudaSuccess) return fail((c), SIFT_ERR_CUDA, #expr, _e); \
+    } while (0)
+
+// GaussianKernel.swift:20-43 ≡ GaussianSeriesKernel.swift:27-51 — host float arithmetic.
+int gaussianWeights(float s, float* out) {
+    const int radius = (int)ceilf(4 * s);
+    const int size = radius * 2 + 1;
+    if (size > kMaxTaps) return -1;
+    float t = 0;
+    const float ss = s * s;
+    for (int k = -radius; k <= radius; k++) {
+        const float kk = (float)(k * k);
+        const float w = expf(-0.5f * (kk / ss));
+        out[k + radius] = w;
+        t += w;
+    }
+    for (int i = 0; i < size; i++) out[i] = out[i] / t;
+    return size;
+}
+
+template <class T>
+cudaError_t devAlloc(SiftContext* c, T** p, size_t count) {
+    void* q = nullptr;
+    const size_t bytes = std::max<size_t>(count * sizeof(T), 256);
+    cudaError_t e = cudaMalloc(&q, bytes);
+    if (e != cudaSuccess) return e;
+    c->allocations.push_back(q);
+    c->deviceBytes += (int64_t)bytes;
+    *p = (T*)q;
+    return cudaSuccess;
+}
+
+void destroy(SiftContext* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (void* p : c->allocations) cudaFree(p);
+    if (c->hCounters) cudaFreeHost(c->hCounters);
+    if (c->hSegStarts) cudaFreeHost(c->hSegStarts);
+    if (c->hKps) cudaFreeHost(c->hKps);
+    if (c->hDesc) cudaFreeHost(c->hDesc);
+    if (c->hKpSeg) cudaFreeHost(c->hKpSeg);
+    for (auto& e : c->ev)
+        if (e) cudaEventDestroy(e);
+    for (auto& e : c->evBlur0)
+        if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sift_config_default(SiftConfig* cfg, int32_t width, int32_t height) {
+    if (!cfg) return SIFT_ERR_INVALID_ARGUMENT;
+    memset(cfg, 0, sizeof *cfg);
+    cfg->width = width;
+    cfg->height = height;
+    cfg->max_batch = 1;
+    cfg->dog_threshold = 0.0133f;
+    cfg->edge_threshold = 10.0f;
+    cfg->max_interpolation_iterations = 5;
+    cfg->max_offset = 0.6f;
+    cfg->image_border = 5;
+    cfg->lambda_orientation = 1.5f;
+    cfg->orientation_threshold = 0.8f;
+    cfg->orientation_smoothing_iterations = 6;
+    return SIFT_OK;
+}
+
+const char* sift_status_string(int status) {
+    switch (status) {
+        case SIFT_OK: return "ok";
+        case SIFT_ERR_INVALID_ARGUMENT: return "invalid argument";
+        case SIFT_ERR_NO_DEVICE: return "no usable sm_100 CUDA device";
+        case SIFT_ERR_CUDA: return "CUDA runtime error";
+        case SIFT_ERR_CAPACITY: return "device list capacity exceeded (results truncated)";
+        case SIFT_ERR_NOT_DETECTED: return "describe called before detect";
+        case SIFT_ERR_OUT_OF_MEMORY: return "out of device memory";
+        default: return "unknown status";
+    }
+}
+
+const char* sift_last_error_string(const SiftContext* c) { return c ? c->lastError.c_str() : ""; }
+
+int sift_create(const SiftConfig* cfg, int device, SiftContext** out) {
+    if (!cfg || !out) return SIFT_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (cfg->width < 8 || cfg->height < 8 || cfg->width > 16384 || cfg->height > 16384 ||
+        cfg->max_batch < 1)
+        return SIFT_ERR_INVALID_ARGUMENT;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count)
+        return SIFT_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SIFT_ERR_NO_DEVICE;
+    if (prop.major != 10) return SIFT_ERR_NO_DEVICE;  // the library carries sm_100a code only
+    if (cudaSetDevice(device) != cudaSuccess) return SIFT_ERR_NO_DEVICE;
+
+    SiftContext* c = new (std::nothrow) SiftContext();
+    if (!c) return SIFT_ERR_OUT_OF_MEMORY;
+    c->cfg = *cfg;
+    c->device = device;
+    c->smCount = prop.multiProcessorCount;
+    c->B = cfg->max_batch;
+    c->nSegs = c->B * kOctaves;
+    const int W = cfg->width, H = cfg->height;
+
+    // ---- schedule: DifferenceOfGaussians.init (:233-344) ------------------------------------
+    const float sigmaMinimum = 0.8f, deltaMinimum = 0.5f, sigmaInput = 0.5f;
+    SiftInfo& I = c->info;
+    I.width = W;
+    I.height = H;
+    I.max_batch = c->B;
+    I.sm_count = c->smCount;
+    {
+        const float i = sigmaMinimum * sigmaMinimum;
+        const float j = sigmaInput * sigmaInput;
+        I.seed_sigma = sqrtf(i - j) / deltaMinimum;
+        c->seedNtaps = gaussianWeights(I.seed_sigma, c->seedTaps.w);
+        I.seed_taps = c->seedNtaps;
+        memcpy(I.seed_weights, c->seedTaps.w, sizeof I.seed_weights);
+    }
+    int blockStart = 0;
+    for (int o = 0; o < kOctaves; o++) {
+        OctaveDev& q = c->P.oct[o];
+        q.delta = deltaMinimum * powf(2, (float)o);
+        q.w = (int)((float)W / q.delta);
+        q.h = (int)((float)H / q.delta);
+        q.pitch = (q.w + 31) / 32 * 32;
+        q.plane = (size_t)q.pitch * q.h;
+        for (int s = 0; s < kGaussians; s++) {
+            const float h = q.delta / deltaMinimum;
+            const float i = (float)s / (float)kScales;
+            const float j = powf(2, i);
+            q.sigmas[s] = (h * sigmaMinimum) * j;
+            I.sigmas[o][s] = q.sigmas[s];
+        }
+        q.log2SigmaRatio = log2f(q.sigmas[1] / q.sigmas[0]);  // SIFTOctave.swift:211
+        q.maskRowWords = (q.w + 31) / 32;
+        q.maskWords = kScales * q.h * q.maskRowWords;
+        q.maskBlocks = (q.maskWords + kScanChunk - 1) / kScanChunk;
+        q.maskBlockStart = blockStart;
+        blockStart += q.maskBlocks;
+        I.octave_width[o] = q.w;
+        I.octave_height[o] = q.h;
+        I.octave_pitch[o] = q.pitch;
+        I.octave_delta[o] = q.delta;
+    }
+    c->P.blocksPerFrame = blockStart;
+    for (int s = 1; s < kGaussians; s++) {
+        // Octave.init (:91-110): rho is identical for every octave; octave 0's values are used
+        const float sa = c->P.oct[0].sigmas[s - 1], sb = c->P.oct[0].sigmas[s];
+        const float rho = sqrtf((sb * sb) - (sa * sa)) / c->P.oct[0].delta;
+        I.rho[s - 1] = rho;
+        c->ntaps[s - 1] = gaussianWeights(rho, c->taps[s - 1].w);
+        I.taps[s - 1] = c->ntaps[s - 1];
+        memcpy(I.weights[s - 1], c->taps[s - 1].w, sizeof I.weights[s - 1]);
+    }
+    if (c->seedNtaps != 11 || c->ntaps[0] != 11 || c->ntaps[1] != 15 || c->ntaps[2] != 17 ||
+        c->ntaps[3] != 21 || c->ntaps[4] != 27) {
+        delete c;
+        return SIFT_ERR_INVALID_ARGUMENT;  // blur kernels are instantiated for the fixed schedule
+    }
+    c->P.dogThreshold = cfg->dog_threshold;
+    c->P.edgeThreshold = cfg->edge_threshold;
+    c->P.maxOffset = cfg->max_offset;
+    c->P.maxIterations = cfg->max_interpolation_iterations;
+    c->P.border = cfg->image_border;
+    c->P.lambdaOri = cfg->lambda_orientation;
+    c->P.oriThreshold = cfg->orientation_threshold;
+    c->P.oriSmoothIterations = cfg->orientation_smoothing_iterations;
+
+    // ---- capacities -------------------------------------------------------------------------
+    const double N = (double)W * H;
+    auto cap = [&](int32_t given, double perPixel, int floor_) -> int {
+        const double perFrame = given > 0 ? (double)given : std::max((double)floor_, N * perPixel);
+        const double total = perFrame * c->B;
+        return (int)std::min(total, 1.0e9);
+    };
+    c->capCand = cap(cfg->max_candidates_per_frame, 0.08, 16384);
+    c->capKp = cap(cfg->max_keypoints_per_frame, 0.04, 8192);
+    c->capDesc = cap(cfg->max_descriptors_per_frame, 0.06, 8192);
+    I.max_candidates_per_frame = c->capCand / c->B;
+    I.max_keypoints_per_frame = c->capKp / c->B;
+    I.max_descriptors_per_frame = c->capDesc / c->B;
+
+    // ---- allocation (all at create, as SIFT.init; nothing is allocated per frame) -----------
+    cudaError_t e = cudaSuccess;
+    auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    A(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    const size_t B = (size_t)c->B;
+    A(devAlloc(c, &c->dInput, B * (size_t)W * H * 4));
+    A(devAlloc(c, &c->dGray, B * (size_t)W * H));
+    c->pitch2 = c->P.oct[0].pitch;
+    A(devAlloc(c, &c->dScaled, B * c->P.oct[0].plane));
+    for (int o = 0; o < kOctaves; o++) {
+        OctaveDev& q = c->P.oct[o];
+        A(devAlloc(c, &q.G, B * kGaussians * q.plane));
+        A(devAlloc(c, &q.D, B * kDogs * q.plane));
+        A(devAlloc(c, &q.grad, B * kScales * q.plane));
+    }
+    const size_t maskWords = B * (size_t)c->P.blocksPerFrame * kScanChunk;
+    A(devAlloc(c, &c->dMask, maskWords));
+    const size_t flagWords = ((size_t)c->capCand / 32 / kScanChunk + 2) * kScanChunk;
+    const size_t nBlockSums = std::max({B * (size_t)c->P.blocksPerFrame, flagWords / kScanChunk + 1,
+                                        (size_t)c->capKp / kScanChunk + 2}) + 16;
+    A(devAlloc(c, &c->dBlockSums, nBlockSums));
+    A(devAlloc(c, &c->dCands, (size_t)c->capCand));
+    A(devAlloc(c, &c->dKpTmp, (size_t)c->capCand));
+    A(devAlloc(c, &c->dFlagWords, flagWords));
+    A(devAlloc(c, &c->dKps, (size_t)c->capKp));
+    A(devAlloc(c, &c->dKpSeg, (size_t)c->capKp));
+    A(devAlloc(c, &c->dSegStarts, 3 * (size_t)(c->nSegs + 1)));
+    A(devAlloc(c, &c->dNOri, (size_t)c->capKp + kScanChunk));
+    A(devAlloc(c, &c->dOriTmp, (size_t)c->capKp * kOriBins));
+    A(devAlloc(c, &c->dOriOffset, (size_t)c->capKp + kScanChunk + 1));
+    A(devAlloc(c, &c->dDesc, (size_t)c->capDesc));
+    A(devAlloc(c, &c->dCounters, 1));
+    if (e == cudaSuccess) A(cudaMemset(c->dMask, 0, maskWords * sizeof(uint32_t)));
+    if (e == cudaSuccess) A(cudaMemset(c->dSegStarts, 0, 3 * (size_t)(c->nSegs + 1) * sizeof(int)));
+    A(cudaMallocHost(&c->hCounters, sizeof(Counters)));
+    A(cudaMallocHost(&c->hSegStarts, 3 * (size_t)(c->nSegs + 1) * sizeof(int)));
+    A(cudaMallocHost(&c->hKps, std::max<size_t>((size_t)c->capKp * sizeof(SiftKeypoint), 64)));
+    A(cudaMallocHost(&c->hDesc, std::max<size_t>((size_t)c->capDesc * sizeof(SiftDescriptor), 64)));
+    A(cudaMallocHost(&c->hKpSeg, std::max<size_t>((size_t)c->capKp * sizeof(int), 64)));
+    for (auto& evn : c->ev) A(cudaEventCreate(&evn));
+    for (auto& evn : c->evBlur0) A(cudaEventCreate(&evn));
+    if (e != cudaSuccess) {
+        const bool oom = (e == cudaErrorMemoryAllocation);
+        destroy(c);
+        cudaGetLastError();
+        return oom ? SIFT_ERR_OUT_OF_MEMORY : SIFT_ERR_CUDA;
+    }
+    c->kpCounts.assign(c->nSegs, 0);
+    c->descCounts.assign(c->nSegs, 0);
+    c->candCounts.assign(c->nSegs, 0);
+    I.device_bytes = c->deviceBytes;
+    *out = c;
+    return SIFT_OK;
+}
+
+void sift_destroy(SiftContext* c) { destroy(c); }
+
+int sift_get_info(const SiftContext* c, SiftInfo* out) {
+    if (!c || !out) return SIFT_ERR_INVALID_ARGUMENT;
+    *out = c->info;
+    return SIFT_OK;
+}
+
+int sift_set_stage_timing(SiftContext* c, int32_t enabled) {
+    if (!c) return SIFT_ERR_INVALID_ARGUMENT;
+    c->stageTiming = enabled != 0;
+    return SIFT_OK;
+}
+
+int sift_last_timings(const SiftContext* c, SiftTimings* out) {
+    if (!c || !out) return SIFT_ERR_INVALID_ARGUMENT;
+    *out = c->timings;
+    return SIFT_OK;
+}
+
+int sift_batch_upload(SiftContext* c, const void* const* images, int32_t n, int32_t pitchBytes) {
+    if (!c || !images || n < 1 || n > c->B || pitchBytes < c->cfg.width * 4)
+        return fail(c, SIFT_ERR_INVALID_ARGUMENT, "sift_batch_upload: bad arguments");
+    CTX_TRY(c, cudaSetDevice(c->device));
+    const size_t rowBytes = (size_t)c->cfg.width * 4;
+    const size_t frameBytes = rowBytes * c->cfg.height;
+    for (int f = 0; f < n; f++) {
+        if (!images[f]) return fail(c, SIFT_ERR_INVALID_ARGUMENT, "sift_batch_upload: null image");
+        CTX_TRY(c, cudaMemcpy2DAsync(c->dInput + f * frameBytes, rowBytes, images[f], pitchBytes,
+                                     rowBytes, c->cfg.height, cudaMemcpyHostToDevice, c->stream));
+    }
+    c->curInput = c->dInput;
+    c->curPitch = (int)rowBytes;
+    c->curFrameStride = (int64_t)frameBytes;
+    c->curFrames = n;
+    c->executed = false;
+    return SIFT_OK;
+}
+
+int sift_batch_set_device_input(SiftContext* c, const void* dev, int32_t n, int32_t pitchBytes,
+                                int64_t frameStrideBytes) {
+    if (!c || !dev || n < 1 || n > c->B || pitchBytes < c->cfg.width * 4 ||
+        (n > 1 && frameStrideBytes < (int64_t)pitchBytes * c->cfg.height) || (pitchBytes & 3) ||
+        (frameStrideBytes & 3) || ((uintptr_t)dev & 3))
+        return fail(c, SIFT_ERR_INVALID_ARGUMENT, "sift_batch_set_device_input: bad arguments");
+    c->curInput = (const uint8_t*)dev;
+    c->curPitch = pitchBytes;
+    c->curFrameStride = frameStrideBytes;
+    c->curFrames = n;
+    c->executed = false;
+    return SIFT_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+// findKeypoints + getKeypointsFromOctaves + interpolateKeypoints (SIFT.swift:154-202), all
+// frames of the batch at once, no host synchronisation inside.
+int runDetect(SiftContext* c) {
+    const int F = c->curFrames;
+    cudaStream_t st = c->stream;
+    const bool T = c->stageTiming;
+    c->launches = 0;
+    CTX_TRY(c, cudaMemsetAsync(c->dCounters, 0, sizeof(Counters), st));
+    if (T) CTX_TRY(c, cudaEventRecord(c->ev[0], st));
+    // DifferenceOfGaussians.encodeSeedTexture (:357-389)
+    const OctaveDev& o0 = c->P.oct[0];
+    CTX_TRY(c, launchGrayUpsample(c->curInput, c->curPitch, c->curFrameStride, c->dGray,
+                                  c->cfg.width, c->cfg.height, c->dScaled, o0.w, o0.h, o0.pitch,
+                                  o0.plane, F, st));
+    {
+        BlurArgs a{};
+        a.in = c->dScaled;
+        a.out = o0.G;  // octave 0 slice 0 (the reference blits seed → slice 0, :176-188)
+        a.w = o0.w; a.h = o0.h; a.pitch = o0.pitch;
+        a.inFrameStride = o0.plane;
+        a.outFrameStride = kGaussians * o0.plane;
+        a.frames = F;
+        CTX_TRY(c, launchBlur(a, c->seedTaps, c->seedNtaps, st));
+    }
+    c->launches += 2;
+    if (T) CTX_TRY(c, cudaEventRecord(c->ev[1], st));
+    // encodeOctaves (:391-406): Gaussian series + DoG; octave o+1 slice 0 = octave o slice 3
+    // decimated (fused into the blur that produces slice 3); SIFTOctave.encodeGradients (:190-196)
+    for (int o = 0; o < kOctaves; o++) {
+        const OctaveDev& q = c->P.oct[o];
+        if (q.w < 1 || q.h < 1) continue;
+        if (T && o == 0) CTX_TRY(c, cudaEventRecord(c->evBlur0[0], st));
+        for (int s = 0; s < kGaussians - 1; s++) {
+            BlurArgs a{};
+            a.in = q.G + (size_t)s * q.plane;
+            a.out = q.G + (size_t)(s + 1) * q.plane;
+            a.dog = q.D + (size_t)s * q.plane;
+            a.w = q.w; a.h = q.h; a.pitch = q.pitch;
+            a.inFrameStride = a.outFrameStride = kGaussians * q.plane;
+            a.dogFrameStride = kDogs * q.plane;
+            if (s + 1 == kScales && o + 1 < kOctaves && c->P.oct[o + 1].w >= 1 && c->P.oct[o + 1].h >= 1) {
+                const OctaveDev& nx = c->P.oct[o + 1];
+                a.half = nx.G;
+                a.halfW = nx.w; a.halfH = nx.h; a.halfPitch = nx.pitch;
+                a.halfFrameStride = kGaussians * nx.plane;
+            }
+            a.frames = F;
+            CTX_TRY(c, launchBlur(a, c->taps[s], c->ntaps[s], st));
+            c->launches++;
+        }
+        if (T && o == 0) CTX_TRY(c, cudaEventRecord(c->evBlur0[1], st));
+        CTX_TRY(c, launchGradient(q, F, st));
+        c->launches++;
+    }
+    if (T) CTX_TRY(c, cudaEventRecord(c->ev[2], st));
+    // SIFTOctave.encodeExtrema (:183-189) + getKeypoints (:198-203)
+    for (int o = 0; o < kOctaves; o++) {
+        if (c->P.oct[o].w < 3 || c->P.oct[o].h < 3) continue;
+        CTX_TRY(c, launchExtremaMask(c->P, o, c->dMask, F, st));
+        c->launches++;
+    }
+    CTX_TRY(c, launchCandidateCompaction(c->P, c->dMask, c->dBlockSums, c->dCands, c->capCand,
+                                         nullptr, c->dCounters, F, st));
+    CTX_TRY(c, launchCandidateSegmentStarts(c->dCands, &c->dCounters->nCandidates, c->dSegStarts,
+                                            F * kOctaves, st));
+    c->launches += 4;
+    if (T) CTX_TRY(c, cudaEventRecord(c->ev[3], st));
+    // interpolateKeypoints (SIFTOctave.swift:205-288)
+    CTX_TRY(c, launchRefine(c->P, c->dCands, c->capCand, c->dKpTmp, c->dFlagWords, c->dBlockSums,
+                            c->dKps, c->dKpSeg, c->capKp, nullptr,
+                            c->dSegStarts + (c->nSegs + 1), F * kOctaves, c->dCounters,
+                            c->smCount, st));
+    c->launches += 5;
+    if (T) CTX_TRY(c, cudaEventRecord(c->ev[4], st));
+    c->executed = true;
+    c->described = false;
+    return SIFT_OK;
+}
+
+// getDescriptors (SIFT.swift:207-238) over the keypoints currently in dKps.
+int runDescribe(SiftContext* c, int nSegs) {
+    cudaStream_t st = c->stream;
+    const bool T = c->stageTiming;
+    CTX_TRY(c, launchDescribe(c->P, c->dKps, c->dKpSeg, c->capKp, c->dSegStarts + (c->nSegs + 1),
+                              c->dNOri, c->dOriTmp, c->dOriOffset, c->dBlockSums, c->dDesc,
+                              c->capDesc, c->dSegStarts + 2 * (c->nSegs + 1), nSegs, c->dCounters,
+                              c->smCount, st, T ? c->ev[5] : nullptr));
+    c->launches += 6;
+    if (T) CTX_TRY(c, cudaEventRecord(c->ev[6], st));
+    c->described = true;
+    return SIFT_OK;
+}
+
+// D2H of the small bookkeeping block, stream drain, timing read-out, overflow check.
+int finish(SiftContext* c, bool withDescribe) {
+    cudaStream_t st = c->stream;
+    CTX_TRY(c, cudaMemcpyAsync(c->hCounters, c->dCounters, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    CTX_TRY(c, cudaMemcpyAsync(c->hSegStarts, c->dSegStarts, 3 * (size_t)(c->nSegs + 1) * sizeof(int),
+                               cudaMemcpyDeviceToHost, st));
+    CTX_TRY(c, cudaStreamSynchronize(st));
+    const int nSegs = c->curFrames * kOctaves;
+    const int* candStart = c->hSegStarts;
+    const int* kpStart = c->hSegStarts + (c->nSegs + 1);
+    const int* descStart = c->hSegStarts + 2 * (c->nSegs + 1);
+    const int nDesc = c->hCounters->nDescriptors;
+    for (int s = 0; s < nSegs; s++) {
+        c->candCounts[s] = candStart[s + 1] - candStart[s];
+        c->kpCounts[s] = kpStart[s + 1] - kpStart[s];
+        c->descCounts[s] = withDescribe ? std::min(descStart[s + 1], nDesc) - std::min(descStart[s], nDesc) : 0;
+    }
+    SiftTimings& t = c->timings;
+    memset(&t, 0, sizeof t);
+    t.kernel_launches = c->launches;
+    t.stage_timing_enabled = c->stageTiming;
+    if (c->stageTiming) {
+        const int last = withDescribe ? SIFT_STAGE_COUNT : 4;
+        for (int i = 0; i < last; i++) cudaEventElapsedTime(&t.stage_ms[i], c->ev[i], c->ev[i + 1]);
+        cudaEventElapsedTime(&t.total_ms, c->ev[0], c->ev[last]);
+        cudaEventElapsedTime(&t.blur_octave0_ms, c->evBlur0[0], c->evBlur0[1]);
+        t.blur_octave0_launches = kGaussians - 1;
+    }
+    if (c->hCounters->overflow) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "list capacity exceeded (mask %d: 1 candidates, 2 keypoints, 4 descriptors)",
+                 c->hCounters->overflow);
+        return fail(c, SIFT_ERR_CAPACITY, buf);
+    }
+    return SIFT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sift_batch_execute(SiftContext* c) {
+    if (!c) return SIFT_ERR_INVALID_ARGUMENT;
+    if (!c->curInput || c->curFrames < 1) return fail(c, SIFT_ERR_INVALID_ARGUMENT, "no input set");
+    CTX_TRY(c, cudaSetDevice(c->device));
+    int r = runDetect(c);
+    if (r != SIFT_OK) return r;
+    r = runDescribe(c, c->curFrames * kOctaves);
+    if (r != SIFT_OK) return r;
+    return finish(c, true);
+}
+
+int sift_batch_download(SiftContext* c, SiftBatchResult* out) {
+    if (!c || !out) return SIFT_ERR_INVALID_ARGUMENT;
+    if (!c->executed) return fail(c, SIFT_ERR_NOT_DETECTED, "download before execute");
+    CTX_TRY(c, cudaSetDevice(c->device));
+    const int64_t nKp = std::min(c->hCounters->nKeypoints, c->capKp);
+    const int64_t nDesc = c->described ? std::min(c->hCounters->nDescriptors, c->capDesc) : 0;
+    if (nKp > 0)
+        CTX_TRY(c, cudaMemcpyAsync(c->hKps, c->dKps, (size_t)nKp * sizeof(SiftKeypoint),
+                                   cudaMemcpyDeviceToHost, c->stream));
+    if (nDesc > 0)
+        CTX_TRY(c, cudaMemcpyAsync(c->hDesc, c->dDesc, (size_t)nDesc * sizeof(SiftDescriptor),
+                                   cudaMemcpyDeviceToHost, c->stream));
+    CTX_TRY(c, cudaStreamSynchronize(c->stream));
+    out->n_frames = c->curFrames;
+    out->keypoint_counts = c->kpCounts.data();
+    out->descriptor_counts = c->descCounts.data();
+    out->candidate_counts = c->candCounts.data();
+    out->keypoints = c->hKps;
+    out->descriptors = c->hDesc;
+    out->total_keypoints = nKp;
+    out->total_descriptors = nDesc;
+    return SIFT_OK;
+}
+
+int sift_detect_and_describe_batch(SiftContext* c, const void* const* images, int32_t n,
+                                   int32_t pitchBytes, SiftBatchResult* out) {
+    int r = sift_batch_upload(c, images, n, pitchBytes);
+    if (r != SIFT_OK) return r;
+    const int re = sift_batch_execute(c);
+    if (re != SIFT_OK && re != SIFT_ERR_CAPACITY) return re;
+    r = sift_batch_download(c, out);
+    return r != SIFT_OK ? r : re;
+}
+
+int sift_detect(SiftContext* c, const void* bgra8, int32_t pitchBytes,
+                const SiftKeypoint** outKps, int32_t counts[SIFT_NUM_OCTAVES]) {
+    if (!c || !bgra8 || !outKps || !counts) return SIFT_ERR_INVALID_ARGUMENT;
+    const void* imgs[1] = {bgra8};
+    int r = sift_batch_upload(c, imgs, 1, pitchBytes);
+    if (r != SIFT_OK) return r;
+    r = runDetect(c);
+    if (r != SIFT_OK) return r;
+    const int re = finish(c, false);
+    if (re != SIFT_OK && re != SIFT_ERR_CAPACITY) return re;
+    SiftBatchResult res;
+    r = sift_batch_download(c, &res);
+    if (r != SIFT_OK) return r;
+    *outKps = res.keypoints;
+    for (int o = 0; o < kOctaves; o++) counts[o] = res.keypoint_counts[o];
+    return re;
+}
+
+int sift_describe(SiftContext* c, const SiftKeypoint* kps, const int32_t counts[SIFT_NUM_OCTAVES],
+                  const SiftDescriptor** outDesc, int32_t descCounts[SIFT_NUM_OCTAVES]) {
+    if (!c || !counts || !outDesc || !descCounts) return SIFT_ERR_INVALID_ARGUMENT;
+    if (!c->executed) return fail(c, SIFT_ERR_NOT_DETECTED, "sift_describe before sift_detect");
+    CTX_TRY(c, cudaSetDevice(c->device));
+    int64_t n = 0;
+    for (int o = 0; o < kOctaves; o++) {
+        if (counts[o] < 0) return fail(c, SIFT_ERR_INVALID_ARGUMENT, "negative count");
+        n += counts[o];
+    }
+    if (n > c->capKp) return fail(c, SIFT_ERR_CAPACITY, "more keypoints than max_keypoints_per_frame");
+    if (n > 0 && !kps) return SIFT_ERR_INVALID_ARGUMENT;
+    // keypoints may alias our own pinned result buffer (the usual detect → describe flow)
+    if (n > 0 && kps != c->hKps) memcpy(c->hKps, kps, (size_t)n * sizeof(SiftKeypoint));
+    int* kpStart = c->hSegStarts + (c->nSegs + 1);
+    int k = 0;
+    for (int o = 0; o < kOctaves; o++) {
+        kpStart[o] = k;
+        for (int i = 0; i < counts[o]; i++) {
+            if (c->hKps[k].octave != o) return fail(c, SIFT_ERR_INVALID_ARGUMENT, "keypoint octave does not match its group");
+            c->hKpSeg[k++] = o;
+        }
+    }
+    for (int s = kOctaves; s <= c->nSegs; s++) kpStart[s] = k;
+    cudaStream_t st = c->stream;
+    c->hCounters->nKeypoints = (int)n;
+    c->hCounters->nDescriptors = 0;
+    c->hCounters->overflow = 0;
+    CTX_TRY(c, cudaMemcpyAsync(c->dCounters, c->hCounters, sizeof(Counters), cudaMemcpyHostToDevice, st));
+    if (n > 0) {
+        CTX_TRY(c, cudaMemcpyAsync(c->dKps, c->hKps, (size_t)n * sizeof(SiftKeypoint), cudaMemcpyHostToDevice, st));
+        CTX_TRY(c, cudaMemcpyAsync(c->dKpSeg, c->hKpSeg, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
+    }
+    CTX_TRY(c, cudaMemcpyAsync(c->dSegStarts + (c->nSegs + 1), kpStart, (size_t)(c->nSegs + 1) * sizeof(int),
+                               cudaMemcpyHostToDevice, st));
+    const bool T = c->stageTiming;
+    c->launches = 0;
+    if (T) CTX_TRY(c, cudaEventRecord(c->ev[4], st));
+    const int savedFrames = c->curFrames;
+    c->curFrames = 1;
+    int r = runDescribe(c, kOctaves);
+    if (r != SIFT_OK) { c->curFrames = savedFrames; return r; }
+    // bookkeeping without touching the detect-stage events
+    const bool savedT = c->stageTiming;
+    c->stageTiming = false;
+    const int re = finish(c, true);
+    c->stageTiming = savedT;
+    if (T) {
+        cudaEventElapsedTime(&c->timings.stage_ms[4], c->ev[4], c->ev[5]);
+        cudaEventElapsedTime(&c->timings.stage_ms[5], c->ev[5], c->ev[6]);
+        cudaEventElapsedTime(&c->timings.total_ms, c->ev[4], c->ev[6]);
+    }
+    if (re != SIFT_OK && re != SIFT_ERR_CAPACITY) { c->curFrames = savedFrames; return re; }
+    SiftBatchResult res;
+    r = sift_batch_download(c, &res);
+    c->curFrames = savedFrames;
+    if (r != SIFT_OK) return r;
+    *outDesc = res.descriptors;
+    for (int o = 0; o < kOctaves; o++) descCounts[o] = res.descriptor_counts[o];
+    return re;
+}
+
+int sift_debug_download(SiftContext* c, int32_t what, int32_t frame, int32_t octave, int32_t slice,
+                        float* dst, int64_t dstFloats) {
+    if (!c || !dst) return SIFT_ERR_INVALID_ARGUMENT;
+    if (!c->executed) return fail(c, SIFT_ERR_NOT_DETECTED, "debug download before execute");
+    if (frame < 0 || frame >= c->curFrames) return fail(c, SIFT_ERR_INVALID_ARGUMENT, "bad frame");
+    CTX_TRY(c, cudaSetDevice(c->device));
+    CTX_TRY(c, cudaStreamSynchronize(c->stream));
+    const float* src = nullptr;
+    int w = 0, h = 0, pitch = 0, comps = 1;
+    if (what == SIFT_PLANE_GRAY) {
+        w = pitch = c->cfg.width; h = c->cfg.height;
+        src = c->dGray + (size_t)frame * w * h;
+    } else {
+        if (what == SIFT_PLANE_SEED) { octave = 0; slice = 0; what = SIFT_PLANE_GAUSSIAN; }
+        if (octave < 0 || octave >= kOctaves) return fail(c, SIFT_ERR_INVALID_ARGUMENT, "bad octave");
+        const OctaveDev& q = c->P.oct[octave];
+        w = q.w; h = q.h; pitch = q.pitch;
+        if (what == SIFT_PLANE_GAUSSIAN && slice >= 0 && slice < kGaussians)
+            src = q.G + ((size_t)frame * kGaussians + slice) * q.plane;
+        else if (what == SIFT_PLANE_DOG && slice >= 0 && slice < kDogs)
+            src = q.D + ((size_t)frame * kDogs + slice) * q.plane;
+        else if (what == SIFT_PLANE_GRADIENT && slice >= 1 && slice <= kScales) {
+            src = (const float*)(q.grad + ((size_t)frame * kScales + (slice - 1)) * q.plane);
+            comps = 2;
+        } else
+            return fail(c, SIFT_ERR_INVALID_ARGUMENT, "bad plane / slice");
+    }
+    if (dstFloats < (int64_t)w * h * comps) return fail(c, SIFT_ERR_INVALID_ARGUMENT, "dst too small");
+    if (w > 0 && h > 0)
+        CTX_TRY(c, cudaMemcpy2D(dst, (size_t)w * comps * 4, src, (size_t)pitch * comps * 4,
+                                (size_t)w * comps * 4, h, cudaMemcpyDeviceToHost));
+    return SIFT_OK;
+}
+
+int64_t sift_debug_candidates(SiftContext* c, int32_t frame, int32_t octave, int32_t* dst,
+                              int64_t capTriples) {
+    if (!c || !c->executed || frame < 0 || frame >= c->curFrames || octave < 0 || octave >= kOctaves)
+        return -(int64_t)SIFT_ERR_INVALID_ARGUMENT;
+    if (cudaSetDevice(c->device) != cudaSuccess) return -(int64_t)SIFT_ERR_CUDA;
+    const int seg = frame * kOctaves + octave;
+    const int nAll = std::min(c->hCounters->nCandidates, c->capCand);
+    const int a = std::min(c->hSegStarts[seg], nAll), b = std::min(c->hSegStarts[seg + 1], nAll);
+    const int n = b - a;
+    if (!dst || n <= 0) return n;
+    std::vector<Candidate> tmp((size_t)n);
+    if (cudaMemcpy(tmp.data(), c->dCands + a, (size_t)n * sizeof(Candidate), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return -(int64_t)SIFT_ERR_CUDA;
+    for (int i = 0; i < n && i < capTriples; i++) {
+        dst[3 * i + 0] = (int32_t)(tmp[i].xys & 0x7fff);
+        dst[3 * i + 1] = (int32_t)((tmp[i].xys >> 15) & 0x7fff);
+        dst[3 * i + 2] = (int32_t)(tmp[i].xys >> 30);
+    }
+    return n;
+}
+
+int sift_debug_math(int device, int32_t op, const float* a, const float* b, float* out, int64_t n) {
+    if (!a || !out || n < 0) return SIFT_ERR_INVALID_ARGUMENT;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return SIFT_ERR_NO_DEVICE;
+    if (cudaSetDevice(device) != cudaSuccess) return SIFT_ERR_NO_DEVICE;
+    if (n == 0) return SIFT_OK;
+    float *da = nullptr, *db = nullptr, *dout = nullptr;
+    cudaError_t e = cudaMalloc(&da, n * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&db, n * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&dout, n * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(da, a, n * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = b ? cudaMemcpy(db, b, n * sizeof(float), cudaMemcpyHostToDevice)
+                                : cudaMemset(db, 0, n * sizeof(float));
+    if (e == cudaSuccess) e = launchMathDebug(op, da, db, dout, n, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(out, dout, n * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(da); cudaFree(db); cudaFree(dout);
+    return e == cudaSuccess ? SIFT_OK : SIFT_ERR_CUDA;
+}
+
+}  // extern "C"

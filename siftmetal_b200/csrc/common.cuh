@@ -1,0 +1,127 @@
+// common.cuh — shared declarations of the sm_100a SIFT engine (libsiftcuda.so).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/siftcuda.h"
+
+namespace sift {
+
+constexpr int kOctaves = SIFT_NUM_OCTAVES;
+constexpr int kScales = SIFT_SCALES_PER_OCTAVE;
+constexpr int kGaussians = SIFT_NUM_GAUSSIANS;
+constexpr int kDogs = SIFT_NUM_DOGS;
+constexpr int kOriBins = SIFT_ORIENTATION_HISTOGRAM_BINS;
+constexpr int kMaxTaps = SIFT_CONVOLUTION_WEIGHTS_LENGTH;
+
+// Scan granularity: one CTA of 256 threads owns 2048 consecutive items (8 per thread).
+constexpr int kScanThreads = 256;
+constexpr int kScanItemsPerThread = 8;
+constexpr int kScanChunk = kScanThreads * kScanItemsPerThread;
+
+struct Taps {
+    float w[kMaxTaps];
+};
+
+// Geometry + device planes of one octave. Planes are pitched linear float arrays laid out
+// [frame][slice][y][x]; `pitch` is in floats and a multiple of 32 (128-byte rows).
+struct OctaveDev {
+    int w, h, pitch;
+    float delta;
+    float sigmas[kGaussians];
+    float log2SigmaRatio;
+    float* G;          // [frame][6][h][pitch]
+    float* D;          // [frame][5][h][pitch]
+    float2* grad;      // [frame][3][h][pitch]  slices 1..3 (orientation, magnitude)
+    size_t plane;      // pitch * h
+    // extrema bitmask: [frame][3][h][maskRowWords] inside the global mask array
+    int maskRowWords;  // ceil(w / 32)
+    int maskWords;     // 3 * h * maskRowWords
+    int maskBlocks;    // ceil(maskWords / kScanChunk)
+    int maskBlockStart;  // first scan block of this octave inside a frame
+};
+
+struct EngineParams {
+    OctaveDev oct[kOctaves];
+    int blocksPerFrame;        // scan blocks of one frame's masks (all octaves)
+    float dogThreshold, edgeThreshold, maxOffset;
+    int maxIterations, border;
+    float lambdaOri, oriThreshold;
+    int oriSmoothIterations;
+};
+
+// Candidate = SIFTExtremaResult (include/SIFTExtrema.h:14-18) packed: x | y << 15 | s << 30,
+// plus the (frame, octave) segment it belongs to.
+struct Candidate {
+    uint32_t xys;
+    int32_t seg;  // frame * 7 + octave
+};
+__host__ __device__ inline uint32_t packXYS(int x, int y, int s) {
+    return (uint32_t)x | ((uint32_t)y << 15) | ((uint32_t)s << 30);
+}
+
+// Device-side counters of one execute (zeroed at its start).
+struct Counters {
+    int nCandidates;
+    int nKeypoints;
+    int nDescriptors;
+    int overflow;  // bit 0 candidates, bit 1 keypoints, bit 2 descriptors
+};
+
+#define SIFT_CUDA_TRY(expr)                                  \
+    do {                                                     \
+        cudaError_t _e = (expr);                             \
+        if (_e != cudaSuccess) return _e;                    \
+    } while (0)
+
+// ---- launchers (each returns cudaGetLastError of its launches) ---------------------------------
+
+// pyramid.cu
+cudaError_t launchGrayUpsample(const uint8_t* bgra, int pitchBytes, int64_t frameStrideBytes,
+                               float* gray, int W, int H, float* scaled, int w2, int h2,
+                               int pitch2, size_t scaledFrameStride, int frames,
+                               cudaStream_t st);
+// out = blur(in); optional dog = out - in; optional decimated copy of out (every other pixel)
+struct BlurArgs {
+    const float* in;
+    float* out;
+    float* dog;      // may be null
+    float* half;     // may be null: next octave's slice 0, receives out[2y][2x]
+    int w, h, pitch;
+    size_t inFrameStride, outFrameStride, dogFrameStride;
+    int halfW, halfH, halfPitch;
+    size_t halfFrameStride;
+    int frames;
+};
+cudaError_t launchBlur(const BlurArgs& a, const Taps& taps, int ntaps, cudaStream_t st);
+cudaError_t launchGradient(const OctaveDev& o, int frames, cudaStream_t st);
+
+// detect.cu
+cudaError_t launchExtremaMask(const EngineParams& P, int octave, uint32_t* mask, int frames,
+                              cudaStream_t st);
+cudaError_t launchCandidateCompaction(const EngineParams& P, const uint32_t* mask,
+                                      int* blockSums, Candidate* cands, int capCandidates,
+                                      int* segCandCount, Counters* counters, int frames,
+                                      cudaStream_t st);
+cudaError_t launchSegmentStarts(const int* kpSeg, const int* nPtr, int* segStart, int nSegs,
+                                cudaStream_t st);
+cudaError_t launchCandidateSegmentStarts(const Candidate* cands, const int* nPtr, int* segStart,
+                                         int nSegs, cudaStream_t st);
+cudaError_t launchRefine(const EngineParams& P, const Candidate* cands, int capCandidates,
+                         SiftKeypoint* kpTmp, uint32_t* flagWords, int* blockSums,
+                         SiftKeypoint* kps, int* kpSeg, int capKeypoints, int* segKpCount,
+                         int* segKpStart, int nSegs, Counters* counters, int smCount,
+                         cudaStream_t st);
+
+// describe.cu
+cudaError_t launchDescribe(const EngineParams& P, const SiftKeypoint* kps, const int* kpSeg,
+                           int capKeypoints, const int* segKpStart, int* nOri, float* oriTmp,
+                           int* oriOffset, int* blockSums, SiftDescriptor* desc,
+                           int capDescriptors, int* segDescStart, int nSegs, Counters* counters,
+                           int smCount, cudaStream_t stream, cudaEvent_t afterOrientation);
+
+// math debug (capi.cu → describe.cu)
+cudaError_t launchMathDebug(int op, const float* a, const float* b, float* out, int64_t n,
+                            cudaStream_t st);
+
+}  // namespace sift

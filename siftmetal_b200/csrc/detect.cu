@@ -1,0 +1,466 @@
+// detect.cu — 3x3x3 extremum detection with the contrast pre-threshold, deterministic
+// compaction, sub-pixel refinement with contrast / edge rejection. Compiled with -fmad=false:
+// every float expression is evaluated exactly as written (arithmetic spec).
+//
+// Replaces, with identical arithmetic:
+//   SIFTExtrema.metal:62-110 siftExtremaList (+ SIFTExtremaListKernel.swift:37-69)  → extremaMaskKernel
+//   SIFTOctave.getKeypoints (SIFTOctave.swift:198-203)                              → scan + scatter
+//   SIFTInterpolate.metal:17-300 siftInterpolate and helpers, Common.hpp:34-47 invert,
+//   SIFTOctave.interpolateKeypoints (SIFTOctave.swift:205-288)                      → refineKernel
+#include "common.cuh"
+#include "dev_math.cuh"
+#include "scan.cuh"
+
+namespace sift {
+
+// ------------------------------------------------------------------------------------------
+// Extrema → bitmask. One thread per (x, y); a warp covers 32 consecutive x and emits one
+// ballot word per scale. Candidate iff strictly below the minimum or above the maximum of
+// neighbours 1..25 of the reference's table (SIFTExtrema.metal:15-45; neighbour 0 =
+// (-1,-1,-1) is skipped at :84) AND |v| > 0.8·C_DoG (first test of siftInterpolate,
+// SIFTInterpolate.metal:208 — fusing it here is result-neutral and lets most pixels exit after
+// three coalesced loads).
+__global__ void __launch_bounds__(256)
+extremaMaskKernel(const OctaveDev o, float softThreshold, uint32_t* __restrict__ mask,
+                  int blocksPerFrame) {
+    const int x = blockIdx.x * 256 + threadIdx.x;
+    const int y = blockIdx.y;
+    const int f = blockIdx.z;
+    const int lane = threadIdx.x & 31;
+    const int xw = x >> 5;
+    if (xw >= o.maskRowWords) return;  // whole warp exits together (x is warp-aligned)
+    const float* __restrict__ D = o.D + (size_t)f * kDogs * o.plane;
+    uint32_t* __restrict__ m =
+        mask + ((size_t)f * blocksPerFrame + o.maskBlockStart) * (size_t)kScanChunk;
+    const bool inside = (x >= 1) && (x <= o.w - 2) && (y >= 1) && (y <= o.h - 2);
+    const size_t c = (size_t)y * o.pitch + x;
+#pragma unroll
+    for (int s = 1; s <= kScales; s++) {
+        bool cand = false;
+        if (inside) {
+            const float* __restrict__ p = D + (size_t)s * o.plane + c;
+            const float v = __ldg(p);
+            if (!(fabsf(v) <= softThreshold)) {
+                float mn = +1000.0f, mx = -1000.0f;
+#pragma unroll
+                for (int ds = -1; ds <= 1; ds++) {
+#pragma unroll
+                    for (int dy = -1; dy <= 1; dy++) {
+#pragma unroll
+                        for (int dx = -1; dx <= 1; dx++) {
+                            if (ds == 0 && dy == 0 && dx == 0) continue;       // the centre
+                            if (ds == -1 && dy == -1 && dx == -1) continue;    // neighbour 0
+                            const float nv = __ldg(p + (ptrdiff_t)ds * (ptrdiff_t)o.plane +
+                                                   (ptrdiff_t)dy * o.pitch + dx);
+                            mn = fminf(mn, nv);
+                            mx = fmaxf(mx, nv);
+                        }
+                    }
+                }
+                cand = (v < mn) || (v > mx);
+            }
+        }
+        const uint32_t word = __ballot_sync(0xffffffffu, cand);
+        if (lane == 0) m[((size_t)(s - 1) * o.h + y) * o.maskRowWords + xw] = word;
+    }
+}
+
+cudaError_t launchExtremaMask(const EngineParams& P, int octave, uint32_t* mask, int frames,
+                              cudaStream_t st) {
+    const OctaveDev& o = P.oct[octave];
+    if (o.w < 3 || o.h < 3) return cudaSuccess;
+    dim3 grid((o.maskRowWords * 32 + 255) / 256, o.h, frames);
+    extremaMaskKernel<<<grid, 256, 0, st>>>(o, P.dogThreshold * 0.8f, mask, P.blocksPerFrame);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// scan phase B (declared in scan.cuh)
+__global__ void __launch_bounds__(1024)
+scanOffsetsKernel(int* blockSums, int n, int* totalOut, int capacity, int* overflow,
+                  int overflowBit) {
+    __shared__ int warpSums[33];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int ipt = (n + 1023) / 1024;
+    const int begin = min(tid * ipt, n), end = min(begin + ipt, n);
+    int s = 0;
+    for (int i = begin; i < end; i++) s += blockSums[i];
+    int inc = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += v;
+    }
+    if (lane == 31) warpSums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        const int ws = warpSums[lane];
+        int winc = ws;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, winc, d);
+            if (lane >= d) winc += v;
+        }
+        warpSums[lane] = winc - ws;
+        if (lane == 31) warpSums[32] = winc;
+    }
+    __syncthreads();
+    int run = inc - s + warpSums[wid];
+    for (int i = begin; i < end; i++) {
+        const int v = blockSums[i];
+        blockSums[i] = run;
+        run += v;
+    }
+    if (tid == 0) {
+        int total = warpSums[32];
+        if (total > capacity) {
+            total = capacity;
+            atomicOr(overflow, overflowBit);
+        }
+        *totalOut = total;
+    }
+}
+
+cudaError_t launchScanOffsets(int* blockSums, int n, int* totalOut, int capacity, int* overflow,
+                              int overflowBit, cudaStream_t st) {
+    scanOffsetsKernel<<<1, 1024, 0, st>>>(blockSums, n, totalOut, capacity, overflow, overflowBit);
+    return cudaGetLastError();
+}
+
+struct MaskPopc {
+    const uint32_t* mask;
+    __device__ int operator()(int i) const { return __popc(__ldg(mask + i)); }
+};
+
+// Phase C for the extrema mask: every set bit becomes a Candidate at its scanned position.
+__global__ void __launch_bounds__(kScanThreads)
+scatterCandidatesKernel(const __grid_constant__ EngineParams P, const uint32_t* __restrict__ mask,
+                        const int* __restrict__ blockOffsets, Candidate* __restrict__ cands,
+                        int capacity) {
+    __shared__ int sh[9];
+    const int b = blockIdx.x;
+    const int frame = b / P.blocksPerFrame;
+    const int fb = b - frame * P.blocksPerFrame;
+    int oc = 0;
+#pragma unroll
+    for (int k = 1; k < kOctaves; k++)
+        if (fb >= P.oct[k].maskBlockStart) oc = k;
+    const OctaveDev& o = P.oct[oc];
+    const int wordInOctave = (fb - o.maskBlockStart) * kScanChunk + threadIdx.x * kScanItemsPerThread;
+    const uint32_t* __restrict__ src = mask + (size_t)b * kScanChunk + threadIdx.x * kScanItemsPerThread;
+    uint32_t words[kScanItemsPerThread];
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItemsPerThread; k++) {
+        words[k] = __ldg(src + k);
+        s += __popc(words[k]);
+    }
+    int total;
+    int pos = blockOffsets[b] + blockExclusiveScan256(s, sh, &total);
+    if (s == 0) return;
+    const int seg = frame * kOctaves + oc;
+#pragma unroll
+    for (int k = 0; k < kScanItemsPerThread; k++) {
+        uint32_t wbits = words[k];
+        if (wbits == 0) continue;
+        const int wi = wordInOctave + k;
+        const int row = wi / o.maskRowWords;         // (s - 1) * h + y
+        const int xw = wi - row * o.maskRowWords;
+        const int sc = row / o.h;
+        const int y = row - sc * o.h;
+        while (wbits) {
+            const int bit = __ffs(wbits) - 1;
+            wbits &= wbits - 1;
+            if (pos < capacity) {
+                Candidate cd;
+                cd.xys = packXYS(xw * 32 + bit, y, sc + 1);
+                cd.seg = seg;
+                cands[pos] = cd;
+            }
+            pos++;
+        }
+    }
+}
+
+cudaError_t launchCandidateCompaction(const EngineParams& P, const uint32_t* mask,
+                                      int* blockSums, Candidate* cands, int capCandidates,
+                                      int* segCandCount, Counters* counters, int frames,
+                                      cudaStream_t st) {
+    (void)segCandCount;
+    const int nBlocks = P.blocksPerFrame * frames;
+    MaskPopc v{mask};
+    scanBlockSumsKernel<<<nBlocks, kScanThreads, 0, st>>>(v, blockSums);
+    SIFT_CUDA_TRY(cudaGetLastError());
+    SIFT_CUDA_TRY(launchScanOffsets(blockSums, nBlocks, &counters->nCandidates, capCandidates,
+                                    &counters->overflow, 1, st));
+    scatterCandidatesKernel<<<nBlocks, kScanThreads, 0, st>>>(P, mask, blockSums, cands,
+                                                              capCandidates);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Refinement.
+struct V3 {
+    float x, y, z;
+};
+__device__ __forceinline__ V3 cross3(const V3 a, const V3 b) {
+    V3 r;
+    r.x = (a.y * b.z) - (a.z * b.y);
+    r.y = (a.z * b.x) - (a.x * b.z);
+    r.z = (a.x * b.y) - (a.y * b.x);
+    return r;
+}
+
+struct DogView {
+    const float* __restrict__ base;  // slice 0 of this frame's DoG stack
+    size_t plane;
+    int pitch;
+    __device__ __forceinline__ float at(int x, int y, int s) const {
+        return __ldg(base + (size_t)s * plane + (size_t)y * pitch + x);
+    }
+};
+
+// SIFTInterpolate.metal:156-177 interpolationStep: alpha = -(H^-1) dD, H from hessian3D
+// (:103-164), inverse by cross products (Common.hpp:34-47) with det = dot(x0, cross(x1, x2)).
+__device__ __forceinline__ V3 interpolationStep(const DogView& t, int x, int y, int s, V3* dDout) {
+    const float zzz = t.at(x, y, s);
+    const float pzz = t.at(x + 1, y, s), nzz = t.at(x - 1, y, s);
+    const float zpz = t.at(x, y + 1, s), znz = t.at(x, y - 1, s);
+    const float zzp = t.at(x, y, s + 1), zzn = t.at(x, y, s - 1);
+    const float ppz = t.at(x + 1, y + 1, s), nnz = t.at(x - 1, y - 1, s);
+    const float npz = t.at(x - 1, y + 1, s), pnz = t.at(x + 1, y - 1, s);
+    const float pzp = t.at(x + 1, y, s + 1), nzp = t.at(x - 1, y, s + 1);
+    const float zpp = t.at(x, y + 1, s + 1), znp = t.at(x, y - 1, s + 1);
+    const float pzn = t.at(x + 1, y, s - 1), nzn = t.at(x - 1, y, s - 1);
+    const float zpn = t.at(x, y + 1, s - 1), znn = t.at(x, y - 1, s - 1);
+
+    const float dxx = (pzz + nzz) - (2 * zzz);
+    const float dyy = (zpz + znz) - (2 * zzz);
+    const float dss = (zzp + zzn) - (2 * zzz);
+    const float dxy = (((ppz - npz) - pnz) + nnz) * 0.25f;
+    const float dxs = (((pzp - nzp) - pzn) + nzn) * 0.25f;
+    const float dys = (((zpp - znp) - zpn) + znn) * 0.25f;
+
+    const V3 x0 = {dxx, dxy, dxs}, x1 = {dxy, dyy, dys}, x2 = {dxs, dys, dss};
+    const V3 c0 = cross3(x1, x2), c1 = cross3(x2, x0), c2 = cross3(x0, x1);
+    const float d = ((x0.x * c0.x) + (x0.y * c0.y)) + (x0.z * c0.z);
+    const float inv = 1.0f / d;
+    const V3 h0 = {-(inv * c0.x), -(inv * c0.y), -(inv * c0.z)};
+    const V3 h1 = {-(inv * c1.x), -(inv * c1.y), -(inv * c1.z)};
+    const V3 h2 = {-(inv * c2.x), -(inv * c2.y), -(inv * c2.z)};
+    V3 dD;
+    dD.x = (pzz - nzz) * 0.5f;
+    dD.y = (zpz - znz) * 0.5f;
+    dD.z = (zzp - zzn) * 0.5f;
+    *dDout = dD;
+    V3 a;
+    a.x = ((h0.x * dD.x) + (h1.x * dD.y)) + (h2.x * dD.z);
+    a.y = ((h0.y * dD.x) + (h1.y * dD.y)) + (h2.y * dD.z);
+    a.z = ((h0.z * dD.x) + (h1.z * dD.y)) + (h2.z * dD.z);
+    return a;
+}
+
+// SIFTInterpolate.metal:17-61 isOnEdge.
+__device__ __forceinline__ bool isOnEdge(const DogView& t, int x, int y, int s, float edgeThreshold) {
+    const float v = t.at(x, y, s);
+    const float zn = t.at(x, y - 1, s), zp = t.at(x, y + 1, s);
+    const float pz = t.at(x + 1, y, s), nz = t.at(x - 1, y, s);
+    const float pp = t.at(x + 1, y + 1, s), np = t.at(x - 1, y + 1, s);
+    const float pn = t.at(x + 1, y - 1, s), nn = t.at(x - 1, y - 1, s);
+    const float hxx = (zn + zp) - (2 * v);
+    const float hyy = (pz + nz) - (2 * v);
+    const float hxy = ((pp - np) - (pn - nn)) * 0.25f;
+    const float trace = hxx + hyy;
+    const float determinant = (hxx * hyy) - (hxy * hxy);
+    if (determinant <= 0) return true;
+    const float threshold = ((edgeThreshold + 1) * (edgeThreshold + 1)) / edgeThreshold;
+    const float curvature = (trace * trace) / determinant;
+    return curvature >= threshold;
+}
+
+__device__ __forceinline__ bool outOfBounds(int x, int y, int s, int w, int h, int border) {
+    return x < border || x > w - border - 1 || y < border || y > h - border - 1 || s < 1 ||
+           s > kScales;
+}
+
+// One thread per candidate, grid-stride by warps so that each warp can ballot its converged
+// flags into one word (index-aligned with the candidate list, hence still canonical order).
+__global__ void __launch_bounds__(256)
+refineKernel(const __grid_constant__ EngineParams P, const Candidate* __restrict__ cands,
+             const Counters* __restrict__ counters, SiftKeypoint* __restrict__ kpTmp,
+             uint32_t* __restrict__ flagWords) {
+    const int n = counters->nCandidates;
+    const int lane = threadIdx.x & 31;
+    const int warpsTotal = (gridDim.x * blockDim.x) >> 5;
+    for (int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; base < n;
+         base += warpsTotal * 32) {
+        const int i = base + lane;
+        bool ok = false;
+        if (i < n) {
+            const Candidate cd = cands[i];
+            const int frame = cd.seg / kOctaves, oc = cd.seg - frame * kOctaves;
+            const OctaveDev& o = P.oct[oc];
+            DogView t;
+            t.base = o.D + (size_t)frame * kDogs * o.plane;
+            t.plane = o.plane;
+            t.pitch = o.pitch;
+            int x = cd.xys & 0x7fff, y = (cd.xys >> 15) & 0x7fff, s = cd.xys >> 30;
+            // the 0.8·C_DoG test (SIFTInterpolate.metal:208) already held in the extrema kernel
+            if (!outOfBounds(x, y, s, o.w, o.h, P.border)) {
+                bool converged = false, alive = true;
+                V3 alpha = {0, 0, 0}, dD = {0, 0, 0};
+                int it = 0;
+                while (it < P.maxIterations) {
+                    alpha = interpolationStep(t, x, y, s, &dD);
+                    if ((fabsf(alpha.x) < P.maxOffset) && (fabsf(alpha.y) < P.maxOffset) &&
+                        (fabsf(alpha.z) < P.maxOffset)) {
+                        converged = true;
+                        break;
+                    }
+                    if (alpha.x > +P.maxOffset) x += 1;
+                    if (alpha.x < -P.maxOffset) x -= 1;
+                    if (alpha.y > +P.maxOffset) y += 1;
+                    if (alpha.y < -P.maxOffset) y -= 1;
+                    if (alpha.z > +P.maxOffset) s += 1;
+                    if (alpha.z < -P.maxOffset) s -= 1;
+                    if (outOfBounds(x, y, s, o.w, o.h, P.border)) {
+                        alive = false;
+                        break;
+                    }
+                    it += 1;
+                }
+                if (alive && converged) {
+                    // interpolateContrast (:90-100): v + 0.5·(dD.x·alpha.x) — x term only
+                    const float value = t.at(x, y, s) + ((dD.x * alpha.x) * 0.5f);
+                    if (!(fabsf(value) <= P.dogThreshold) &&
+                        !isOnEdge(t, x, y, s, P.edgeThreshold)) {
+                        SiftKeypoint k;
+                        k.octave = oc;
+                        k.scale = s;
+                        k.subScale = alpha.z;
+                        k.scaledX = x;
+                        k.scaledY = y;
+                        k.absoluteX = ((float)x + alpha.x) * o.delta;
+                        k.absoluteY = ((float)y + alpha.y) * o.delta;
+                        k.normalizedX = (float)x / (float)o.w;
+                        k.normalizedY = (float)y / (float)o.h;
+                        k.sigma = o.sigmas[s] * dm_exp2f(alpha.z * o.log2SigmaRatio);
+                        k.value = value;
+                        kpTmp[i] = k;
+                        ok = true;
+                    }
+                }
+            }
+        }
+        const uint32_t word = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) flagWords[base >> 5] = word;
+    }
+}
+
+struct FlagPopc {
+    const uint32_t* flags;
+    const Counters* counters;
+    __device__ int operator()(int i) const {
+        const int nWords = (counters->nCandidates + 31) >> 5;
+        return i < nWords ? __popc(flags[i]) : 0;
+    }
+};
+
+__global__ void __launch_bounds__(kScanThreads)
+scatterKeypointsKernel(const uint32_t* __restrict__ flags, const Counters* __restrict__ counters,
+                       const int* __restrict__ blockOffsets, const Candidate* __restrict__ cands,
+                       const SiftKeypoint* __restrict__ kpTmp, SiftKeypoint* __restrict__ kps,
+                       int* __restrict__ kpSeg, int capacity) {
+    __shared__ int sh[9];
+    const int nWords = (counters->nCandidates + 31) >> 5;
+    const int w0 = blockIdx.x * kScanChunk + threadIdx.x * kScanItemsPerThread;
+    uint32_t words[kScanItemsPerThread];
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItemsPerThread; k++) {
+        words[k] = (w0 + k) < nWords ? flags[w0 + k] : 0u;
+        s += __popc(words[k]);
+    }
+    int total;
+    int pos = blockOffsets[blockIdx.x] + blockExclusiveScan256(s, sh, &total);
+#pragma unroll
+    for (int k = 0; k < kScanItemsPerThread; k++) {
+        uint32_t wbits = words[k];
+        while (wbits) {
+            const int bit = __ffs(wbits) - 1;
+            wbits &= wbits - 1;
+            const int i = (w0 + k) * 32 + bit;
+            if (pos < capacity) {
+                kps[pos] = kpTmp[i];
+                kpSeg[pos] = cands[i].seg;
+            }
+            pos++;
+        }
+    }
+}
+
+// segStart[seg] = first index whose seg >= seg (lower bound) — lists are sorted by segment, so
+// per-(frame, octave) counts are differences; no atomics.
+__global__ void segmentStartsKernel(const int* __restrict__ kpSeg, const int* __restrict__ nPtr,
+                                    int* __restrict__ segStart, int nSegs) {
+    const int seg = blockIdx.x * blockDim.x + threadIdx.x;
+    if (seg > nSegs) return;
+    const int n = *nPtr;
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (kpSeg[mid] < seg) lo = mid + 1;
+        else hi = mid;
+    }
+    segStart[seg] = lo;
+}
+
+__global__ void candidateSegmentStartsKernel(const Candidate* __restrict__ cands,
+                                             const int* __restrict__ nPtr,
+                                             int* __restrict__ segStart, int nSegs) {
+    const int seg = blockIdx.x * blockDim.x + threadIdx.x;
+    if (seg > nSegs) return;
+    const int n = *nPtr;
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (cands[mid].seg < seg) lo = mid + 1;
+        else hi = mid;
+    }
+    segStart[seg] = lo;
+}
+
+cudaError_t launchSegmentStarts(const int* kpSeg, const int* nPtr, int* segStart, int nSegs,
+                                cudaStream_t st) {
+    segmentStartsKernel<<<(nSegs + 1 + 127) / 128, 128, 0, st>>>(kpSeg, nPtr, segStart, nSegs);
+    return cudaGetLastError();
+}
+
+cudaError_t launchCandidateSegmentStarts(const Candidate* cands, const int* nPtr, int* segStart,
+                                         int nSegs, cudaStream_t st) {
+    candidateSegmentStartsKernel<<<(nSegs + 1 + 127) / 128, 128, 0, st>>>(cands, nPtr, segStart, nSegs);
+    return cudaGetLastError();
+}
+
+cudaError_t launchRefine(const EngineParams& P, const Candidate* cands, int capCandidates,
+                         SiftKeypoint* kpTmp, uint32_t* flagWords, int* blockSums,
+                         SiftKeypoint* kps, int* kpSeg, int capKeypoints, int* segKpCount,
+                         int* segKpStart, int nSegs, Counters* counters, int smCount,
+                         cudaStream_t st) {
+    (void)segKpCount;
+    refineKernel<<<smCount * 8, 256, 0, st>>>(P, cands, counters, kpTmp, flagWords);
+    SIFT_CUDA_TRY(cudaGetLastError());
+    const int capWords = (capCandidates + 31) / 32;
+    const int nBlocks = (capWords + kScanChunk - 1) / kScanChunk;
+    FlagPopc v{flagWords, counters};
+    scanBlockSumsKernel<<<nBlocks, kScanThreads, 0, st>>>(v, blockSums);
+    SIFT_CUDA_TRY(cudaGetLastError());
+    SIFT_CUDA_TRY(launchScanOffsets(blockSums, nBlocks, &counters->nKeypoints, capKeypoints,
+                                    &counters->overflow, 2, st));
+    scatterKeypointsKernel<<<nBlocks, kScanThreads, 0, st>>>(flagWords, counters, blockSums, cands,
+                                                            kpTmp, kps, kpSeg, capKeypoints);
+    SIFT_CUDA_TRY(cudaGetLastError());
+    return launchSegmentStarts(kpSeg, &counters->nKeypoints, segKpStart, nSegs, st);
+}
+
+}  // namespace sift

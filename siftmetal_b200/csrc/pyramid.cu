@@ -1,0 +1,267 @@
+// pyramid.cu — seed image, separable Gaussian series fused with the DoG subtraction, gradient
+// field. Hand-written for sm_100a; compiled with -fmad=false: every float expression is
+// evaluated exactly as written (the arithmetic spec of DESIGN.md), only explicit fmaf() fuses.
+//
+// Replaces, with identical per-pixel arithmetic:
+//   ConvertSRGBToGrayscale.metal:11-23, BilinearUpScale.metal:12-64       → grayUpsampleKernel
+//   Convolution.metal:15-52, ConvolutionSeries.metal:16-53 (X then Y),
+//   Subtract.metal:12-21, NearestNeighborDownScale.metal:15-22            → blurKernel
+//   SIFTGradient.metal:15-39                                              → gradientKernel
+#include "common.cuh"
+#include "dev_math.cuh"
+
+namespace sift {
+
+// Common.hpp:15-22 symmetrizedCoordinates (floor-mod form, identical for i >= -2l).
+__device__ __forceinline__ int symmetrized(int i, int l) {
+    int ll = 2 * l;
+    i = ((i % ll) + ll) % ll;
+    if (i > l - 1) i = ll - 1 - i;
+    return i;
+}
+
+// ------------------------------------------------------------------------------------------
+// Gray + 2x bilinear upsample. One thread per output pixel of the 2W x 2H plane.
+__device__ __forceinline__ float grayOf(const uint8_t* row, int x) {
+    const uchar4 p = *reinterpret_cast<const uchar4*>(row + 4 * x);  // b, g, r, a
+    const float b = (float)p.x / 255.0f;
+    const float g = (float)p.y / 255.0f;
+    const float r = (float)p.z / 255.0f;
+    return ((0.0f + (0.212639005871510f * r)) + (0.715168678767756f * g)) +
+           (0.072192315360734f * b);
+}
+
+__global__ void __launch_bounds__(256)
+grayUpsampleKernel(const uint8_t* __restrict__ bgra, int pitchBytes, int64_t frameStrideBytes,
+                   float* __restrict__ gray, int W, int H, float* __restrict__ scaled, int w2,
+                   int h2, int pitch2, size_t scaledFrameStride) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    const int f = blockIdx.z;
+    if (i >= w2) return;
+    const uint8_t* src = bgra + (size_t)f * frameStrideBytes;
+    const float dx = (float)W / (float)w2;
+    const float dy = (float)H / (float)h2;
+    const float x = (float)i * dx;
+    const float y = (float)j * dy;
+    int im = (int)x, jm = (int)y;
+    int ip = im + 1, jp = jm + 1;
+    if (ip >= W) ip = 2 * W - 1 - ip;
+    if (im >= W) im = 2 * W - 1 - im;
+    if (jp >= H) jp = 2 * H - 1 - jp;
+    if (jm >= H) jm = 2 * H - 1 - jm;
+    const float fx = x - floorf(x);
+    const float fy = y - floorf(y);
+    const uint8_t* rowP = src + (size_t)jp * pitchBytes;
+    const uint8_t* rowM = src + (size_t)jm * pitchBytes;
+    const float c0 = grayOf(rowP, ip), c1 = grayOf(rowM, ip);
+    const float c2 = grayOf(rowP, im), c3 = grayOf(rowM, im);
+    const float a = (fy * c0) + ((1 - fy) * c1);
+    const float b = (fy * c2) + ((1 - fy) * c3);
+    scaled[(size_t)f * scaledFrameStride + (size_t)j * pitch2 + i] = (fx * a) + ((1 - fx) * b);
+    if (gray != nullptr && (i & 1) == 0 && (j & 1) == 0 && (i >> 1) < W && (j >> 1) < H)
+        gray[((size_t)f * H + (j >> 1)) * W + (i >> 1)] = c3;  // even (i, j): (im, jm) = (i/2, j/2)
+}
+
+cudaError_t launchGrayUpsample(const uint8_t* bgra, int pitchBytes, int64_t frameStrideBytes,
+                               float* gray, int W, int H, float* scaled, int w2, int h2,
+                               int pitch2, size_t scaledFrameStride, int frames,
+                               cudaStream_t st) {
+    dim3 grid((w2 + 255) / 256, h2, frames);
+    grayUpsampleKernel<<<grid, 256, 0, st>>>(bgra, pitchBytes, frameStrideBytes, gray, W, H,
+                                             scaled, w2, h2, pitch2, scaledFrameStride);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Separable Gaussian blur, X pass then Y pass through shared memory, fused with
+//   dog  = out - in            (Subtract.metal)
+//   half = out[2y][2x]         (NearestNeighborDownScale.metal, seeds the next octave)
+// Per output pixel the accumulation is sum = fma(w[i], c, sum), i ascending, as the oracle.
+//
+// Tile: TX x TY outputs per CTA of 256 threads. Shared memory holds the input tile with halo
+// (rows TY + 2R, columns TX + 2RP, RP = R rounded up to 4 so that rows stay 16-byte aligned
+// with global memory) and the X-pass result (rows TY + 2R, columns TX). Both row pitches are
+// 4 * odd floats: 8 lanes on 8 consecutive rows issuing LDS.128 / STS.128 hit 8 distinct
+// 4-bank groups, so the row-per-lane X pass is conflict-free; the Y pass walks columns with
+// consecutive lanes on consecutive x, also conflict-free.
+template <int NTAPS, int TX, int TY>
+struct BlurCfg {
+    static constexpr int R = NTAPS / 2;
+    static constexpr int RP = (R + 3) / 4 * 4;
+    static constexpr int IN_W = TX + 2 * RP;
+    static constexpr int IN_H = TY + 2 * R;
+    static constexpr int IP = (IN_W % 8 == 4) ? IN_W : IN_W + 4;  // IN_W is a multiple of 4
+    static constexpr int TP = (TX % 8 == 4) ? TX : TX + 4;
+    static constexpr int SMEM_FLOATS = IN_H * IP + IN_H * TP;
+    static constexpr int XSEG = 8;   // outputs per thread in the X pass
+    static constexpr int RY = 8;     // outputs per thread in the Y pass
+};
+
+template <int NTAPS, int TX, int TY>
+__global__ void __launch_bounds__(256)
+blurKernel(const BlurArgs a, const __grid_constant__ Taps taps) {
+    using C = BlurCfg<NTAPS, TX, TY>;
+    constexpr int R = C::R, RP = C::RP, IN_W = C::IN_W, IN_H = C::IN_H, IP = C::IP, TP = C::TP;
+    extern __shared__ __align__(16) float smem[];
+    float* sIn = smem;
+    float* sTmp = smem + IN_H * IP;
+
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+    const int f = blockIdx.z;
+    const float* __restrict__ in = a.in + (size_t)f * a.inFrameStride;
+    const int w = a.w, h = a.h, pitch = a.pitch;
+
+    // ---- load the input tile with halo --------------------------------------------------
+    const bool interior = (x0 - RP >= 0) && (x0 + TX + RP <= w) && (y0 - R >= 0) &&
+                          (y0 + TY + R <= h);
+    if (interior) {
+        constexpr int V = IN_W / 4;
+        const float* base = in + (size_t)(y0 - R) * pitch + (x0 - RP);
+        for (int idx = tid; idx < IN_H * V; idx += 256) {
+            const int r = idx / V, c4 = idx - r * V;
+            const float* g = base + (size_t)r * pitch + 4 * c4;
+            const unsigned s = (unsigned)__cvta_generic_to_shared(sIn + r * IP + 4 * c4);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(g));
+        }
+        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+    } else {
+        for (int idx = tid; idx < IN_H * IN_W; idx += 256) {
+            const int r = idx / IN_W, c = idx - r * IN_W;
+            const int gy = symmetrized(y0 - R + r, h);
+            const int gx = symmetrized(x0 - RP + c, w);
+            sIn[r * IP + c] = __ldg(in + (size_t)gy * pitch + gx);
+        }
+    }
+    __syncthreads();
+
+    // ---- X pass: one row, 8 consecutive outputs per thread ---------------------------------
+    {
+        constexpr int SEGS = TX / C::XSEG;
+        constexpr int NV = (C::XSEG + 2 * RP) / 4;
+        for (int t = tid; t < IN_H * SEGS; t += 256) {
+            const int seg = t / IN_H, r = t - seg * IN_H;
+            const float4* src = reinterpret_cast<const float4*>(sIn + r * IP + seg * C::XSEG);
+            float v[NV * 4];
+#pragma unroll
+            for (int k = 0; k < NV; k++) {
+                const float4 q = src[k];
+                v[4 * k + 0] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+            }
+            float acc[C::XSEG];
+#pragma unroll
+            for (int k = 0; k < C::XSEG; k++) acc[k] = 0.0f;
+#pragma unroll
+            for (int i = 0; i < NTAPS; i++) {
+                const float wi = taps.w[i];
+#pragma unroll
+                for (int k = 0; k < C::XSEG; k++) acc[k] = fmaf(wi, v[k + (RP - R) + i], acc[k]);
+            }
+            float4* dst = reinterpret_cast<float4*>(sTmp + r * TP + seg * C::XSEG);
+            dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        }
+    }
+    __syncthreads();
+
+    // ---- Y pass: one column, 8 consecutive rows per thread; fused DoG / decimation ---------
+    {
+        constexpr int RY = C::RY;
+        float* __restrict__ out = a.out + (size_t)f * a.outFrameStride;
+        float* __restrict__ dog = a.dog ? a.dog + (size_t)f * a.dogFrameStride : nullptr;
+        float* __restrict__ half = a.half ? a.half + (size_t)f * a.halfFrameStride : nullptr;
+        for (int t = tid; t < TX * (TY / RY); t += 256) {
+            const int yb = t / TX, x = t - yb * TX;
+            const int gx = x0 + x;
+            float v[RY + 2 * R];
+#pragma unroll
+            for (int k = 0; k < RY + 2 * R; k++) v[k] = sTmp[(yb * RY + k) * TP + x];
+            float acc[RY];
+#pragma unroll
+            for (int q = 0; q < RY; q++) acc[q] = 0.0f;
+#pragma unroll
+            for (int i = 0; i < NTAPS; i++) {
+                const float wi = taps.w[i];
+#pragma unroll
+                for (int q = 0; q < RY; q++) acc[q] = fmaf(wi, v[q + i], acc[q]);
+            }
+            if (gx < w) {
+#pragma unroll
+                for (int q = 0; q < RY; q++) {
+                    const int gy = y0 + yb * RY + q;
+                    if (gy < h) {
+                        const size_t o = (size_t)gy * pitch + gx;
+                        out[o] = acc[q];
+                        if (dog) dog[o] = acc[q] - sIn[(yb * RY + q + R) * IP + RP + x];
+                        if (half && ((gx | gy) & 1) == 0 && (gx >> 1) < a.halfW &&
+                            (gy >> 1) < a.halfH)
+                            half[(size_t)(gy >> 1) * a.halfPitch + (gx >> 1)] = acc[q];
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int NTAPS>
+static cudaError_t launchBlurT(const BlurArgs& a, const Taps& taps, cudaStream_t st) {
+    constexpr int TX = 64, TY = 64;
+    using C = BlurCfg<NTAPS, TX, TY>;
+    static_assert(C::IN_W % 4 == 0 && C::IP % 8 == 4 && C::TP % 8 == 4, "bank layout");
+    const int smemBytes = C::SMEM_FLOATS * (int)sizeof(float);
+    static unsigned long long configured = 0;  // per-device bit: the attribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!((configured >> (dev & 63)) & 1ull)) {
+        cudaError_t e = cudaFuncSetAttribute(blurKernel<NTAPS, TX, TY>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes);
+        if (e != cudaSuccess) return e;
+        configured |= 1ull << (dev & 63);
+    }
+    dim3 grid((a.w + TX - 1) / TX, (a.h + TY - 1) / TY, a.frames);
+    blurKernel<NTAPS, TX, TY><<<grid, 256, smemBytes, st>>>(a, taps);
+    return cudaGetLastError();
+}
+
+cudaError_t launchBlur(const BlurArgs& a, const Taps& taps, int ntaps, cudaStream_t st) {
+    switch (ntaps) {
+        case 11: return launchBlurT<11>(a, taps, st);
+        case 15: return launchBlurT<15>(a, taps, st);
+        case 17: return launchBlurT<17>(a, taps, st);
+        case 21: return launchBlurT<21>(a, taps, st);
+        case 27: return launchBlurT<27>(a, taps, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// SIFTGradient.metal:15-39 for Gaussian slices 1..3 (the only ones ever read downstream:
+// refined scale is in [1, 3], SIFTInterpolate.metal:187-189).
+__global__ void __launch_bounds__(256) gradientKernel(const OctaveDev o) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int s = blockIdx.z % kScales;   // 0..2 → Gaussian slice s + 1
+    const int f = blockIdx.z / kScales;
+    if (x >= o.w) return;
+    const float* __restrict__ g = o.G + ((size_t)f * kGaussians + (s + 1)) * o.plane;
+    const int px = symmetrized(x + 1, o.w), mx = symmetrized(x - 1, o.w);
+    const int py = symmetrized(y + 1, o.h), my = symmetrized(y - 1, o.h);
+    const float cpx = __ldg(g + (size_t)y * o.pitch + px);
+    const float cmx = __ldg(g + (size_t)y * o.pitch + mx);
+    const float cpy = __ldg(g + (size_t)py * o.pitch + x);
+    const float cmy = __ldg(g + (size_t)my * o.pitch + x);
+    const float tx = (cpx - cmx) * 0.5f;
+    const float ty = (cpy - cmy) * 0.5f;
+    const float oa = dm_atan2f(tx, ty);
+    const float om = sqrtf((tx * tx) + (ty * ty));
+    o.grad[((size_t)f * kScales + s) * o.plane + (size_t)y * o.pitch + x] = make_float2(oa, om);
+}
+
+cudaError_t launchGradient(const OctaveDev& o, int frames, cudaStream_t st) {
+    dim3 grid((o.w + 255) / 256, o.h, kScales * frames);
+    gradientKernel<<<grid, 256, 0, st>>>(o);
+    return cudaGetLastError();
+}
+
+}  // namespace sift

@@ -1,0 +1,107 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/siftcuda.h declares, the header is valid C, the ctypes mirrors have the C layouts, and
+without a GPU the product fails loudly instead of falling back to anything."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from siftmetal_b200 import _abi, api
+
+HEADER = os.path.join(ROOT, "include", "siftcuda.h")
+
+
+def _declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sift_[a-z_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from siftmetal_b200.build import build
+
+    build()
+    return api.load_library()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    names = _declared_functions()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in siftcuda.h but not exported"
+    assert sorted(api.EXPORTED_SYMBOLS) == names
+
+
+def test_header_is_plain_c_and_layouts_match(tmp_path):
+    prog = tmp_path / "layout.c"
+    prog.write_text(
+        '#include <stdio.h>\n#include "siftcuda.h"\n'
+        "int main(void){printf(\"%zu %zu %zu %zu %zu %zu\\n\", sizeof(SiftConfig), sizeof(SiftKeypoint),"
+        " sizeof(SiftDescriptor), sizeof(SiftBatchResult), sizeof(SiftInfo), sizeof(SiftTimings));return 0;}\n"
+    )
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)], check=True)
+    sizes = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    assert sizes == [C.sizeof(_abi.SiftConfig), _abi.KEYPOINT_DTYPE.itemsize, _abi.DESCRIPTOR_DTYPE.itemsize,
+                     C.sizeof(_abi.SiftBatchResult), C.sizeof(_abi.SiftInfo), C.sizeof(_abi.SiftTimings)]
+    assert sizes[1] == 44 and sizes[2] == 136
+
+
+def test_cpp_host_mirror_compiles(tmp_path):
+    """include/SIFT.hpp (C++ mirror of the Swift API) compiles against the C ABI and links."""
+    hpp = os.path.join(ROOT, "include", "SIFT.hpp")
+    if not os.path.exists(hpp):
+        pytest.skip("C++ mirror not present")
+    prog = tmp_path / "use.cpp"
+    prog.write_text(
+        '#include "SIFT.hpp"\n#include <cstdio>\n'
+        "int main(){ try { siftcuda::SIFT s(0, siftcuda::SIFT::Configuration(siftcuda::IntegralSize{64,48})); }\n"
+        " catch (const std::exception& e) { std::printf(\"%s\\n\", e.what()); return 3; } return 0; }\n"
+    )
+    exe = tmp_path / "use"
+    libdir = os.path.dirname(api.LIB_PATH)
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe),
+                    "-L", libdir, "-lsiftcuda", f"-Wl,-rpath,{libdir}"], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode in (0, 3)  # 3 = no GPU here: the mirror must throw, not fall back
+
+
+def test_defaults_are_the_reference_literals(lib):
+    cfg = _abi.SiftConfig()
+    assert lib.sift_config_default(C.byref(cfg), 512, 340) == 0
+    # SIFTOctave.swift:217-226, :296-300; SIFTInterpolate.metal:182; SIFTOrientation.metal:167
+    assert (cfg.width, cfg.height, cfg.max_batch) == (512, 340, 1)
+    assert np.float32(cfg.dog_threshold) == np.float32(0.0133)
+    assert cfg.edge_threshold == 10.0 and cfg.max_interpolation_iterations == 5
+    assert np.float32(cfg.max_offset) == np.float32(0.6) and cfg.image_border == 5
+    assert cfg.lambda_orientation == 1.5 and np.float32(cfg.orientation_threshold) == np.float32(0.8)
+    assert cfg.orientation_smoothing_iterations == 6
+    assert lib.sift_status_string(_abi.SIFT_ERR_CAPACITY).decode().startswith("device list capacity")
+
+
+def test_no_gpu_means_loud_failure(lib):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(api.SiftError) as ei:
+        api.Engine(64, 48)
+    assert ei.value.status == _abi.SIFT_ERR_NO_DEVICE
+    out = np.zeros(4, np.float32)
+    assert lib.sift_debug_math(0, 0, out.ctypes.data, None, out.ctypes.data, 4) == _abi.SIFT_ERR_NO_DEVICE
+
+
+def test_product_does_not_reference_the_oracle():
+    """The oracle is test infrastructure: nothing under siftmetal_b200/ or include/ may name it."""
+    for base in ("siftmetal_b200", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                    text = open(os.path.join(dirpath, f), errors="ignore").read()
+                    assert "libsiftoracle" not in text and "oracle_lib" not in text and "sift_oracle" not in text, f
+    assert b"oracle_" not in open(api.LIB_PATH, "rb").read()
