@@ -148,6 +148,7 @@ typedef struct SiftTimings {
     float total_ms;                      /* first launch → last kernel                           */
     float stage_ms[SIFT_STAGE_COUNT];    /* valid when stage timing was enabled                   */
     float blur_octave0_ms;               /* the dominant kernel: 5 octave-0 blur launches, summed */
+    float blur_octave0_launch_ms[SIFT_NUM_GAUSSIANS - 1]; /* each of them (11,15,17,21,27 taps)   */
     int32_t blur_octave0_launches;
     int32_t kernel_launches;             /* kernels launched by the last execute                  */
     int32_t stage_timing_enabled;

@@ -79,6 +79,7 @@ class SiftTimings(C.Structure):
         ("total_ms", C.c_float),
         ("stage_ms", C.c_float * 6),
         ("blur_octave0_ms", C.c_float),
+        ("blur_octave0_launch_ms", C.c_float * (NUM_GAUSSIANS - 1)),
         ("blur_octave0_launches", C.c_int32),
         ("kernel_launches", C.c_int32),
         ("stage_timing_enabled", C.c_int32),

@@ -221,7 +221,8 @@ class Engine:
         t = SiftTimings()
         self._check(self.L.sift_last_timings(self.ctx, C.byref(t)))
         d = {"total_ms": t.total_ms, "kernel_launches": t.kernel_launches,
-             "blur_octave0_ms": t.blur_octave0_ms, "blur_octave0_launches": t.blur_octave0_launches}
+             "blur_octave0_ms": t.blur_octave0_ms, "blur_octave0_launches": t.blur_octave0_launches,
+             "blur_octave0_launch_ms": list(t.blur_octave0_launch_ms)}
         for i, name in enumerate(_abi.STAGE_NAMES):
             d[name + "_ms"] = t.stage_ms[i]
         return d

@@ -74,7 +74,7 @@ struct SiftContext {
     // timing
     bool stageTiming = true;
     cudaEvent_t ev[SIFT_STAGE_COUNT + 1]{};
-    cudaEvent_t evBlur0[2]{};
+    cudaEvent_t evBlur0[kGaussians]{};
     SiftTimings timings{};
     int launches = 0;
 
@@ -429,8 +429,8 @@ int runDetect(SiftContext* c) {
     for (int o = 0; o < kOctaves; o++) {
         const OctaveDev& q = c->P.oct[o];
         if (q.w < 1 || q.h < 1) continue;
-        if (T && o == 0) CTX_TRY(c, cudaEventRecord(c->evBlur0[0], st));
         for (int s = 0; s < kGaussians - 1; s++) {
+            if (T && o == 0) CTX_TRY(c, cudaEventRecord(c->evBlur0[s], st));
             BlurArgs a{};
             a.in = q.G + (size_t)s * q.plane;
             a.out = q.G + (size_t)(s + 1) * q.plane;
@@ -448,7 +448,7 @@ int runDetect(SiftContext* c) {
             CTX_TRY(c, launchBlur(a, c->taps[s], c->ntaps[s], st));
             c->launches++;
         }
-        if (T && o == 0) CTX_TRY(c, cudaEventRecord(c->evBlur0[1], st));
+        if (T && o == 0) CTX_TRY(c, cudaEventRecord(c->evBlur0[kGaussians - 1], st));
         CTX_TRY(c, launchGradient(q, F, st));
         c->launches++;
     }
@@ -516,7 +516,9 @@ int finish(SiftContext* c, bool withDescribe) {
         const int last = withDescribe ? SIFT_STAGE_COUNT : 4;
         for (int i = 0; i < last; i++) cudaEventElapsedTime(&t.stage_ms[i], c->ev[i], c->ev[i + 1]);
         cudaEventElapsedTime(&t.total_ms, c->ev[0], c->ev[last]);
-        cudaEventElapsedTime(&t.blur_octave0_ms, c->evBlur0[0], c->evBlur0[1]);
+        cudaEventElapsedTime(&t.blur_octave0_ms, c->evBlur0[0], c->evBlur0[kGaussians - 1]);
+        for (int s = 0; s < kGaussians - 1; s++)
+            cudaEventElapsedTime(&t.blur_octave0_launch_ms[s], c->evBlur0[s], c->evBlur0[s + 1]);
         t.blur_octave0_launches = kGaussians - 1;
     }
     if (c->hCounters->overflow) {
