@@ -23,7 +23,7 @@ COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "-prec-div=tr
 SOURCES = {
     "pyramid.cu": ["-fmad=false"],
     "detect.cu": ["-fmad=false"],
-    "describe.cu": [],
+    "describe.cu": (["-DSIFT_DEBUG_DESC"] if os.environ.get("SIFT_DEBUG_DESC") else []),
     "capi.cu": [],
 }
 HEADERS = ["common.cuh", "dev_math.cuh", "scan.cuh", os.path.join(ROOT, "include", "siftcuda.h")]

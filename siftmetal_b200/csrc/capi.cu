@@ -303,8 +303,8 @@ int sift_create(const SiftConfig* cfg, int device, SiftContext** out) {
     }
     const size_t maskWords = B * (size_t)c->P.blocksPerFrame * kScanChunk;
     A(devAlloc(c, &c->dMask, maskWords));
-    const size_t flagWords = ((size_t)c->capCand / 32 / kScanChunk + 2) * kScanChunk;
-    const size_t nBlockSums = std::max({B * (size_t)c->P.blocksPerFrame, flagWords / kScanChunk + 1,
+    const size_t flagWords = (size_t)c->capCand / 32 + 64;
+    const size_t nBlockSums = std::max({B * (size_t)c->P.blocksPerFrame, (size_t)c->capCand / 256 + 2,
                                         (size_t)c->capKp / kScanChunk + 2}) + 16;
     A(devAlloc(c, &c->dBlockSums, nBlockSums));
     A(devAlloc(c, &c->dCands, (size_t)c->capCand));

@@ -13,6 +13,7 @@
 // order, so they differ from the oracle in the last bits; every quantity that drives a
 // *discontinuous* decision (bin index, window radius, sample coordinate, border filter) is
 // evaluated with the spec's exact operation sequence.
+#include <stdio.h>
 #include "common.cuh"
 #include "dev_math.cuh"
 #include "scan.cuh"
@@ -22,7 +23,8 @@ namespace sift {
 constexpr float kTau = 6.28318530717958647692f;  // 2 * M_PI_F in float
 
 // ------------------------------------------------------------------------------------------
-constexpr int kOriWarps = 8;  // warps (keypoints in flight) per CTA
+constexpr int kOriWarps = 8;      // warps (keypoints in flight) per CTA
+constexpr int kOriMaxSide = 96;   // window side 2r+1; r = ceil(4.5 sigma') <= 17 for detected keypoints
 
 __global__ void __launch_bounds__(kOriWarps * 32)
 orientationKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __restrict__ kps,
@@ -30,14 +32,16 @@ orientationKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __
                   int* __restrict__ nOri, float* __restrict__ oriTmp) {
     __shared__ float sHist[kOriWarps][kOriBins * 32];  // [bin][lane] per warp
     __shared__ float sH[kOriWarps][2][kOriBins];
+    __shared__ float sW[kOriWarps][kOriMaxSide];       // separable Gaussian window weights
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int n = counters->nKeypoints;
     float* hist = sHist[wid];
+    float* wt = sW[wid];
     for (int k = blockIdx.x * kOriWarps + wid; k < n; k += gridDim.x * kOriWarps) {
         const SiftKeypoint kp = kps[k];
         const int frame = kpSeg[k] / kOctaves;
         const OctaveDev& o = P.oct[kp.octave];
-        // host filter of SIFTOctave.swift:303-329 on the untruncated coordinates
+        // host filter of SIFTOctave.swift:303-329 on the untruncated coordinates (exact sequence)
         const float lambda = P.lambdaOri;
         const float fx = __fdiv_rn(kp.absoluteX, o.delta);
         const float fy = __fdiv_rn(kp.absoluteY, o.delta);
@@ -47,7 +51,9 @@ orientationKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __
                             (ceilf(__fadd_rn(fx, rf)) > (float)(o.w - 2)) ||
                             (floorf(__fsub_rn(fy, rf)) < 1.0f) ||
                             (ceilf(__fadd_rn(fy, rf)) > (float)(o.h - 2));
-        if (reject || kp.scale < 1 || kp.scale > kScales) {
+        const int r = (int)rf;
+        const int side = 2 * r + 1;
+        if (reject || kp.scale < 1 || kp.scale > kScales || side > kOriMaxSide || !(rf >= 0.0f)) {
             if (lane == 0) nOri[k] = 0;
             continue;
         }
@@ -55,28 +61,31 @@ orientationKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __
         const int x = (int)roundf(__fdiv_rn((float)(int)kp.absoluteX, o.delta));
         const int y = (int)roundf(__fdiv_rn((float)(int)kp.absoluteY, o.delta));
         const float expDen = __fmul_rn(__fmul_rn(2.0f, lambda), lambda);
-        const int r = (int)rf;
-        const int side = 2 * r + 1;
         const float2* __restrict__ g =
             o.grad + ((size_t)frame * kScales + (kp.scale - 1)) * o.plane;
 
+        // w(i, j) = exp(-((i/s)^2 + (j/s)^2) / (2 lambda^2)) evaluated as the product of two 1-D
+        // factors (continuous quantity: differs from the oracle's single exp in the last bits)
+        for (int t = lane; t < side; t += 32) {
+            const float u = __fdiv_rn((float)(t - r), sigma);
+            wt[t] = dm_expf(__fdiv_rn(-__fmul_rn(u, u), expDen));
+        }
 #pragma unroll
         for (int b = 0; b < kOriBins; b++) hist[b * 32 + lane] = 0.0f;
+        __syncwarp();
+        const float invSide = 1.0f / (float)side;
         for (int idx = lane; idx < side * side; idx += 32) {
-            const int jj = idx / side;
-            const int j = jj - r, i = idx - jj * side - r;
-            const int sx = x + i, sy = y + j;
+            const int jj = (int)(((float)idx + 0.5f) * invSide);
+            const int ii = idx - jj * side;
+            const int sx = x + ii - r, sy = y + jj - r;
             if (sx < 0 || sx >= o.w || sy < 0 || sy >= o.h) continue;
-            const float u = __fdiv_rn((float)i, sigma);
-            const float v = __fdiv_rn((float)j, sigma);
-            const float r2 = __fadd_rn(__fmul_rn(u, u), __fmul_rn(v, v));
-            const float w = dm_expf(__fdiv_rn(-r2, expDen));
             const float2 gm = __ldg(g + (size_t)sy * o.pitch + sx);
+            // bin index: discontinuous → the spec's exact sequence
             const float t = __fdiv_rn(gm.x, kTau);
             int bin = (int)roundf(__fmul_rn(t, (float)kOriBins));
             if (bin < 0) bin += kOriBins;
             if (bin >= kOriBins) bin -= kOriBins;
-            hist[bin * 32 + lane] += __fmul_rn(w, gm.y);
+            hist[bin * 32 + lane] += (wt[ii] * wt[jj]) * gm.y;
         }
         __syncwarp();
         // reduce the 32 lane-private copies of each bin, rotated start → conflict-free
@@ -84,6 +93,7 @@ orientationKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __
         float* h1 = sH[wid][1];
         for (int b = lane; b < kOriBins; b += 32) {
             float s = 0.0f;
+#pragma unroll 8
             for (int l = 0; l < 32; l++) s += hist[b * 32 + ((l + lane) & 31)];
             h0[b] = s;
         }
@@ -172,7 +182,16 @@ __global__ void descSegmentStartsKernel(const int* __restrict__ segKpStart,
 }
 
 // ------------------------------------------------------------------------------------------
-constexpr int kDescWarps = 4;  // 4 warps x 16 KB of lane-private histograms = 64 KB per CTA
+// Descriptor. One warp per (keypoint, theta). The reference walks the whole (2·radius+1)^2
+// window and lets addValue drop what falls outside the 4x4 grid (SIFTDescriptor.metal:53-79);
+// only samples inside the rotated square |rx|, |ry| < 2.5 can contribute, so each window row's
+// contributing span is computed analytically (widened by one pixel, then culled by the same
+// test the reference's cell bounds imply) and the lanes walk the flattened spans densely.
+// Window radius, sample coordinates and centre truncation follow the spec's exact sequences;
+// per-sample weights use FMA / reciprocal / ex2.approx — continuous quantities within the ±1
+// tolerance of the quantised features.
+constexpr int kDescWarps = 4;      // 4 warps x 16 KB of lane-private histograms = 64 KB per CTA
+constexpr int kDescMaxSide = 128;  // 2·radius+1; radius <= 39 for detected keypoints
 
 __global__ void __launch_bounds__(kDescWarps * 32)
 descriptorKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __restrict__ kps,
@@ -181,8 +200,12 @@ descriptorKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __r
                  const float* __restrict__ oriTmp, SiftDescriptor* __restrict__ desc,
                  int capacity) {
     extern __shared__ __align__(16) float sDesc[];  // [warp][128 bins][32 lanes]
+    __shared__ int sRowStart[kDescWarps][kDescMaxSide + 1];
+    __shared__ int sRowLo[kDescWarps][kDescMaxSide];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     float* hist = sDesc + wid * (128 * 32);
+    int* rowStart = sRowStart[wid];
+    int* rowLo = sRowLo[wid];
     const int nKp = counters->nKeypoints;
     int nDesc = oriOffset[nKp];
     if (nDesc > capacity) nDesc = capacity;
@@ -196,38 +219,87 @@ descriptorKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __r
         }
         const int k = lo;
         const SiftKeypoint kp = kps[k];
-        const int seg = kpSeg[k];
-        const int frame = seg / kOctaves;
+        const int frame = kpSeg[k] / kOctaves;
         const float theta = oriTmp[(size_t)k * kOriBins + (d - oriOffset[k])];
         const OctaveDev& o = P.oct[kp.octave];
         const float2* __restrict__ g =
             o.grad + ((size_t)frame * kScales + (kp.scale - 1)) * o.plane;
 
-        // SIFTDescriptor.metal:137-166, inputs truncated as SIFTOctave.swift:417-418
+        // SIFTDescriptor.metal:137-166 (exact sequences), inputs truncated as SIFTOctave.swift:417-418
         const float px = __fdiv_rn((float)(int)kp.absoluteX, o.delta);
         const float py = __fdiv_rn((float)(int)kp.absoluteY, o.delta);
         float sinT, cosT;
         dm_sincosf(theta, &sinT, &cosT);
-        const float binsPerRadian = __fdiv_rn(8.0f, kTau);
         const float interval = __fadd_rn((float)kp.scale, kp.subScale);
         const float scale = __fmul_rn(1.6f, dm_exp2f(__fdiv_rn(interval, 3.0f)));
         const float hw = __fmul_rn(3.0f, scale);
-        const int radius = (int)__fadd_rn(
+        int radius = (int)__fadd_rn(
             __fmul_rn(__fmul_rn(__fmul_rn(hw, sqrtf(2.0f)), 5.0f), 0.5f), 0.5f);
+        radius = max(0, min(radius, (kDescMaxSide - 1) / 2));
         const int side = 2 * radius + 1;
+        const float a = cosT / hw, b = sinT / hw;   // rx = j a - i b, ry = j b + i a
 
+        // contributing span of every window row j (x offset): |rx| < 2.5 and |ry| < 2.5
+        int cnt[kDescMaxSide / 32];
+#pragma unroll
+        for (int q = 0; q < kDescMaxSide / 32; q++) {
+            const int jj = q * 32 + lane;
+            int c = 0;
+            if (jj < side) {
+                const float fj = (float)(jj - radius);
+                float lo1 = -1e30f, hi1 = 1e30f, lo2 = -1e30f, hi2 = 1e30f;
+                bool empty = false;
+                if (fabsf(b) > 1e-6f) {   // i b in (j a - 2.5, j a + 2.5)
+                    const float p = (fj * a - 2.5f) / b, q2 = (fj * a + 2.5f) / b;
+                    lo1 = fminf(p, q2); hi1 = fmaxf(p, q2);
+                } else if (!(fabsf(fj * a) < 2.5f + 1e-3f)) empty = true;
+                if (fabsf(a) > 1e-6f) {   // i a in (-2.5 - j b, 2.5 - j b)
+                    const float p = (-2.5f - fj * b) / a, q2 = (2.5f - fj * b) / a;
+                    lo2 = fminf(p, q2); hi2 = fmaxf(p, q2);
+                } else if (!(fabsf(fj * b) < 2.5f + 1e-3f)) empty = true;
+                // widened by < 1 on each side by the floor / ceil; the loop culls exactly.
+                // Image rows: sample y = trunc(py + i) must lie in [0, h).
+                const float flo = fmaxf(fmaxf(fmaxf(lo1, lo2), -(float)radius), -py);
+                const float fhi = fminf(fminf(fminf(hi1, hi2), (float)radius), (float)o.h - py);
+                const int ilo = (int)floorf(flo), ihi = (int)ceilf(fhi);
+                c = (empty || ihi < ilo) ? 0 : ihi - ilo + 1;
+                rowLo[jj] = ilo;
+#ifdef SIFT_DEBUG_DESC
+                if (d == 0 && (lane == 0 || lane == 21)) printf("SPAN lane=%d q=%d jj=%d fj=%g lo1=%g hi1=%g lo2=%g hi2=%g flo=%g fhi=%g ilo=%d ihi=%d empty=%d c=%d oh=%d py=%g\n", lane, q, jj, fj, lo1, hi1, lo2, hi2, flo, fhi, ilo, ihi, (int)empty, c, o.h, py);
+#endif
+            }
+            cnt[q] = c;
+        }
+        int base = 0;
+#pragma unroll
+        for (int q = 0; q < kDescMaxSide / 32; q++) {
+            int inc = cnt[q];
+#pragma unroll
+            for (int dd = 1; dd < 32; dd <<= 1) {
+                const int nb = __shfl_up_sync(0xffffffffu, inc, dd);
+                if (lane >= dd) inc += nb;
+            }
+            const int jj = q * 32 + lane;
+            if (jj < side) rowStart[jj] = base + inc - cnt[q];
+            base += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        const int total = base;
+        if (lane == 0) rowStart[side] = total;
+#ifdef SIFT_DEBUG_DESC
+        if (d == 0 && lane == 0) printf("DESC0 side=%d radius=%d total=%d a=%g b=%g hw=%g px=%g py=%g cnt0=%d cnt1=%d\n", side, radius, total, a, b, hw, px, py, cnt[0], cnt[1]);
+#endif
 #pragma unroll 8
-        for (int b = 0; b < 128; b++) hist[b * 32 + lane] = 0.0f;
+        for (int bb = 0; bb < 128; bb++) hist[bb * 32 + lane] = 0.0f;
+        __syncwarp();
 
-        for (int idx = lane; idx < side * side; idx += 32) {
-            const int jj = idx / side;
-            const int j = jj - radius;             // x offset (outer loop of the reference)
-            const int i = idx - jj * side - radius;  // y offset
-            const float fj = (float)j, fi = (float)i;
-            const float rx = __fdiv_rn(__fsub_rn(__fmul_rn(fj, cosT), __fmul_rn(fi, sinT)), hw);
-            const float ry = __fdiv_rn(__fadd_rn(__fmul_rn(fj, sinT), __fmul_rn(fi, cosT)), hw);
-            const float bx = __fsub_rn(__fadd_rn(rx, 2.0f), 0.5f);
-            const float by = __fsub_rn(__fadd_rn(ry, 2.0f), 0.5f);
+        int row = 0;
+        for (int idx = lane; idx < total; idx += 32) {
+            while (idx >= rowStart[row + 1]) row++;
+            const int i = rowLo[row] + (idx - rowStart[row]);   // y offset
+            const float fj = (float)(row - radius), fi = (float)i;
+            const float rx = fj * a - fi * b;
+            const float ry = fj * b + fi * a;
+            const float bx = rx + 1.5f, by = ry + 1.5f;
             // addValue drops cells outside [0, 4): nothing lands unless -1 < b < 4 on both axes
             if (!(bx > -1.0f && bx < 4.0f && by > -1.0f && by < 4.0f)) continue;
             const float cxf = __fadd_rn(px, fj), cyf = __fadd_rn(py, fi);
@@ -235,43 +307,54 @@ descriptorKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __r
             const int sx = (int)cxf, sy = (int)cyf;
             if (sx >= o.w || sy >= o.h) continue;
             const float2 gm = __ldg(g + (size_t)sy * o.pitch + sx);
-            float orientation = __fsub_rn(gm.x, theta);
-            while (orientation < 0.0f) orientation = __fadd_rn(orientation, kTau);
-            while (orientation >= kTau) orientation = __fsub_rn(orientation, kTau);
-            const float bin = __fmul_rn(orientation, binsPerRadian);
-            const float en = __fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry));
-            const float w = dm_expf(__fdiv_rn(-en, 8.0f));
-            const float value = __fmul_rn(gm.y, w);
-
-            // addFeature (:82-117): trilinear spread over floor/ceil cells and bins
-            const float flx = floorf(bx), fly = floorf(by), flb = floorf(bin);
-            const int x0 = (int)flx, x1 = (int)ceilf(bx);
-            const int y0 = (int)fly, y1 = (int)ceilf(by);
-            int b0 = (int)flb, b1 = (int)ceilf(bin);
-            if (b0 >= 8) b0 -= 8;
-            if (b1 >= 8) b1 -= 8;
-            const float iMax = __fsub_rn(bx, flx), iMin = __fsub_rn(1.0f, iMax);
-            const float jMax = __fsub_rn(by, fly), jMin = __fsub_rn(1.0f, jMax);
-            const float bMax = __fsub_rn(bin, flb), bMin = __fsub_rn(1.0f, bMax);
-            const bool vx0 = (x0 >= 0) && (x0 < 4), vx1 = (x1 >= 0) && (x1 < 4);
-            const bool vy0 = (y0 >= 0) && (y0 < 4), vy1 = (y1 >= 0) && (y1 < 4);
-#define SIFT_ADD(cx, cy, cb, wx, wy, wb)                                                     \
-    hist[(((cy) * 4 + (cx)) * 8 + (cb)) * 32 + lane] +=                                      \
-        __fmul_rn(__fmul_rn(__fmul_rn(wx, wy), wb), value)
-            if (vx0 && vy0) { SIFT_ADD(x0, y0, b0, iMin, jMin, bMin); SIFT_ADD(x0, y0, b1, iMin, jMin, bMax); }
-            if (vx1 && vy0) { SIFT_ADD(x1, y0, b0, iMax, jMin, bMin); SIFT_ADD(x1, y0, b1, iMax, jMin, bMax); }
-            if (vx1 && vy1) { SIFT_ADD(x1, y1, b0, iMax, jMax, bMin); SIFT_ADD(x1, y1, b1, iMax, jMax, bMax); }
-            if (vx0 && vy1) { SIFT_ADD(x0, y1, b0, iMin, jMax, bMin); SIFT_ADD(x0, y1, b1, iMin, jMax, bMax); }
-#undef SIFT_ADD
+            float ori = gm.x - theta;                 // in (-3 pi, pi]
+            ori += (ori < 0.0f) ? kTau : 0.0f;
+            ori += (ori < 0.0f) ? kTau : 0.0f;
+            ori -= (ori >= kTau) ? kTau : 0.0f;
+            const float bin = ori * (8.0f / kTau);
+            const int bi = (int)bin;                   // bin >= 0: truncation = floor
+            const float fb = bin - (float)bi;
+            const int b0 = bi & 7, b1 = (bi + 1) & 7;
+            const float w = __expf(-(rx * rx + ry * ry) * 0.125f);
+            const float val = gm.y * w;
+#ifdef SIFT_DEBUG_DESC
+            if (d == 0 && idx < 64) printf("  idx=%d row=%d i=%d bx=%g by=%g sx=%d sy=%d mag=%g w=%g bin=%g\n", idx, row, i, bx, by, sx, sy, gm.y, w, bin);
+#endif
+            const int x0 = __float2int_rd(bx), y0 = __float2int_rd(by);
+            const float fxw = bx - (float)x0, fyw = by - (float)y0;
+            // trilinear spread (addFeature, :82-117). ceil = floor + 1 except on exact integers,
+            // where the reference adds a zero weight to the floor cell — same sums either way.
+            const float vx0 = val * (1.0f - fxw), vx1 = val * fxw;
+            const float v00 = vx0 * (1.0f - fyw), v01 = vx0 * fyw;
+            const float v10 = vx1 * (1.0f - fyw), v11 = vx1 * fyw;
+            const bool okx0 = (x0 >= 0), okx1 = (x0 < 3), oky0 = (y0 >= 0), oky1 = (y0 < 3);
+            float* h00 = hist + ((y0 * 4 + x0) * 8) * 32 + lane;   // cell (x0, y0), bin 0
+            float* h10 = h00 + 8 * 32;                              // (x0+1, y0)
+            float* h01 = h00 + 4 * 8 * 32;                          // (x0, y0+1)
+            float* h11 = h01 + 8 * 32;                              // (x0+1, y0+1)
+            const int o0 = b0 * 32, o1 = b1 * 32;
+            const float g0 = 1.0f - fb;
+            // the eight addresses are distinct: load all, add, store all
+            float t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0, t6 = 0, t7 = 0;
+            const bool c00 = okx0 && oky0, c10 = okx1 && oky0, c01 = okx0 && oky1, c11 = okx1 && oky1;
+            if (c00) { t0 = h00[o0]; t1 = h00[o1]; }
+            if (c10) { t2 = h10[o0]; t3 = h10[o1]; }
+            if (c01) { t4 = h01[o0]; t5 = h01[o1]; }
+            if (c11) { t6 = h11[o0]; t7 = h11[o1]; }
+            if (c00) { h00[o0] = t0 + v00 * g0; h00[o1] = t1 + v00 * fb; }
+            if (c10) { h10[o0] = t2 + v10 * g0; h10[o1] = t3 + v10 * fb; }
+            if (c01) { h01[o0] = t4 + v01 * g0; h01[o1] = t5 + v01 * fb; }
+            if (c11) { h11[o0] = t6 + v11 * g0; h11[o1] = t7 + v11 * fb; }
         }
         __syncwarp();
         // reduce lane-private copies: lane owns bins lane, lane+32, lane+64, lane+96
         float f[4];
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            const int b = q * 32 + lane;
+            const int bb = q * 32 + lane;
             float s = 0.0f;
-            for (int l = 0; l < 32; l++) s += hist[b * 32 + ((l + lane) & 31)];
+#pragma unroll 8
+            for (int l = 0; l < 32; l++) s += hist[bb * 32 + ((l + lane) & 31)];
             f[q] = s;
         }
         // normalize → clip 0.2 → normalize → quantize (SIFTDescriptor.metal:15-50, 227-230)

@@ -14,54 +14,111 @@
 namespace sift {
 
 // ------------------------------------------------------------------------------------------
-// Extrema → bitmask. One thread per (x, y); a warp covers 32 consecutive x and emits one
-// ballot word per scale. Candidate iff strictly below the minimum or above the maximum of
-// neighbours 1..25 of the reference's table (SIFTExtrema.metal:15-45; neighbour 0 =
-// (-1,-1,-1) is skipped at :84) AND |v| > 0.8·C_DoG (first test of siftInterpolate,
-// SIFTInterpolate.metal:208 — fusing it here is result-neutral and lets most pixels exit after
-// three coalesced loads).
-__global__ void __launch_bounds__(256)
+// Extrema → bitmask. A warp owns 32 consecutive x (one mask word) and marches down kExtRows
+// output rows holding a 3-row window of all 5 DoG slices in registers: per new row and slice
+// one coalesced load + two shuffles give (left, centre, right); row-wise partial minima /
+// maxima are kept so every 3x3 block needs 2-3 more min/max. Candidate iff strictly below the
+// minimum or above the maximum of neighbours 1..25 of the reference's table
+// (SIFTExtrema.metal:15-45; neighbour 0 = (-1,-1,-1) is skipped at :84 — hence the `cr`
+// partials that leave the left pixel of the row above in the slice below out) AND
+// |v| > 0.8·C_DoG (first test of siftInterpolate, SIFTInterpolate.metal:208; fusing it here is
+// result-neutral). min/max are exact, so evaluation order is free.
+constexpr int kExtRows = 30;    // output rows per warp (32 rows loaded)
+constexpr int kExtWarps = 8;
+
+struct RowPart {
+    float c;          // centre
+    float h3n, h3x;   // min / max of (left, centre, right)
+    float lrn, lrx;   // min / max of (left, right)
+    float crn, crx;   // min / max of (centre, right)
+};
+
+// Raw values of one row of the five slices: the lane's own pixel and, for lanes 0 / 31, the
+// pixel just outside the warp's 32 columns (other lanes re-read their own pixel: same cache
+// line, no divergence). All ten loads of a row are independent and issued back to back.
+struct RowRaw {
+    float c[kDogs], e[kDogs];
+};
+
+__device__ __forceinline__ RowRaw loadRowRaw(const float* __restrict__ D, size_t plane, size_t rowOff,
+                                             int x, int ex) {
+    RowRaw r;
+#pragma unroll
+    for (int t = 0; t < kDogs; t++) {
+        const float* __restrict__ row = D + (size_t)t * plane + rowOff;
+        r.c[t] = __ldg(row + x);
+        r.e[t] = __ldg(row + ex);
+    }
+    return r;
+}
+
+__device__ __forceinline__ RowPart makeRowPart(float c, float e, int lane) {
+    float l = __shfl_up_sync(0xffffffffu, c, 1);
+    float r = __shfl_down_sync(0xffffffffu, c, 1);
+    if (lane == 0) l = e;
+    if (lane == 31) r = e;
+    RowPart p;
+    p.c = c;
+    p.lrn = fminf(l, r);
+    p.lrx = fmaxf(l, r);
+    p.crn = fminf(c, r);
+    p.crx = fmaxf(c, r);
+    p.h3n = fminf(l, p.crn);
+    p.h3x = fmaxf(l, p.crx);
+    return p;
+}
+
+__global__ void __launch_bounds__(kExtWarps * 32)
 extremaMaskKernel(const OctaveDev o, float softThreshold, uint32_t* __restrict__ mask,
                   int blocksPerFrame) {
-    const int x = blockIdx.x * 256 + threadIdx.x;
-    const int y = blockIdx.y;
-    const int f = blockIdx.z;
     const int lane = threadIdx.x & 31;
-    const int xw = x >> 5;
-    if (xw >= o.maskRowWords) return;  // whole warp exits together (x is warp-aligned)
+    const int xw = blockIdx.x * kExtWarps + (threadIdx.x >> 5);
+    if (xw >= o.maskRowWords) return;  // whole warp
+    const int x = xw * 32 + lane;      // < pitch: readable even beyond w (masked below)
+    const int ex = (lane == 0) ? max(x - 1, 0) : ((lane == 31) ? min(x + 1, o.w - 1) : x);
+    const int yFirst = 1 + blockIdx.y * kExtRows;          // first output row of this warp
+    const int f = blockIdx.z;
     const float* __restrict__ D = o.D + (size_t)f * kDogs * o.plane;
     uint32_t* __restrict__ m =
         mask + ((size_t)f * blocksPerFrame + o.maskBlockStart) * (size_t)kScanChunk;
-    const bool inside = (x >= 1) && (x <= o.w - 2) && (y >= 1) && (y <= o.h - 2);
-    const size_t c = (size_t)y * o.pitch + x;
+    const bool xInside = (x >= 1) && (x <= o.w - 2);
+
+    RowPart win[kDogs][3];  // [slice][row slot]; slots rotate statically (loop unrolled by 3)
+    auto rowOffset = [&](int y) { return (size_t)min(y, o.h - 1) * o.pitch; };
+    {
+        const RowRaw r0 = loadRowRaw(D, o.plane, rowOffset(yFirst - 1), x, ex);
+        const RowRaw r1 = loadRowRaw(D, o.plane, rowOffset(yFirst), x, ex);
 #pragma unroll
-    for (int s = 1; s <= kScales; s++) {
-        bool cand = false;
-        if (inside) {
-            const float* __restrict__ p = D + (size_t)s * o.plane + c;
-            const float v = __ldg(p);
-            if (!(fabsf(v) <= softThreshold)) {
-                float mn = +1000.0f, mx = -1000.0f;
+        for (int t = 0; t < kDogs; t++) {
+            win[t][0] = makeRowPart(r0.c[t], r0.e[t], lane);
+            win[t][1] = makeRowPart(r1.c[t], r1.e[t], lane);
+        }
+    }
+    RowRaw ahead = loadRowRaw(D, o.plane, rowOffset(yFirst + 1), x, ex);   // software pipeline
+    for (int r0 = 0; r0 < kExtRows; r0 += 3) {
 #pragma unroll
-                for (int ds = -1; ds <= 1; ds++) {
+        for (int k = 0; k < 3; k++) {
+            const int y = yFirst + r0 + k;
+            const int prev = k % 3, cur = (k + 1) % 3, next = (k + 2) % 3;
+            if (y > o.h - 2) return;  // warp-uniform
+            const RowRaw now = ahead;
+            ahead = loadRowRaw(D, o.plane, rowOffset(y + 2), x, ex);       // consumed next iteration
 #pragma unroll
-                    for (int dy = -1; dy <= 1; dy++) {
+            for (int t = 0; t < kDogs; t++) win[t][next] = makeRowPart(now.c[t], now.e[t], lane);
 #pragma unroll
-                        for (int dx = -1; dx <= 1; dx++) {
-                            if (ds == 0 && dy == 0 && dx == 0) continue;       // the centre
-                            if (ds == -1 && dy == -1 && dx == -1) continue;    // neighbour 0
-                            const float nv = __ldg(p + (ptrdiff_t)ds * (ptrdiff_t)o.plane +
-                                                   (ptrdiff_t)dy * o.pitch + dx);
-                            mn = fminf(mn, nv);
-                            mx = fmaxf(mx, nv);
-                        }
-                    }
-                }
-                cand = (v < mn) || (v > mx);
+            for (int s = 1; s <= kScales; s++) {
+                const float v = win[s][cur].c;
+                float mn = fminf(fminf(win[s][prev].h3n, win[s][next].h3n), win[s][cur].lrn);
+                float mx = fmaxf(fmaxf(win[s][prev].h3x, win[s][next].h3x), win[s][cur].lrx);
+                mn = fminf(mn, fminf(fminf(win[s + 1][prev].h3n, win[s + 1][cur].h3n), win[s + 1][next].h3n));
+                mx = fmaxf(mx, fmaxf(fmaxf(win[s + 1][prev].h3x, win[s + 1][cur].h3x), win[s + 1][next].h3x));
+                mn = fminf(mn, fminf(fminf(win[s - 1][prev].crn, win[s - 1][cur].h3n), win[s - 1][next].h3n));
+                mx = fmaxf(mx, fmaxf(fmaxf(win[s - 1][prev].crx, win[s - 1][cur].h3x), win[s - 1][next].h3x));
+                const bool cand = xInside && !(fabsf(v) <= softThreshold) && ((v < mn) || (v > mx));
+                const uint32_t word = __ballot_sync(0xffffffffu, cand);
+                if (lane == 0) m[((size_t)(s - 1) * o.h + y) * o.maskRowWords + xw] = word;
             }
         }
-        const uint32_t word = __ballot_sync(0xffffffffu, cand);
-        if (lane == 0) m[((size_t)(s - 1) * o.h + y) * o.maskRowWords + xw] = word;
     }
 }
 
@@ -69,8 +126,8 @@ cudaError_t launchExtremaMask(const EngineParams& P, int octave, uint32_t* mask,
                               cudaStream_t st) {
     const OctaveDev& o = P.oct[octave];
     if (o.w < 3 || o.h < 3) return cudaSuccess;
-    dim3 grid((o.maskRowWords * 32 + 255) / 256, o.h, frames);
-    extremaMaskKernel<<<grid, 256, 0, st>>>(o, P.dogThreshold * 0.8f, mask, P.blocksPerFrame);
+    dim3 grid((o.maskRowWords + kExtWarps - 1) / kExtWarps, (o.h - 2 + kExtRows - 1) / kExtRows, frames);
+    extremaMaskKernel<<<grid, kExtWarps * 32, 0, st>>>(o, P.dogThreshold * 0.8f, mask, P.blocksPerFrame);
     return cudaGetLastError();
 }
 
@@ -283,119 +340,106 @@ __device__ __forceinline__ bool outOfBounds(int x, int y, int s, int w, int h, i
            s > kScales;
 }
 
-// One thread per candidate, grid-stride by warps so that each warp can ballot its converged
-// flags into one word (index-aligned with the candidate list, hence still canonical order).
-__global__ void __launch_bounds__(256)
+// One thread per candidate; a CTA of 256 threads owns 256 consecutive candidates, ballots the
+// converged flags into 8 words and publishes its count, so the following scan + scatter keep the
+// canonical candidate order and every thread copies at most one keypoint.
+constexpr int kRefineThreads = 256;
+
+__global__ void __launch_bounds__(kRefineThreads)
 refineKernel(const __grid_constant__ EngineParams P, const Candidate* __restrict__ cands,
              const Counters* __restrict__ counters, SiftKeypoint* __restrict__ kpTmp,
-             uint32_t* __restrict__ flagWords) {
+             uint32_t* __restrict__ flagWords, int* __restrict__ blockSums) {
+    __shared__ int warpCount[kRefineThreads / 32];
     const int n = counters->nCandidates;
-    const int lane = threadIdx.x & 31;
-    const int warpsTotal = (gridDim.x * blockDim.x) >> 5;
-    for (int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; base < n;
-         base += warpsTotal * 32) {
-        const int i = base + lane;
-        bool ok = false;
-        if (i < n) {
-            const Candidate cd = cands[i];
-            const int frame = cd.seg / kOctaves, oc = cd.seg - frame * kOctaves;
-            const OctaveDev& o = P.oct[oc];
-            DogView t;
-            t.base = o.D + (size_t)frame * kDogs * o.plane;
-            t.plane = o.plane;
-            t.pitch = o.pitch;
-            int x = cd.xys & 0x7fff, y = (cd.xys >> 15) & 0x7fff, s = cd.xys >> 30;
-            // the 0.8·C_DoG test (SIFTInterpolate.metal:208) already held in the extrema kernel
-            if (!outOfBounds(x, y, s, o.w, o.h, P.border)) {
-                bool converged = false, alive = true;
-                V3 alpha = {0, 0, 0}, dD = {0, 0, 0};
-                int it = 0;
-                while (it < P.maxIterations) {
-                    alpha = interpolationStep(t, x, y, s, &dD);
-                    if ((fabsf(alpha.x) < P.maxOffset) && (fabsf(alpha.y) < P.maxOffset) &&
-                        (fabsf(alpha.z) < P.maxOffset)) {
-                        converged = true;
-                        break;
-                    }
-                    if (alpha.x > +P.maxOffset) x += 1;
-                    if (alpha.x < -P.maxOffset) x -= 1;
-                    if (alpha.y > +P.maxOffset) y += 1;
-                    if (alpha.y < -P.maxOffset) y -= 1;
-                    if (alpha.z > +P.maxOffset) s += 1;
-                    if (alpha.z < -P.maxOffset) s -= 1;
-                    if (outOfBounds(x, y, s, o.w, o.h, P.border)) {
-                        alive = false;
-                        break;
-                    }
-                    it += 1;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int i = blockIdx.x * kRefineThreads + threadIdx.x;
+    bool ok = false;
+    if (i < n) {
+        const Candidate cd = cands[i];
+        const int frame = cd.seg / kOctaves, oc = cd.seg - frame * kOctaves;
+        const OctaveDev& o = P.oct[oc];
+        DogView t;
+        t.base = o.D + (size_t)frame * kDogs * o.plane;
+        t.plane = o.plane;
+        t.pitch = o.pitch;
+        int x = cd.xys & 0x7fff, y = (cd.xys >> 15) & 0x7fff, s = cd.xys >> 30;
+        // the 0.8·C_DoG test (SIFTInterpolate.metal:208) already held in the extrema kernel
+        if (!outOfBounds(x, y, s, o.w, o.h, P.border)) {
+            bool converged = false, alive = true;
+            V3 alpha = {0, 0, 0}, dD = {0, 0, 0};
+            int it = 0;
+            while (it < P.maxIterations) {
+                alpha = interpolationStep(t, x, y, s, &dD);
+                if ((fabsf(alpha.x) < P.maxOffset) && (fabsf(alpha.y) < P.maxOffset) &&
+                    (fabsf(alpha.z) < P.maxOffset)) {
+                    converged = true;
+                    break;
                 }
-                if (alive && converged) {
-                    // interpolateContrast (:90-100): v + 0.5·(dD.x·alpha.x) — x term only
-                    const float value = t.at(x, y, s) + ((dD.x * alpha.x) * 0.5f);
-                    if (!(fabsf(value) <= P.dogThreshold) &&
-                        !isOnEdge(t, x, y, s, P.edgeThreshold)) {
-                        SiftKeypoint k;
-                        k.octave = oc;
-                        k.scale = s;
-                        k.subScale = alpha.z;
-                        k.scaledX = x;
-                        k.scaledY = y;
-                        k.absoluteX = ((float)x + alpha.x) * o.delta;
-                        k.absoluteY = ((float)y + alpha.y) * o.delta;
-                        k.normalizedX = (float)x / (float)o.w;
-                        k.normalizedY = (float)y / (float)o.h;
-                        k.sigma = o.sigmas[s] * dm_exp2f(alpha.z * o.log2SigmaRatio);
-                        k.value = value;
-                        kpTmp[i] = k;
-                        ok = true;
-                    }
+                if (alpha.x > +P.maxOffset) x += 1;
+                if (alpha.x < -P.maxOffset) x -= 1;
+                if (alpha.y > +P.maxOffset) y += 1;
+                if (alpha.y < -P.maxOffset) y -= 1;
+                if (alpha.z > +P.maxOffset) s += 1;
+                if (alpha.z < -P.maxOffset) s -= 1;
+                if (outOfBounds(x, y, s, o.w, o.h, P.border)) {
+                    alive = false;
+                    break;
+                }
+                it += 1;
+            }
+            if (alive && converged) {
+                // interpolateContrast (:90-100): v + 0.5·(dD.x·alpha.x) — x term only
+                const float value = t.at(x, y, s) + ((dD.x * alpha.x) * 0.5f);
+                if (!(fabsf(value) <= P.dogThreshold) && !isOnEdge(t, x, y, s, P.edgeThreshold)) {
+                    SiftKeypoint k;
+                    k.octave = oc;
+                    k.scale = s;
+                    k.subScale = alpha.z;
+                    k.scaledX = x;
+                    k.scaledY = y;
+                    k.absoluteX = ((float)x + alpha.x) * o.delta;
+                    k.absoluteY = ((float)y + alpha.y) * o.delta;
+                    k.normalizedX = (float)x / (float)o.w;
+                    k.normalizedY = (float)y / (float)o.h;
+                    k.sigma = o.sigmas[s] * dm_exp2f(alpha.z * o.log2SigmaRatio);
+                    k.value = value;
+                    kpTmp[i] = k;
+                    ok = true;
                 }
             }
         }
-        const uint32_t word = __ballot_sync(0xffffffffu, ok);
-        if (lane == 0) flagWords[base >> 5] = word;
+    }
+    const uint32_t word = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) {
+        flagWords[i >> 5] = word;
+        warpCount[wid] = __popc(word);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int total = 0;
+#pragma unroll
+        for (int k = 0; k < kRefineThreads / 32; k++) total += warpCount[k];
+        blockSums[blockIdx.x] = total;
     }
 }
 
-struct FlagPopc {
-    const uint32_t* flags;
-    const Counters* counters;
-    __device__ int operator()(int i) const {
-        const int nWords = (counters->nCandidates + 31) >> 5;
-        return i < nWords ? __popc(flags[i]) : 0;
-    }
-};
-
-__global__ void __launch_bounds__(kScanThreads)
+__global__ void __launch_bounds__(kRefineThreads)
 scatterKeypointsKernel(const uint32_t* __restrict__ flags, const Counters* __restrict__ counters,
                        const int* __restrict__ blockOffsets, const Candidate* __restrict__ cands,
                        const SiftKeypoint* __restrict__ kpTmp, SiftKeypoint* __restrict__ kps,
                        int* __restrict__ kpSeg, int capacity) {
-    __shared__ int sh[9];
-    const int nWords = (counters->nCandidates + 31) >> 5;
-    const int w0 = blockIdx.x * kScanChunk + threadIdx.x * kScanItemsPerThread;
-    uint32_t words[kScanItemsPerThread];
-    int s = 0;
-#pragma unroll
-    for (int k = 0; k < kScanItemsPerThread; k++) {
-        words[k] = (w0 + k) < nWords ? flags[w0 + k] : 0u;
-        s += __popc(words[k]);
-    }
-    int total;
-    int pos = blockOffsets[blockIdx.x] + blockExclusiveScan256(s, sh, &total);
-#pragma unroll
-    for (int k = 0; k < kScanItemsPerThread; k++) {
-        uint32_t wbits = words[k];
-        while (wbits) {
-            const int bit = __ffs(wbits) - 1;
-            wbits &= wbits - 1;
-            const int i = (w0 + k) * 32 + bit;
-            if (pos < capacity) {
-                kps[pos] = kpTmp[i];
-                kpSeg[pos] = cands[i].seg;
-            }
-            pos++;
-        }
+    const int n = counters->nCandidates;
+    const int i = blockIdx.x * kRefineThreads + threadIdx.x;
+    if (blockIdx.x * kRefineThreads >= n) return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t* __restrict__ w = flags + blockIdx.x * (kRefineThreads / 32);
+    const uint32_t mine = w[wid];
+    if (!((mine >> lane) & 1u)) return;
+    int pos = blockOffsets[blockIdx.x] + __popc(mine & ((1u << lane) - 1u));
+    for (int k = 0; k < wid; k++) pos += __popc(w[k]);
+    if (pos < capacity) {
+        kps[pos] = kpTmp[i];
+        kpSeg[pos] = cands[i].seg;
     }
 }
 
@@ -448,17 +492,14 @@ cudaError_t launchRefine(const EngineParams& P, const Candidate* cands, int capC
                          int* segKpStart, int nSegs, Counters* counters, int smCount,
                          cudaStream_t st) {
     (void)segKpCount;
-    refineKernel<<<smCount * 8, 256, 0, st>>>(P, cands, counters, kpTmp, flagWords);
-    SIFT_CUDA_TRY(cudaGetLastError());
-    const int capWords = (capCandidates + 31) / 32;
-    const int nBlocks = (capWords + kScanChunk - 1) / kScanChunk;
-    FlagPopc v{flagWords, counters};
-    scanBlockSumsKernel<<<nBlocks, kScanThreads, 0, st>>>(v, blockSums);
+    (void)smCount;
+    const int nBlocks = (capCandidates + kRefineThreads - 1) / kRefineThreads;
+    refineKernel<<<nBlocks, kRefineThreads, 0, st>>>(P, cands, counters, kpTmp, flagWords, blockSums);
     SIFT_CUDA_TRY(cudaGetLastError());
     SIFT_CUDA_TRY(launchScanOffsets(blockSums, nBlocks, &counters->nKeypoints, capKeypoints,
                                     &counters->overflow, 2, st));
-    scatterKeypointsKernel<<<nBlocks, kScanThreads, 0, st>>>(flagWords, counters, blockSums, cands,
-                                                            kpTmp, kps, kpSeg, capKeypoints);
+    scatterKeypointsKernel<<<nBlocks, kRefineThreads, 0, st>>>(flagWords, counters, blockSums, cands,
+                                                              kpTmp, kps, kpSeg, capKeypoints);
     SIFT_CUDA_TRY(cudaGetLastError());
     return launchSegmentStarts(kpSeg, &counters->nKeypoints, segKpStart, nSegs, st);
 }

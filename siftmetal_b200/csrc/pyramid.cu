@@ -21,55 +21,83 @@ __device__ __forceinline__ int symmetrized(int i, int l) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Gray + 2x bilinear upsample. One thread per output pixel of the 2W x 2H plane.
-__device__ __forceinline__ float grayOf(const uint8_t* row, int x) {
-    const uchar4 p = *reinterpret_cast<const uchar4*>(row + 4 * x);  // b, g, r, a
-    const float b = (float)p.x / 255.0f;
-    const float g = (float)p.y / 255.0f;
-    const float r = (float)p.z / 255.0f;
-    return ((0.0f + (0.212639005871510f * r)) + (0.715168678767756f * g)) +
-           (0.072192315360734f * b);
+// Gray conversion: 4 pixels per thread. byte/255 has only 256 values, so the (exactly rounded)
+// quotients are tabulated once per CTA in shared memory instead of 12 IEEE divisions per thread.
+__global__ void __launch_bounds__(256)
+grayKernel(const uint8_t* __restrict__ bgra, int pitchBytes, int64_t frameStrideBytes,
+           float* __restrict__ gray, int W, int H) {
+    __shared__ float lut[256];
+    lut[threadIdx.x] = (float)threadIdx.x / 255.0f;
+    __syncthreads();
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y, f = blockIdx.z;
+    if (x4 >= W) return;
+    const uint8_t* row = bgra + (size_t)f * frameStrideBytes + (size_t)y * pitchBytes;
+    float* out = gray + ((size_t)f * H + y) * W;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int x = x4 + k;
+        if (x < W) {
+            const uchar4 p = *reinterpret_cast<const uchar4*>(row + 4 * x);  // b, g, r, a
+            const float b = lut[p.x], g = lut[p.y], r = lut[p.z];
+            out[x] = ((0.0f + (0.212639005871510f * r)) + (0.715168678767756f * g)) +
+                     (0.072192315360734f * b);
+        }
+    }
 }
 
+// 2x bilinear upsample (BilinearUpScale.metal:12-64), the reference's general formula evaluated
+// per output pixel; 4 consecutive outputs per thread.
 __global__ void __launch_bounds__(256)
-grayUpsampleKernel(const uint8_t* __restrict__ bgra, int pitchBytes, int64_t frameStrideBytes,
-                   float* __restrict__ gray, int W, int H, float* __restrict__ scaled, int w2,
-                   int h2, int pitch2, size_t scaledFrameStride) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y;
-    const int f = blockIdx.z;
-    if (i >= w2) return;
-    const uint8_t* src = bgra + (size_t)f * frameStrideBytes;
+upsampleKernel(const float* __restrict__ gray, int W, int H, float* __restrict__ scaled, int w2,
+               int h2, int pitch2, size_t scaledFrameStride) {
+    const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int j = blockIdx.y, f = blockIdx.z;
+    if (i0 >= w2) return;
+    const float* __restrict__ src = gray + (size_t)f * W * H;
     const float dx = (float)W / (float)w2;
     const float dy = (float)H / (float)h2;
-    const float x = (float)i * dx;
     const float y = (float)j * dy;
-    int im = (int)x, jm = (int)y;
-    int ip = im + 1, jp = jm + 1;
-    if (ip >= W) ip = 2 * W - 1 - ip;
-    if (im >= W) im = 2 * W - 1 - im;
+    int jm = (int)y, jp = jm + 1;
     if (jp >= H) jp = 2 * H - 1 - jp;
     if (jm >= H) jm = 2 * H - 1 - jm;
-    const float fx = x - floorf(x);
     const float fy = y - floorf(y);
-    const uint8_t* rowP = src + (size_t)jp * pitchBytes;
-    const uint8_t* rowM = src + (size_t)jm * pitchBytes;
-    const float c0 = grayOf(rowP, ip), c1 = grayOf(rowM, ip);
-    const float c2 = grayOf(rowP, im), c3 = grayOf(rowM, im);
-    const float a = (fy * c0) + ((1 - fy) * c1);
-    const float b = (fy * c2) + ((1 - fy) * c3);
-    scaled[(size_t)f * scaledFrameStride + (size_t)j * pitch2 + i] = (fx * a) + ((1 - fx) * b);
-    if (gray != nullptr && (i & 1) == 0 && (j & 1) == 0 && (i >> 1) < W && (j >> 1) < H)
-        gray[((size_t)f * H + (j >> 1)) * W + (i >> 1)] = c3;  // even (i, j): (im, jm) = (i/2, j/2)
+    const float* __restrict__ rowP = src + (size_t)jp * W;
+    const float* __restrict__ rowM = src + (size_t)jm * W;
+    float o[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int i = i0 + k;
+        const float x = (float)i * dx;
+        int im = (int)x, ip = im + 1;
+        if (ip >= W) ip = 2 * W - 1 - ip;
+        if (im >= W) im = 2 * W - 1 - im;
+        const float fx = x - floorf(x);
+        const float c0 = __ldg(rowP + ip), c1 = __ldg(rowM + ip);
+        const float c2 = __ldg(rowP + im), c3 = __ldg(rowM + im);
+        const float a = (fy * c0) + ((1 - fy) * c1);
+        const float b = (fy * c2) + ((1 - fy) * c3);
+        o[k] = (fx * a) + ((1 - fx) * b);
+    }
+    float* dst = scaled + (size_t)f * scaledFrameStride + (size_t)j * pitch2 + i0;
+    if (i0 + 3 < w2) {
+        *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (i0 + k < w2) dst[k] = o[k];
+    }
 }
 
 cudaError_t launchGrayUpsample(const uint8_t* bgra, int pitchBytes, int64_t frameStrideBytes,
                                float* gray, int W, int H, float* scaled, int w2, int h2,
                                int pitch2, size_t scaledFrameStride, int frames,
                                cudaStream_t st) {
-    dim3 grid((w2 + 255) / 256, h2, frames);
-    grayUpsampleKernel<<<grid, 256, 0, st>>>(bgra, pitchBytes, frameStrideBytes, gray, W, H,
-                                             scaled, w2, h2, pitch2, scaledFrameStride);
+    dim3 g1((W + 1023) / 1024, H, frames);
+    grayKernel<<<g1, 256, 0, st>>>(bgra, pitchBytes, frameStrideBytes, gray, W, H);
+    SIFT_CUDA_TRY(cudaGetLastError());
+    dim3 g2((w2 + 1023) / 1024, h2, frames);
+    upsampleKernel<<<g2, 256, 0, st>>>(gray, W, H, scaled, w2, h2, pitch2, scaledFrameStride);
     return cudaGetLastError();
 }
 
@@ -127,11 +155,19 @@ blurKernel(const BlurArgs a, const __grid_constant__ Taps taps) {
         }
         asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
     } else {
-        for (int idx = tid; idx < IN_H * IN_W; idx += 256) {
-            const int r = idx / IN_W, c = idx - r * IN_W;
+        // edge tile: mirror boundary. One warp per row (row index reflected once per warp),
+        // lanes across columns with a single-reflection fast path.
+        const int lane = tid & 31, wid = tid >> 5;
+        for (int r = wid; r < IN_H; r += 8) {
             const int gy = symmetrized(y0 - R + r, h);
-            const int gx = symmetrized(x0 - RP + c, w);
-            sIn[r * IP + c] = __ldg(in + (size_t)gy * pitch + gx);
+            const float* __restrict__ srow = in + (size_t)gy * pitch;
+            for (int c = lane; c < IN_W; c += 32) {
+                int gx = x0 - RP + c;
+                if (gx < 0) gx = -1 - gx;
+                else if (gx >= w) gx = 2 * w - 1 - gx;
+                if (gx < 0 || gx >= w) gx = symmetrized(x0 - RP + c, w);
+                sIn[r * IP + c] = __ldg(srow + gx);
+            }
         }
     }
     __syncthreads();
@@ -237,29 +273,48 @@ cudaError_t launchBlur(const BlurArgs& a, const Taps& taps, int ntaps, cudaStrea
 
 // ------------------------------------------------------------------------------------------
 // SIFTGradient.metal:15-39 for Gaussian slices 1..3 (the only ones ever read downstream:
-// refined scale is in [1, 3], SIFTInterpolate.metal:187-189).
+// refined scale is in [1, 3], SIFTInterpolate.metal:187-189). 4 pixels per thread, float4
+// loads of the three rows, two float4 stores of (orientation, magnitude) pairs. The mirror
+// boundary of symmetrizedCoordinates reduces to a clamp for offsets of one pixel.
 __global__ void __launch_bounds__(256) gradientKernel(const OctaveDev o) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int y = blockIdx.y;
     const int s = blockIdx.z % kScales;   // 0..2 → Gaussian slice s + 1
     const int f = blockIdx.z / kScales;
-    if (x >= o.w) return;
+    if (x0 >= o.w) return;
     const float* __restrict__ g = o.G + ((size_t)f * kGaussians + (s + 1)) * o.plane;
-    const int px = symmetrized(x + 1, o.w), mx = symmetrized(x - 1, o.w);
-    const int py = symmetrized(y + 1, o.h), my = symmetrized(y - 1, o.h);
-    const float cpx = __ldg(g + (size_t)y * o.pitch + px);
-    const float cmx = __ldg(g + (size_t)y * o.pitch + mx);
-    const float cpy = __ldg(g + (size_t)py * o.pitch + x);
-    const float cmy = __ldg(g + (size_t)my * o.pitch + x);
-    const float tx = (cpx - cmx) * 0.5f;
-    const float ty = (cpy - cmy) * 0.5f;
-    const float oa = dm_atan2f(tx, ty);
-    const float om = sqrtf((tx * tx) + (ty * ty));
-    o.grad[((size_t)f * kScales + s) * o.plane + (size_t)y * o.pitch + x] = make_float2(oa, om);
+    const int py = (y + 1 < o.h) ? y + 1 : o.h - 1;   // symmetrized(h) = h - 1
+    const int my = (y - 1 >= 0) ? y - 1 : 0;          // symmetrized(-1) = 0
+    const float* __restrict__ rc = g + (size_t)y * o.pitch;
+    // rows are padded to a multiple of 32 floats, so the float4 reads stay inside the row
+    const float4 c4 = __ldg(reinterpret_cast<const float4*>(rc + x0));
+    const float4 p4 = __ldg(reinterpret_cast<const float4*>(g + (size_t)py * o.pitch + x0));
+    const float4 m4 = __ldg(reinterpret_cast<const float4*>(g + (size_t)my * o.pitch + x0));
+    const float c[4] = {c4.x, c4.y, c4.z, c4.w};
+    const float dn[4] = {p4.x, p4.y, p4.z, p4.w};
+    const float up[4] = {m4.x, m4.y, m4.z, m4.w};
+    const float left = __ldg(rc + (x0 > 0 ? x0 - 1 : 0));
+    const float right = __ldg(rc + (x0 + 4 < o.w ? x0 + 4 : o.w - 1));
+    float r[8];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int x = x0 + k;
+        const float cmx = (k == 0) ? left : c[k - 1];
+        float cpx = (k == 3) ? right : c[k + 1];
+        if (x + 1 >= o.w) cpx = c[k];              // symmetrized(w) = w - 1 (this pixel)
+        const float tx = (cpx - cmx) * 0.5f;
+        const float ty = (dn[k] - up[k]) * 0.5f;
+        r[2 * k] = dm_atan2f(tx, ty);
+        r[2 * k + 1] = sqrtf((tx * tx) + (ty * ty));
+    }
+    float2* dst = o.grad + ((size_t)f * kScales + s) * o.plane + (size_t)y * o.pitch + x0;
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    d4[0] = make_float4(r[0], r[1], r[2], r[3]);
+    d4[1] = make_float4(r[4], r[5], r[6], r[7]);
 }
 
 cudaError_t launchGradient(const OctaveDev& o, int frames, cudaStream_t st) {
-    dim3 grid((o.w + 255) / 256, o.h, kScales * frames);
+    dim3 grid((o.w + 1023) / 1024, o.h, kScales * frames);
     gradientKernel<<<grid, 256, 0, st>>>(o);
     return cudaGetLastError();
 }
