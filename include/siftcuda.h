@@ -138,8 +138,8 @@ typedef struct SiftInfo {
 /* Per-stage device times of the last sift_batch_execute, from CUDA events recorded on the
  * context's own stream (replaces measure(name:) of Utilities/Performance.swift:12-20). ms. */
 #define SIFT_STAGE_SEED 0
-#define SIFT_STAGE_PYRAMID 1     /* blur + DoG + gradient, all octaves                            */
-#define SIFT_STAGE_EXTREMA 2
+#define SIFT_STAGE_PYRAMID 1     /* blur + DoG + gradient + extrema mask, octaves on forked streams */
+#define SIFT_STAGE_EXTREMA 2     /* mask -> ordered candidate list (scan + scatter)                */
 #define SIFT_STAGE_REFINE 3
 #define SIFT_STAGE_ORIENTATION 4
 #define SIFT_STAGE_DESCRIPTOR 5

@@ -23,6 +23,11 @@ struct SiftContext {
     int device = 0;
     int smCount = 0;
     cudaStream_t stream = nullptr;
+    // octave o >= 1 runs its blur chain + gradient + extrema mask on its own stream as soon as
+    // octave o-1 has produced Gaussian slice 3 (fork / join around the main stream)
+    cudaStream_t octStream[kOctaves]{};
+    cudaEvent_t evSeeded[kOctaves]{};   // octave o's slice 3 (and octave o+1's slice 0) written
+    cudaEvent_t evOctDone[kOctaves]{};
     SiftInfo info{};
     EngineParams P{};
     Taps seedTaps{};
@@ -144,6 +149,11 @@ void destroy(SiftContext* c) {
         if (e) cudaEventDestroy(e);
     for (auto& e : c->evBlur0)
         if (e) cudaEventDestroy(e);
+    for (int o = 0; o < kOctaves; o++) {
+        if (c->evSeeded[o]) cudaEventDestroy(c->evSeeded[o]);
+        if (c->evOctDone[o]) cudaEventDestroy(c->evOctDone[o]);
+        if (o > 0 && c->octStream[o]) cudaStreamDestroy(c->octStream[o]);
+    }
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -327,6 +337,12 @@ int sift_create(const SiftConfig* cfg, int device, SiftContext** out) {
     A(cudaMallocHost(&c->hKpSeg, std::max<size_t>((size_t)c->capKp * sizeof(int), 64)));
     for (auto& evn : c->ev) A(cudaEventCreate(&evn));
     for (auto& evn : c->evBlur0) A(cudaEventCreate(&evn));
+    c->octStream[0] = c->stream;
+    for (int o = 0; o < kOctaves; o++) {
+        if (o > 0) A(cudaStreamCreateWithFlags(&c->octStream[o], cudaStreamNonBlocking));
+        A(cudaEventCreateWithFlags(&c->evSeeded[o], cudaEventDisableTiming));
+        A(cudaEventCreateWithFlags(&c->evOctDone[o], cudaEventDisableTiming));
+    }
     if (e != cudaSuccess) {
         const bool oom = (e == cudaErrorMemoryAllocation);
         destroy(c);
@@ -426,11 +442,20 @@ int runDetect(SiftContext* c) {
     if (T) CTX_TRY(c, cudaEventRecord(c->ev[1], st));
     // encodeOctaves (:391-406): Gaussian series + DoG; octave o+1 slice 0 = octave o slice 3
     // decimated (fused into the blur that produces slice 3); SIFTOctave.encodeGradients (:190-196)
+    // and encodeExtrema (:183-189). Octaves form a fork/join DAG: octave o+1 starts on its own
+    // stream once octave o has written slice 3, so the small octaves (launch-latency bound) run
+    // under the large kernels of octaves 0 and 1 instead of after them.
+    bool forked[kOctaves] = {};
     for (int o = 0; o < kOctaves; o++) {
         const OctaveDev& q = c->P.oct[o];
         if (q.w < 1 || q.h < 1) continue;
+        cudaStream_t so = c->octStream[o];
+        if (o > 0) {
+            CTX_TRY(c, cudaStreamWaitEvent(so, c->evSeeded[o - 1], 0));
+            forked[o] = true;
+        }
         for (int s = 0; s < kGaussians - 1; s++) {
-            if (T && o == 0) CTX_TRY(c, cudaEventRecord(c->evBlur0[s], st));
+            if (T && o == 0) CTX_TRY(c, cudaEventRecord(c->evBlur0[s], so));
             BlurArgs a{};
             a.in = q.G + (size_t)s * q.plane;
             a.out = q.G + (size_t)(s + 1) * q.plane;
@@ -445,20 +470,23 @@ int runDetect(SiftContext* c) {
                 a.halfFrameStride = kGaussians * nx.plane;
             }
             a.frames = F;
-            CTX_TRY(c, launchBlur(a, c->taps[s], c->ntaps[s], st));
+            CTX_TRY(c, launchBlur(a, c->taps[s], c->ntaps[s], so));
+            c->launches++;
+            if (s + 1 == kScales) CTX_TRY(c, cudaEventRecord(c->evSeeded[o], so));
+        }
+        if (T && o == 0) CTX_TRY(c, cudaEventRecord(c->evBlur0[kGaussians - 1], so));
+        CTX_TRY(c, launchGradient(q, F, so));
+        c->launches++;
+        if (q.w >= 3 && q.h >= 3) {
+            CTX_TRY(c, launchExtremaMask(c->P, o, c->dMask, F, so));
             c->launches++;
         }
-        if (T && o == 0) CTX_TRY(c, cudaEventRecord(c->evBlur0[kGaussians - 1], st));
-        CTX_TRY(c, launchGradient(q, F, st));
-        c->launches++;
+        if (o > 0) CTX_TRY(c, cudaEventRecord(c->evOctDone[o], so));
     }
+    for (int o = 1; o < kOctaves; o++)
+        if (forked[o]) CTX_TRY(c, cudaStreamWaitEvent(st, c->evOctDone[o], 0));
     if (T) CTX_TRY(c, cudaEventRecord(c->ev[2], st));
-    // SIFTOctave.encodeExtrema (:183-189) + getKeypoints (:198-203)
-    for (int o = 0; o < kOctaves; o++) {
-        if (c->P.oct[o].w < 3 || c->P.oct[o].h < 3) continue;
-        CTX_TRY(c, launchExtremaMask(c->P, o, c->dMask, F, st));
-        c->launches++;
-    }
+    // SIFTOctave.getKeypoints (:198-203): mask → ordered candidate list
     CTX_TRY(c, launchCandidateCompaction(c->P, c->dMask, c->dBlockSums, c->dCands, c->capCand,
                                          nullptr, c->dCounters, F, st));
     CTX_TRY(c, launchCandidateSegmentStarts(c->dCands, &c->dCounters->nCandidates, c->dSegStarts,

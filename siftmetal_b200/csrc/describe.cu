@@ -13,7 +13,6 @@
 // order, so they differ from the oracle in the last bits; every quantity that drives a
 // *discontinuous* decision (bin index, window radius, sample coordinate, border filter) is
 // evaluated with the spec's exact operation sequence.
-#include <stdio.h>
 #include "common.cuh"
 #include "dev_math.cuh"
 #include "scan.cuh"
@@ -74,18 +73,39 @@ orientationKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __
         for (int b = 0; b < kOriBins; b++) hist[b * 32 + lane] = 0.0f;
         __syncwarp();
         const float invSide = 1.0f / (float)side;
-        for (int idx = lane; idx < side * side; idx += 32) {
-            const int jj = (int)(((float)idx + 0.5f) * invSide);
-            const int ii = idx - jj * side;
-            const int sx = x + ii - r, sy = y + jj - r;
-            if (sx < 0 || sx >= o.w || sy < 0 || sy >= o.h) continue;
-            const float2 gm = __ldg(g + (size_t)sy * o.pitch + sx);
-            // bin index: discontinuous → the spec's exact sequence
-            const float t = __fdiv_rn(gm.x, kTau);
-            int bin = (int)roundf(__fmul_rn(t, (float)kOriBins));
-            if (bin < 0) bin += kOriBins;
-            if (bin >= kOriBins) bin -= kOriBins;
-            hist[bin * 32 + lane] += (wt[ii] * wt[jj]) * gm.y;
+        const int nSamples = side * side;
+        // four gathers in flight per lane: the loop is bound by the latency of the gradient
+        // loads, not by arithmetic
+        for (int base = 0; base < nSamples; base += 128) {
+            float2 gm[4];
+            float wgt[4];
+            bool ok[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int idx = base + u * 32 + lane;
+                ok[u] = false;
+                if (idx < nSamples) {
+                    const int jj = (int)(((float)idx + 0.5f) * invSide);
+                    const int ii = idx - jj * side;
+                    const int sx = x + ii - r, sy = y + jj - r;
+                    if (sx >= 0 && sx < o.w && sy >= 0 && sy < o.h) {
+                        ok[u] = true;
+                        gm[u] = __ldg(g + (size_t)sy * o.pitch + sx);
+                        wgt[u] = wt[ii] * wt[jj];
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (ok[u]) {
+                    // bin index: discontinuous → the spec's exact sequence
+                    const float t = __fdiv_rn(gm[u].x, kTau);
+                    int bin = (int)roundf(__fmul_rn(t, (float)kOriBins));
+                    if (bin < 0) bin += kOriBins;
+                    if (bin >= kOriBins) bin -= kOriBins;
+                    hist[bin * 32 + lane] += wgt[u] * gm[u].y;
+                }
+            }
         }
         __syncwarp();
         // reduce the 32 lane-private copies of each bin, rotated start → conflict-free
@@ -190,7 +210,7 @@ __global__ void descSegmentStartsKernel(const int* __restrict__ segKpStart,
 // Window radius, sample coordinates and centre truncation follow the spec's exact sequences;
 // per-sample weights use FMA / reciprocal / ex2.approx — continuous quantities within the ±1
 // tolerance of the quantised features.
-constexpr int kDescWarps = 4;      // 4 warps x 16 KB of lane-private histograms = 64 KB per CTA
+constexpr int kDescWarps = 2;      // 2 warps x 16 KB of lane-private histograms = 32 KB per CTA
 constexpr int kDescMaxSide = 128;  // 2·radius+1; radius <= 39 for detected keypoints
 
 __global__ void __launch_bounds__(kDescWarps * 32)
@@ -264,9 +284,6 @@ descriptorKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __r
                 const int ilo = (int)floorf(flo), ihi = (int)ceilf(fhi);
                 c = (empty || ihi < ilo) ? 0 : ihi - ilo + 1;
                 rowLo[jj] = ilo;
-#ifdef SIFT_DEBUG_DESC
-                if (d == 0 && (lane == 0 || lane == 21)) printf("SPAN lane=%d q=%d jj=%d fj=%g lo1=%g hi1=%g lo2=%g hi2=%g flo=%g fhi=%g ilo=%d ihi=%d empty=%d c=%d oh=%d py=%g\n", lane, q, jj, fj, lo1, hi1, lo2, hi2, flo, fhi, ilo, ihi, (int)empty, c, o.h, py);
-#endif
             }
             cnt[q] = c;
         }
@@ -285,66 +302,81 @@ descriptorKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __r
         }
         const int total = base;
         if (lane == 0) rowStart[side] = total;
-#ifdef SIFT_DEBUG_DESC
-        if (d == 0 && lane == 0) printf("DESC0 side=%d radius=%d total=%d a=%g b=%g hw=%g px=%g py=%g cnt0=%d cnt1=%d\n", side, radius, total, a, b, hw, px, py, cnt[0], cnt[1]);
-#endif
 #pragma unroll 8
         for (int bb = 0; bb < 128; bb++) hist[bb * 32 + lane] = 0.0f;
         __syncwarp();
 
         int row = 0;
-        for (int idx = lane; idx < total; idx += 32) {
-            while (idx >= rowStart[row + 1]) row++;
-            const int i = rowLo[row] + (idx - rowStart[row]);   // y offset
-            const float fj = (float)(row - radius), fi = (float)i;
-            const float rx = fj * a - fi * b;
-            const float ry = fj * b + fi * a;
-            const float bx = rx + 1.5f, by = ry + 1.5f;
-            // addValue drops cells outside [0, 4): nothing lands unless -1 < b < 4 on both axes
-            if (!(bx > -1.0f && bx < 4.0f && by > -1.0f && by < 4.0f)) continue;
-            const float cxf = __fadd_rn(px, fj), cyf = __fadd_rn(py, fi);
-            if (cxf < 0.0f || cyf < 0.0f) continue;
-            const int sx = (int)cxf, sy = (int)cyf;
-            if (sx >= o.w || sy >= o.h) continue;
-            const float2 gm = __ldg(g + (size_t)sy * o.pitch + sx);
-            float ori = gm.x - theta;                 // in (-3 pi, pi]
-            ori += (ori < 0.0f) ? kTau : 0.0f;
-            ori += (ori < 0.0f) ? kTau : 0.0f;
-            ori -= (ori >= kTau) ? kTau : 0.0f;
-            const float bin = ori * (8.0f / kTau);
-            const int bi = (int)bin;                   // bin >= 0: truncation = floor
-            const float fb = bin - (float)bi;
-            const int b0 = bi & 7, b1 = (bi + 1) & 7;
-            const float w = __expf(-(rx * rx + ry * ry) * 0.125f);
-            const float val = gm.y * w;
-#ifdef SIFT_DEBUG_DESC
-            if (d == 0 && idx < 64) printf("  idx=%d row=%d i=%d bx=%g by=%g sx=%d sy=%d mag=%g w=%g bin=%g\n", idx, row, i, bx, by, sx, sy, gm.y, w, bin);
-#endif
-            const int x0 = __float2int_rd(bx), y0 = __float2int_rd(by);
-            const float fxw = bx - (float)x0, fyw = by - (float)y0;
-            // trilinear spread (addFeature, :82-117). ceil = floor + 1 except on exact integers,
-            // where the reference adds a zero weight to the floor cell — same sums either way.
-            const float vx0 = val * (1.0f - fxw), vx1 = val * fxw;
-            const float v00 = vx0 * (1.0f - fyw), v01 = vx0 * fyw;
-            const float v10 = vx1 * (1.0f - fyw), v11 = vx1 * fyw;
-            const bool okx0 = (x0 >= 0), okx1 = (x0 < 3), oky0 = (y0 >= 0), oky1 = (y0 < 3);
-            float* h00 = hist + ((y0 * 4 + x0) * 8) * 32 + lane;   // cell (x0, y0), bin 0
-            float* h10 = h00 + 8 * 32;                              // (x0+1, y0)
-            float* h01 = h00 + 4 * 8 * 32;                          // (x0, y0+1)
-            float* h11 = h01 + 8 * 32;                              // (x0+1, y0+1)
-            const int o0 = b0 * 32, o1 = b1 * 32;
-            const float g0 = 1.0f - fb;
-            // the eight addresses are distinct: load all, add, store all
-            float t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0, t6 = 0, t7 = 0;
-            const bool c00 = okx0 && oky0, c10 = okx1 && oky0, c01 = okx0 && oky1, c11 = okx1 && oky1;
-            if (c00) { t0 = h00[o0]; t1 = h00[o1]; }
-            if (c10) { t2 = h10[o0]; t3 = h10[o1]; }
-            if (c01) { t4 = h01[o0]; t5 = h01[o1]; }
-            if (c11) { t6 = h11[o0]; t7 = h11[o1]; }
-            if (c00) { h00[o0] = t0 + v00 * g0; h00[o1] = t1 + v00 * fb; }
-            if (c10) { h10[o0] = t2 + v10 * g0; h10[o1] = t3 + v10 * fb; }
-            if (c01) { h01[o0] = t4 + v01 * g0; h01[o1] = t5 + v01 * fb; }
-            if (c11) { h11[o0] = t6 + v11 * g0; h11[o1] = t7 + v11 * fb; }
+        // four gathers in flight per lane (latency-bound loop); accumulation afterwards, in order
+        for (int base = 0; base < total; base += 128) {
+            float2 gm[4];
+            float bxs[4], bys[4], r2s[4];
+            bool ok[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int idx = base + u * 32 + lane;
+                ok[u] = false;
+                if (idx < total) {
+                    while (idx >= rowStart[row + 1]) row++;
+                    const int i = rowLo[row] + (idx - rowStart[row]);   // y offset
+                    const float fj = (float)(row - radius), fi = (float)i;
+                    const float rx = fj * a - fi * b;
+                    const float ry = fj * b + fi * a;
+                    const float bx = rx + 1.5f, by = ry + 1.5f;
+                    // addValue drops cells outside [0, 4): nothing lands unless -1 < b < 4
+                    if (bx > -1.0f && bx < 4.0f && by > -1.0f && by < 4.0f) {
+                        const float cxf = __fadd_rn(px, fj), cyf = __fadd_rn(py, fi);
+                        const int sx = (int)cxf, sy = (int)cyf;
+                        if (cxf >= 0.0f && cyf >= 0.0f && sx < o.w && sy < o.h) {
+                            ok[u] = true;
+                            gm[u] = __ldg(g + (size_t)sy * o.pitch + sx);
+                            bxs[u] = bx;
+                            bys[u] = by;
+                            r2s[u] = rx * rx + ry * ry;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (!ok[u]) continue;
+                const float bx = bxs[u], by = bys[u];
+                float ori = gm[u].x - theta;                 // in (-3 pi, pi]
+                ori += (ori < 0.0f) ? kTau : 0.0f;
+                ori += (ori < 0.0f) ? kTau : 0.0f;
+                ori -= (ori >= kTau) ? kTau : 0.0f;
+                const float bin = ori * (8.0f / kTau);
+                const int bi = (int)bin;                   // bin >= 0: truncation = floor
+                const float fb = bin - (float)bi;
+                const int b0 = bi & 7, b1 = (bi + 1) & 7;
+                const float w = __expf(-r2s[u] * 0.125f);
+                const float val = gm[u].y * w;
+                const int x0 = __float2int_rd(bx), y0 = __float2int_rd(by);
+                const float fxw = bx - (float)x0, fyw = by - (float)y0;
+                // trilinear spread (addFeature, :82-117). ceil = floor + 1 except on exact
+                // integers, where the reference adds a zero weight to the floor cell — same sums.
+                const float vx0 = val * (1.0f - fxw), vx1 = val * fxw;
+                const float v00 = vx0 * (1.0f - fyw), v01 = vx0 * fyw;
+                const float v10 = vx1 * (1.0f - fyw), v11 = vx1 * fyw;
+                const bool okx0 = (x0 >= 0), okx1 = (x0 < 3), oky0 = (y0 >= 0), oky1 = (y0 < 3);
+                float* h00 = hist + ((y0 * 4 + x0) * 8) * 32 + lane;   // cell (x0, y0), bin 0
+                float* h10 = h00 + 8 * 32;                              // (x0+1, y0)
+                float* h01 = h00 + 4 * 8 * 32;                          // (x0, y0+1)
+                float* h11 = h01 + 8 * 32;                              // (x0+1, y0+1)
+                const int o0 = b0 * 32, o1 = b1 * 32;
+                const float g0 = 1.0f - fb;
+                // the eight addresses are distinct: load all, add, store all
+                float t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0, t6 = 0, t7 = 0;
+                const bool c00 = okx0 && oky0, c10 = okx1 && oky0, c01 = okx0 && oky1, c11 = okx1 && oky1;
+                if (c00) { t0 = h00[o0]; t1 = h00[o1]; }
+                if (c10) { t2 = h10[o0]; t3 = h10[o1]; }
+                if (c01) { t4 = h01[o0]; t5 = h01[o1]; }
+                if (c11) { t6 = h11[o0]; t7 = h11[o1]; }
+                if (c00) { h00[o0] = t0 + v00 * g0; h00[o1] = t1 + v00 * fb; }
+                if (c10) { h10[o0] = t2 + v10 * g0; h10[o1] = t3 + v10 * fb; }
+                if (c01) { h01[o0] = t4 + v01 * g0; h01[o1] = t5 + v01 * fb; }
+                if (c11) { h11[o0] = t6 + v11 * g0; h11[o1] = t7 + v11 * fb; }
+            }
         }
         __syncwarp();
         // reduce lane-private copies: lane owns bins lane, lane+32, lane+64, lane+96
@@ -419,7 +451,7 @@ cudaError_t launchDescribe(const EngineParams& P, const SiftKeypoint* kps, const
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes));
         configured |= 1ull << (dev & 63);
     }
-    descriptorKernel<<<smCount * 3, kDescWarps * 32, smemBytes, st>>>(
+    descriptorKernel<<<smCount * 6, kDescWarps * 32, smemBytes, st>>>(
         P, kps, kpSeg, segKpStart, counters, oriOffset, oriTmp, desc, capDescriptors);
     return cudaGetLastError();
 }

@@ -23,7 +23,7 @@ namespace sift {
 // partials that leave the left pixel of the row above in the slice below out) AND
 // |v| > 0.8·C_DoG (first test of siftInterpolate, SIFTInterpolate.metal:208; fusing it here is
 // result-neutral). min/max are exact, so evaluation order is free.
-constexpr int kExtRows = 30;    // output rows per warp (32 rows loaded)
+constexpr int kExtRows = 30;    // output rows per warp for large planes (32 rows loaded)
 constexpr int kExtWarps = 8;
 
 struct RowPart {
@@ -70,13 +70,13 @@ __device__ __forceinline__ RowPart makeRowPart(float c, float e, int lane) {
 
 __global__ void __launch_bounds__(kExtWarps * 32)
 extremaMaskKernel(const OctaveDev o, float softThreshold, uint32_t* __restrict__ mask,
-                  int blocksPerFrame) {
+                  int blocksPerFrame, int rowsPerWarp) {
     const int lane = threadIdx.x & 31;
     const int xw = blockIdx.x * kExtWarps + (threadIdx.x >> 5);
     if (xw >= o.maskRowWords) return;  // whole warp
     const int x = xw * 32 + lane;      // < pitch: readable even beyond w (masked below)
     const int ex = (lane == 0) ? max(x - 1, 0) : ((lane == 31) ? min(x + 1, o.w - 1) : x);
-    const int yFirst = 1 + blockIdx.y * kExtRows;          // first output row of this warp
+    const int yFirst = 1 + blockIdx.y * rowsPerWarp;       // first output row of this warp
     const int f = blockIdx.z;
     const float* __restrict__ D = o.D + (size_t)f * kDogs * o.plane;
     uint32_t* __restrict__ m =
@@ -94,15 +94,18 @@ extremaMaskKernel(const OctaveDev o, float softThreshold, uint32_t* __restrict__
             win[t][1] = makeRowPart(r1.c[t], r1.e[t], lane);
         }
     }
-    RowRaw ahead = loadRowRaw(D, o.plane, rowOffset(yFirst + 1), x, ex);   // software pipeline
-    for (int r0 = 0; r0 < kExtRows; r0 += 3) {
+    // software pipeline, two rows ahead: 20 independent loads in flight per lane
+    RowRaw ahead0 = loadRowRaw(D, o.plane, rowOffset(yFirst + 1), x, ex);
+    RowRaw ahead1 = loadRowRaw(D, o.plane, rowOffset(yFirst + 2), x, ex);
+    for (int r0 = 0; r0 < rowsPerWarp; r0 += 3) {
 #pragma unroll
         for (int k = 0; k < 3; k++) {
             const int y = yFirst + r0 + k;
             const int prev = k % 3, cur = (k + 1) % 3, next = (k + 2) % 3;
             if (y > o.h - 2) return;  // warp-uniform
-            const RowRaw now = ahead;
-            ahead = loadRowRaw(D, o.plane, rowOffset(y + 2), x, ex);       // consumed next iteration
+            const RowRaw now = ahead0;
+            ahead0 = ahead1;
+            ahead1 = loadRowRaw(D, o.plane, rowOffset(y + 3), x, ex);      // consumed two rows later
 #pragma unroll
             for (int t = 0; t < kDogs; t++) win[t][next] = makeRowPart(now.c[t], now.e[t], lane);
 #pragma unroll
@@ -126,8 +129,13 @@ cudaError_t launchExtremaMask(const EngineParams& P, int octave, uint32_t* mask,
                               cudaStream_t st) {
     const OctaveDev& o = P.oct[octave];
     if (o.w < 3 || o.h < 3) return cudaSuccess;
-    dim3 grid((o.maskRowWords + kExtWarps - 1) / kExtWarps, (o.h - 2 + kExtRows - 1) / kExtRows, frames);
-    extremaMaskKernel<<<grid, kExtWarps * 32, 0, st>>>(o, P.dogThreshold * 0.8f, mask, P.blocksPerFrame);
+    // rows per warp (multiple of 3): long strips amortise the 2-row halo on large planes; small
+    // planes get short strips so that the serial row loop does not bound the launch
+    const int gx = (o.maskRowWords + kExtWarps - 1) / kExtWarps;
+    int rows = kExtRows;
+    while (rows > 6 && (long)gx * ((o.h - 2 + rows - 1) / rows) * frames < 592) rows -= 6;
+    dim3 grid(gx, (o.h - 2 + rows - 1) / rows, frames);
+    extremaMaskKernel<<<grid, kExtWarps * 32, 0, st>>>(o, P.dogThreshold * 0.8f, mask, P.blocksPerFrame, rows);
     return cudaGetLastError();
 }
 

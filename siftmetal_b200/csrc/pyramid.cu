@@ -126,8 +126,8 @@ struct BlurCfg {
     static constexpr int RY = 8;     // outputs per thread in the Y pass
 };
 
-template <int NTAPS, int TX, int TY>
-__global__ void __launch_bounds__(256)
+template <int NTAPS, int TX, int TY, int NT>
+__global__ void __launch_bounds__(NT)
 blurKernel(const BlurArgs a, const __grid_constant__ Taps taps) {
     using C = BlurCfg<NTAPS, TX, TY>;
     constexpr int R = C::R, RP = C::RP, IN_W = C::IN_W, IN_H = C::IN_H, IP = C::IP, TP = C::TP;
@@ -147,7 +147,7 @@ blurKernel(const BlurArgs a, const __grid_constant__ Taps taps) {
     if (interior) {
         constexpr int V = IN_W / 4;
         const float* base = in + (size_t)(y0 - R) * pitch + (x0 - RP);
-        for (int idx = tid; idx < IN_H * V; idx += 256) {
+        for (int idx = tid; idx < IN_H * V; idx += NT) {
             const int r = idx / V, c4 = idx - r * V;
             const float* g = base + (size_t)r * pitch + 4 * c4;
             const unsigned s = (unsigned)__cvta_generic_to_shared(sIn + r * IP + 4 * c4);
@@ -158,7 +158,7 @@ blurKernel(const BlurArgs a, const __grid_constant__ Taps taps) {
         // edge tile: mirror boundary. One warp per row (row index reflected once per warp),
         // lanes across columns with a single-reflection fast path.
         const int lane = tid & 31, wid = tid >> 5;
-        for (int r = wid; r < IN_H; r += 8) {
+        for (int r = wid; r < IN_H; r += NT / 32) {
             const int gy = symmetrized(y0 - R + r, h);
             const float* __restrict__ srow = in + (size_t)gy * pitch;
             for (int c = lane; c < IN_W; c += 32) {
@@ -166,9 +166,11 @@ blurKernel(const BlurArgs a, const __grid_constant__ Taps taps) {
                 if (gx < 0) gx = -1 - gx;
                 else if (gx >= w) gx = 2 * w - 1 - gx;
                 if (gx < 0 || gx >= w) gx = symmetrized(x0 - RP + c, w);
-                sIn[r * IP + c] = __ldg(srow + gx);
+                const unsigned s = (unsigned)__cvta_generic_to_shared(sIn + r * IP + c);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(srow + gx));
             }
         }
+        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
     }
     __syncthreads();
 
@@ -176,7 +178,7 @@ blurKernel(const BlurArgs a, const __grid_constant__ Taps taps) {
     {
         constexpr int SEGS = TX / C::XSEG;
         constexpr int NV = (C::XSEG + 2 * RP) / 4;
-        for (int t = tid; t < IN_H * SEGS; t += 256) {
+        for (int t = tid; t < IN_H * SEGS; t += NT) {
             const int seg = t / IN_H, r = t - seg * IN_H;
             const float4* src = reinterpret_cast<const float4*>(sIn + r * IP + seg * C::XSEG);
             float v[NV * 4];
@@ -207,7 +209,7 @@ blurKernel(const BlurArgs a, const __grid_constant__ Taps taps) {
         float* __restrict__ out = a.out + (size_t)f * a.outFrameStride;
         float* __restrict__ dog = a.dog ? a.dog + (size_t)f * a.dogFrameStride : nullptr;
         float* __restrict__ half = a.half ? a.half + (size_t)f * a.halfFrameStride : nullptr;
-        for (int t = tid; t < TX * (TY / RY); t += 256) {
+        for (int t = tid; t < TX * (TY / RY); t += NT) {
             const int yb = t / TX, x = t - yb * TX;
             const int gx = x0 + x;
             float v[RY + 2 * R];
@@ -240,24 +242,34 @@ blurKernel(const BlurArgs a, const __grid_constant__ Taps taps) {
     }
 }
 
-template <int NTAPS>
-static cudaError_t launchBlurT(const BlurArgs& a, const Taps& taps, cudaStream_t st) {
-    constexpr int TX = 64, TY = 64;
+template <int NTAPS, int TX, int TY, int NT>
+static cudaError_t launchBlurCfg(const BlurArgs& a, const Taps& taps, cudaStream_t st) {
     using C = BlurCfg<NTAPS, TX, TY>;
     static_assert(C::IN_W % 4 == 0 && C::IP % 8 == 4 && C::TP % 8 == 4, "bank layout");
+    static_assert(TX % C::XSEG == 0 && TY % C::RY == 0, "tile shape");
     const int smemBytes = C::SMEM_FLOATS * (int)sizeof(float);
     static unsigned long long configured = 0;  // per-device bit: the attribute is per device
     int dev = 0;
     cudaGetDevice(&dev);
     if (!((configured >> (dev & 63)) & 1ull)) {
-        cudaError_t e = cudaFuncSetAttribute(blurKernel<NTAPS, TX, TY>,
+        cudaError_t e = cudaFuncSetAttribute(blurKernel<NTAPS, TX, TY, NT>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes);
         if (e != cudaSuccess) return e;
         configured |= 1ull << (dev & 63);
     }
     dim3 grid((a.w + TX - 1) / TX, (a.h + TY - 1) / TY, a.frames);
-    blurKernel<NTAPS, TX, TY><<<grid, 256, smemBytes, st>>>(a, taps);
+    blurKernel<NTAPS, TX, TY, NT><<<grid, NT, smemBytes, st>>>(a, taps);
     return cudaGetLastError();
+}
+
+// Large planes: 64x64 tiles, 256 threads (least halo overhead). Planes that would not give every
+// SM two such tiles: 32x32 tiles, 128 threads — a launch is then bound by the latency of one
+// tile, so smaller tiles on more SMs finish sooner.
+template <int NTAPS>
+static cudaError_t launchBlurT(const BlurArgs& a, const Taps& taps, cudaStream_t st) {
+    const long tiles64 = (long)((a.w + 63) / 64) * ((a.h + 63) / 64) * a.frames;
+    if (tiles64 >= 2 * 148) return launchBlurCfg<NTAPS, 64, 64, 256>(a, taps, st);
+    return launchBlurCfg<NTAPS, 32, 32, 128>(a, taps, st);
 }
 
 cudaError_t launchBlur(const BlurArgs& a, const Taps& taps, int ntaps, cudaStream_t st) {
