@@ -341,11 +341,10 @@ descriptorKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __r
             for (int u = 0; u < 4; u++) {
                 if (!ok[u]) continue;
                 const float bx = bxs[u], by = bys[u];
-                float ori = gm[u].x - theta;                 // in (-3 pi, pi]
-                ori += (ori < 0.0f) ? kTau : 0.0f;
-                ori += (ori < 0.0f) ? kTau : 0.0f;
-                ori -= (ori >= kTau) ? kTau : 0.0f;
-                const float bin = ori * (8.0f / kTau);
+                // orientation relative to theta, wrapped to [0, 1) turns, then 8 bins
+                float turn = (gm[u].x - theta) * (1.0f / kTau);
+                turn -= floorf(turn);
+                const float bin = turn * 8.0f;
                 const int bi = (int)bin;                   // bin >= 0: truncation = floor
                 const float fb = bin - (float)bi;
                 const int b0 = bi & 7, b1 = (bi + 1) & 7;

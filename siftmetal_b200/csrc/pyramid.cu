@@ -113,8 +113,9 @@ cudaError_t launchGrayUpsample(const uint8_t* bgra, int pitchBytes, int64_t fram
 // 4 * odd floats: 8 lanes on 8 consecutive rows issuing LDS.128 / STS.128 hit 8 distinct
 // 4-bank groups, so the row-per-lane X pass is conflict-free; the Y pass walks columns with
 // consecutive lanes on consecutive x, also conflict-free.
-template <int NTAPS, int TX, int TY>
+template <int NTAPS, int TX, int TY, int NT>
 struct BlurCfg {
+    static constexpr int RY = TX * TY / (4 * NT);   // Y pass: 4 columns x RY rows per thread
     static constexpr int R = NTAPS / 2;
     static constexpr int RP = (R + 3) / 4 * 4;
     static constexpr int IN_W = TX + 2 * RP;
@@ -123,13 +124,12 @@ struct BlurCfg {
     static constexpr int TP = (TX % 8 == 4) ? TX : TX + 4;
     static constexpr int SMEM_FLOATS = IN_H * IP + IN_H * TP;
     static constexpr int XSEG = 8;   // outputs per thread in the X pass
-    static constexpr int RY = 8;     // outputs per thread in the Y pass
 };
 
-template <int NTAPS, int TX, int TY, int NT>
+template <int NTAPS, int TX, int TY, int NT, bool DOG, bool HALF>
 __global__ void __launch_bounds__(NT)
 blurKernel(const BlurArgs a, const __grid_constant__ Taps taps) {
-    using C = BlurCfg<NTAPS, TX, TY>;
+    using C = BlurCfg<NTAPS, TX, TY, NT>;
     constexpr int R = C::R, RP = C::RP, IN_W = C::IN_W, IN_H = C::IN_H, IP = C::IP, TP = C::TP;
     extern __shared__ __align__(16) float smem[];
     float* sIn = smem;
@@ -203,63 +203,96 @@ blurKernel(const BlurArgs a, const __grid_constant__ Taps taps) {
     }
     __syncthreads();
 
-    // ---- Y pass: one column, 8 consecutive rows per thread; fused DoG / decimation ---------
+    // ---- Y pass: 4 adjacent columns x RY rows per thread, streaming over the X-pass rows -----
+    // Row k of the X-pass result feeds output row q with tap i = k - q, so walking k upwards
+    // accumulates every output in ascending tap order (the spec's order) while only the RY
+    // float4 accumulators and one float4 of input are live. LDS.128 / STG.128 throughout.
     {
         constexpr int RY = C::RY;
+        constexpr int CGS = TX / 4;
+        static_assert(CGS * (TY / RY) == NT, "one Y-pass task per thread");
         float* __restrict__ out = a.out + (size_t)f * a.outFrameStride;
-        float* __restrict__ dog = a.dog ? a.dog + (size_t)f * a.dogFrameStride : nullptr;
-        float* __restrict__ half = a.half ? a.half + (size_t)f * a.halfFrameStride : nullptr;
-        for (int t = tid; t < TX * (TY / RY); t += NT) {
-            const int yb = t / TX, x = t - yb * TX;
-            const int gx = x0 + x;
-            float v[RY + 2 * R];
+        float* __restrict__ dog = DOG ? a.dog + (size_t)f * a.dogFrameStride : nullptr;
+        float* __restrict__ half = HALF ? a.half + (size_t)f * a.halfFrameStride : nullptr;
+        const int yb = tid / CGS, cg = tid - yb * CGS;
+        const int gx = x0 + 4 * cg;
+        float4 acc[RY];
 #pragma unroll
-            for (int k = 0; k < RY + 2 * R; k++) v[k] = sTmp[(yb * RY + k) * TP + x];
-            float acc[RY];
+        for (int q = 0; q < RY; q++) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int q = 0; q < RY; q++) acc[q] = 0.0f;
+        for (int k = 0; k < RY + 2 * R; k++) {
+            const float4 v = *reinterpret_cast<const float4*>(sTmp + (yb * RY + k) * TP + 4 * cg);
 #pragma unroll
-            for (int i = 0; i < NTAPS; i++) {
-                const float wi = taps.w[i];
-#pragma unroll
-                for (int q = 0; q < RY; q++) acc[q] = fmaf(wi, v[q + i], acc[q]);
+            for (int q = 0; q < RY; q++) {
+                const int i = k - q;
+                if (i >= 0 && i < NTAPS) {
+                    const float wi = taps.w[i];
+                    acc[q].x = fmaf(wi, v.x, acc[q].x);
+                    acc[q].y = fmaf(wi, v.y, acc[q].y);
+                    acc[q].z = fmaf(wi, v.z, acc[q].z);
+                    acc[q].w = fmaf(wi, v.w, acc[q].w);
+                }
             }
-            if (gx < w) {
+        }
+        const bool full = (x0 + TX <= w) && (y0 + TY <= h);   // CTA-uniform
 #pragma unroll
-                for (int q = 0; q < RY; q++) {
-                    const int gy = y0 + yb * RY + q;
-                    if (gy < h) {
-                        const size_t o = (size_t)gy * pitch + gx;
-                        out[o] = acc[q];
-                        if (dog) dog[o] = acc[q] - sIn[(yb * RY + q + R) * IP + RP + x];
-                        if (half && ((gx | gy) & 1) == 0 && (gx >> 1) < a.halfW &&
-                            (gy >> 1) < a.halfH)
-                            half[(size_t)(gy >> 1) * a.halfPitch + (gx >> 1)] = acc[q];
+        for (int q = 0; q < RY; q++) {
+            const int gy = y0 + yb * RY + q;
+            const size_t o = (size_t)gy * pitch + gx;
+            float4 d4;
+            if (DOG) {
+                const float4 c = *reinterpret_cast<const float4*>(sIn + (yb * RY + q + R) * IP + RP + 4 * cg);
+                d4 = make_float4(acc[q].x - c.x, acc[q].y - c.y, acc[q].z - c.z, acc[q].w - c.w);
+            }
+            if (full) {
+                *reinterpret_cast<float4*>(out + o) = acc[q];
+                if (DOG) *reinterpret_cast<float4*>(dog + o) = d4;
+            } else if (gy < h) {
+                const float av[4] = {acc[q].x, acc[q].y, acc[q].z, acc[q].w};
+                const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    if (gx + e < w) {
+                        out[o + e] = av[e];
+                        if (DOG) dog[o + e] = dv[e];
                     }
                 }
+            }
+            if (HALF && (gy & 1) == 0 && (gy >> 1) < a.halfH && gy < h) {
+                float* hrow = half + (size_t)(gy >> 1) * a.halfPitch + (gx >> 1);
+                if ((gx >> 1) < a.halfW && gx < w) hrow[0] = acc[q].x;
+                if ((gx >> 1) + 1 < a.halfW && gx + 2 < w) hrow[1] = acc[q].z;
             }
         }
     }
 }
 
-template <int NTAPS, int TX, int TY, int NT>
+template <int NTAPS, int TX, int TY, int NT, bool DOG, bool HALF>
 static cudaError_t launchBlurCfg(const BlurArgs& a, const Taps& taps, cudaStream_t st) {
-    using C = BlurCfg<NTAPS, TX, TY>;
+    using C = BlurCfg<NTAPS, TX, TY, NT>;
     static_assert(C::IN_W % 4 == 0 && C::IP % 8 == 4 && C::TP % 8 == 4, "bank layout");
-    static_assert(TX % C::XSEG == 0 && TY % C::RY == 0, "tile shape");
+    static_assert(TX % C::XSEG == 0 && C::RY >= 1 && TY % C::RY == 0, "tile shape");
     const int smemBytes = C::SMEM_FLOATS * (int)sizeof(float);
     static unsigned long long configured = 0;  // per-device bit: the attribute is per device
     int dev = 0;
     cudaGetDevice(&dev);
     if (!((configured >> (dev & 63)) & 1ull)) {
-        cudaError_t e = cudaFuncSetAttribute(blurKernel<NTAPS, TX, TY, NT>,
+        cudaError_t e = cudaFuncSetAttribute(blurKernel<NTAPS, TX, TY, NT, DOG, HALF>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes);
         if (e != cudaSuccess) return e;
         configured |= 1ull << (dev & 63);
     }
     dim3 grid((a.w + TX - 1) / TX, (a.h + TY - 1) / TY, a.frames);
-    blurKernel<NTAPS, TX, TY, NT><<<grid, NT, smemBytes, st>>>(a, taps);
+    blurKernel<NTAPS, TX, TY, NT, DOG, HALF><<<grid, NT, smemBytes, st>>>(a, taps);
     return cudaGetLastError();
+}
+
+template <int NTAPS, int TX, int TY, int NT>
+static cudaError_t launchBlurFlags(const BlurArgs& a, const Taps& taps, cudaStream_t st) {
+    if (a.dog && a.half) return launchBlurCfg<NTAPS, TX, TY, NT, true, true>(a, taps, st);
+    if (a.dog) return launchBlurCfg<NTAPS, TX, TY, NT, true, false>(a, taps, st);
+    if (a.half) return cudaErrorInvalidValue;
+    return launchBlurCfg<NTAPS, TX, TY, NT, false, false>(a, taps, st);
 }
 
 // Large planes: 64x64 tiles, 256 threads (least halo overhead). Planes that would not give every
@@ -268,8 +301,8 @@ static cudaError_t launchBlurCfg(const BlurArgs& a, const Taps& taps, cudaStream
 template <int NTAPS>
 static cudaError_t launchBlurT(const BlurArgs& a, const Taps& taps, cudaStream_t st) {
     const long tiles64 = (long)((a.w + 63) / 64) * ((a.h + 63) / 64) * a.frames;
-    if (tiles64 >= 2 * 148) return launchBlurCfg<NTAPS, 64, 64, 256>(a, taps, st);
-    return launchBlurCfg<NTAPS, 32, 32, 128>(a, taps, st);
+    if (tiles64 >= 2 * 148) return launchBlurFlags<NTAPS, 64, 64, 256>(a, taps, st);
+    return launchBlurFlags<NTAPS, 32, 32, 128>(a, taps, st);
 }
 
 cudaError_t launchBlur(const BlurArgs& a, const Taps& taps, int ntaps, cudaStream_t st) {
