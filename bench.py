@@ -207,14 +207,21 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     w, h, total, sharded = WORKLOADS[args.workload]
-    n_local = max(1, total // world) if sharded else total   # frames this rank owns per step
+    from siftmetal_b200.sharding import shard_range
+
+    if sharded:   # contiguous frame blocks per rank, no collective on the data path
+        first, last = shard_range(total, rank, world)
+        n_local = max(1, last - first)
+        frames_per_step_job = total
+    else:         # single-image workloads: one replica per GPU
+        first, n_local = 0, total
+        frames_per_step_job = total * world
     scaling = "strong" if sharded else "weak"
-    frames_per_step_job = n_local * world
     # frames resident per execute: bounded by memory (≈ 70 B per octave pixel, 5.33 octave px / px)
     per_frame_bytes = w * h * 5.34 * 76 + w * h * 8
     chunk = args.chunk or max(1, min(n_local, int(60e9 // per_frame_bytes)))
     eng = Engine(w, h, device=local, max_batch=chunk)
-    frames = make_frames(w, h, n_local, first_index=rank * n_local if sharded else 0)
+    frames = make_frames(w, h, n_local, first_index=first)
 
     # pinned host staging of this rank's frames (e2e path) — torch only as the pinned allocator
     pinned = torch.empty((n_local, h, w, 4), dtype=torch.uint8, pin_memory=True)

@@ -26,6 +26,7 @@ struct SiftContext {
     // octave o >= 1 runs its blur chain + gradient + extrema mask on its own stream as soon as
     // octave o-1 has produced Gaussian slice 3 (fork / join around the main stream)
     cudaStream_t octStream[kOctaves]{};
+
     cudaEvent_t evSeeded[kOctaves]{};   // octave o's slice 3 (and octave o+1's slice 0) written
     cudaEvent_t evOctDone[kOctaves]{};
     SiftInfo info{};
@@ -153,6 +154,7 @@ void destroy(SiftContext* c) {
         if (c->evSeeded[o]) cudaEventDestroy(c->evSeeded[o]);
         if (c->evOctDone[o]) cudaEventDestroy(c->evOctDone[o]);
         if (o > 0 && c->octStream[o]) cudaStreamDestroy(c->octStream[o]);
+
     }
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -342,6 +344,7 @@ int sift_create(const SiftConfig* cfg, int device, SiftContext** out) {
         if (o > 0) A(cudaStreamCreateWithFlags(&c->octStream[o], cudaStreamNonBlocking));
         A(cudaEventCreateWithFlags(&c->evSeeded[o], cudaEventDisableTiming));
         A(cudaEventCreateWithFlags(&c->evOctDone[o], cudaEventDisableTiming));
+
     }
     if (e != cudaSuccess) {
         const bool oom = (e == cudaErrorMemoryAllocation);
@@ -475,6 +478,8 @@ int runDetect(SiftContext* c) {
             if (s + 1 == kScales) CTX_TRY(c, cudaEventRecord(c->evSeeded[o], so));
         }
         if (T && o == 0) CTX_TRY(c, cudaEventRecord(c->evBlur0[kGaussians - 1], so));
+        // (running the gradient beside blur s = 3, 4 on a side stream was measured: no gain, the
+        // stage is throughput-bound, and it blurs the per-launch timing of the blur kernel)
         CTX_TRY(c, launchGradient(q, F, so));
         c->launches++;
         if (q.w >= 3 && q.h >= 3) {

@@ -259,31 +259,34 @@ descriptorKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __r
         const int side = 2 * radius + 1;
         const float a = cosT / hw, b = sinT / hw;   // rx = j a - i b, ry = j b + i a
 
-        // contributing span of every window row j (x offset): |rx| < 2.5 and |ry| < 2.5
+        // contributing span of every window row (y offset i): the x offsets j with |rx| < 2.5 and
+        // |ry| < 2.5. Lanes then walk x fastest, so a warp's gathers are contiguous in memory.
         int cnt[kDescMaxSide / 32];
 #pragma unroll
         for (int q = 0; q < kDescMaxSide / 32; q++) {
-            const int jj = q * 32 + lane;
+            const int ii = q * 32 + lane;
             int c = 0;
-            if (jj < side) {
-                const float fj = (float)(jj - radius);
+            if (ii < side) {
+                const float fi = (float)(ii - radius);
                 float lo1 = -1e30f, hi1 = 1e30f, lo2 = -1e30f, hi2 = 1e30f;
                 bool empty = false;
-                if (fabsf(b) > 1e-6f) {   // i b in (j a - 2.5, j a + 2.5)
-                    const float p = (fj * a - 2.5f) / b, q2 = (fj * a + 2.5f) / b;
+                if (fabsf(a) > 1e-6f) {   // j a in (i b - 2.5, i b + 2.5)
+                    const float p = (fi * b - 2.5f) / a, q2 = (fi * b + 2.5f) / a;
                     lo1 = fminf(p, q2); hi1 = fmaxf(p, q2);
-                } else if (!(fabsf(fj * a) < 2.5f + 1e-3f)) empty = true;
-                if (fabsf(a) > 1e-6f) {   // i a in (-2.5 - j b, 2.5 - j b)
-                    const float p = (-2.5f - fj * b) / a, q2 = (2.5f - fj * b) / a;
+                } else if (!(fabsf(fi * b) < 2.5f + 1e-3f)) empty = true;
+                if (fabsf(b) > 1e-6f) {   // j b in (-2.5 - i a, 2.5 - i a)
+                    const float p = (-2.5f - fi * a) / b, q2 = (2.5f - fi * a) / b;
                     lo2 = fminf(p, q2); hi2 = fmaxf(p, q2);
-                } else if (!(fabsf(fj * b) < 2.5f + 1e-3f)) empty = true;
-                // widened by < 1 on each side by the floor / ceil; the loop culls exactly.
-                // Image rows: sample y = trunc(py + i) must lie in [0, h).
-                const float flo = fmaxf(fmaxf(fmaxf(lo1, lo2), -(float)radius), -py);
-                const float fhi = fminf(fminf(fminf(hi1, hi2), (float)radius), (float)o.h - py);
-                const int ilo = (int)floorf(flo), ihi = (int)ceilf(fhi);
-                c = (empty || ihi < ilo) ? 0 : ihi - ilo + 1;
-                rowLo[jj] = ilo;
+                } else if (!(fabsf(fi * a) < 2.5f + 1e-3f)) empty = true;
+                // image: sample y = trunc(py + i) in [0, h); sample x = trunc(px + j) in [0, w)
+                const float cyf = py + fi;
+                if (cyf < 0.0f || (int)cyf >= o.h) empty = true;
+                // widened by < 1 on each side by the floor / ceil; the loop culls exactly
+                const float flo = fmaxf(fmaxf(fmaxf(lo1, lo2), -(float)radius), -px);
+                const float fhi = fminf(fminf(fminf(hi1, hi2), (float)radius), (float)o.w - px);
+                const int jlo = (int)floorf(flo), jhi = (int)ceilf(fhi);
+                c = (empty || jhi < jlo) ? 0 : jhi - jlo + 1;
+                rowLo[ii] = jlo;
             }
             cnt[q] = c;
         }
@@ -296,8 +299,8 @@ descriptorKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __r
                 const int nb = __shfl_up_sync(0xffffffffu, inc, dd);
                 if (lane >= dd) inc += nb;
             }
-            const int jj = q * 32 + lane;
-            if (jj < side) rowStart[jj] = base + inc - cnt[q];
+            const int ii = q * 32 + lane;
+            if (ii < side) rowStart[ii] = base + inc - cnt[q];
             base += __shfl_sync(0xffffffffu, inc, 31);
         }
         const int total = base;
@@ -318,8 +321,8 @@ descriptorKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __r
                 ok[u] = false;
                 if (idx < total) {
                     while (idx >= rowStart[row + 1]) row++;
-                    const int i = rowLo[row] + (idx - rowStart[row]);   // y offset
-                    const float fj = (float)(row - radius), fi = (float)i;
+                    const int j = rowLo[row] + (idx - rowStart[row]);   // x offset
+                    const float fj = (float)j, fi = (float)(row - radius);
                     const float rx = fj * a - fi * b;
                     const float ry = fj * b + fi * a;
                     const float bx = rx + 1.5f, by = ry + 1.5f;

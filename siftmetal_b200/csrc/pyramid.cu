@@ -7,10 +7,29 @@
 //   Convolution.metal:15-52, ConvolutionSeries.metal:16-53 (X then Y),
 //   Subtract.metal:12-21, NearestNeighborDownScale.metal:15-22            → blurKernel
 //   SIFTGradient.metal:15-39                                              → gradientKernel
+#include <algorithm>
+
 #include "common.cuh"
 #include "dev_math.cuh"
 
 namespace sift {
+
+// Packed fp32x2 FMA (sm_100 FFMA2): two independent IEEE fused multiply-adds per instruction,
+// bit-identical to two fmaf(). Halves the issue slots of the convolution inner loops.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
 
 // Common.hpp:15-22 symmetrizedCoordinates (floor-mod form, identical for i >= -2l).
 __device__ __forceinline__ int symmetrized(int i, int l) {
@@ -107,12 +126,15 @@ cudaError_t launchGrayUpsample(const uint8_t* bgra, int pitchBytes, int64_t fram
 //   half = out[2y][2x]         (NearestNeighborDownScale.metal, seeds the next octave)
 // Per output pixel the accumulation is sum = fma(w[i], c, sum), i ascending, as the oracle.
 //
-// Tile: TX x TY outputs per CTA of 256 threads. Shared memory holds the input tile with halo
-// (rows TY + 2R, columns TX + 2RP, RP = R rounded up to 4 so that rows stay 16-byte aligned
-// with global memory) and the X-pass result (rows TY + 2R, columns TX). Both row pitches are
-// 4 * odd floats: 8 lanes on 8 consecutive rows issuing LDS.128 / STS.128 hit 8 distinct
-// 4-bank groups, so the row-per-lane X pass is conflict-free; the Y pass walks columns with
-// consecutive lanes on consecutive x, also conflict-free.
+// One CTA per TX x TY output tile (tiles of all frames in one linear grid). The input tile with
+// halo (rows TY + 2R, columns TX + 2RP, RP = R rounded up to 4 so that rows stay 16-byte aligned
+// with global memory) arrives by cp.async; a second buffer holds the X-pass result (rows
+// TY + 2R, columns TX). (BlurCfg::NBUF = 2 turns the kernel into persistent CTAs with the next
+// tile's copies in flight during the current tile's FMAs; measured slower on B200 because the
+// doubled shared memory leaves 2 instead of 3 CTAs per SM.) All row pitches are 4 * odd floats: 8 lanes on 8 consecutive rows issuing
+// LDS.128 / STS.128 hit 8 distinct 4-bank groups, so the row-per-lane X pass is conflict-free;
+// the Y pass reads float4 columns with consecutive lanes on consecutive groups, also
+// conflict-free.
 template <int NTAPS, int TX, int TY, int NT>
 struct BlurCfg {
     static constexpr int RY = TX * TY / (4 * NT);   // Y pass: 4 columns x RY rows per thread
@@ -122,7 +144,8 @@ struct BlurCfg {
     static constexpr int IN_H = TY + 2 * R;
     static constexpr int IP = (IN_W % 8 == 4) ? IN_W : IN_W + 4;  // IN_W is a multiple of 4
     static constexpr int TP = (TX % 8 == 4) ? TX : TX + 4;
-    static constexpr int SMEM_FLOATS = IN_H * IP + IN_H * TP;
+    static constexpr int NBUF = 1;   // input buffers (2 = persistent CTAs with prefetch; measured slower: fewer resident warps)
+    static constexpr int SMEM_FLOATS = NBUF * IN_H * IP + IN_H * TP;
     static constexpr int XSEG = 8;   // outputs per thread in the X pass
 };
 
@@ -132,137 +155,171 @@ blurKernel(const BlurArgs a, const __grid_constant__ Taps taps) {
     using C = BlurCfg<NTAPS, TX, TY, NT>;
     constexpr int R = C::R, RP = C::RP, IN_W = C::IN_W, IN_H = C::IN_H, IP = C::IP, TP = C::TP;
     extern __shared__ __align__(16) float smem[];
-    float* sIn = smem;
-    float* sTmp = smem + IN_H * IP;
+    float* sTmp = smem + C::NBUF * IN_H * IP;
 
     const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
-    const int f = blockIdx.z;
-    const float* __restrict__ in = a.in + (size_t)f * a.inFrameStride;
     const int w = a.w, h = a.h, pitch = a.pitch;
+    const int tilesX = (w + TX - 1) / TX, tilesY = (h + TY - 1) / TY;
+    const int tilesPerFrame = tilesX * tilesY;
+    const int nTiles = tilesPerFrame * a.frames;
 
-    // ---- load the input tile with halo --------------------------------------------------
-    const bool interior = (x0 - RP >= 0) && (x0 + TX + RP <= w) && (y0 - R >= 0) &&
-                          (y0 + TY + R <= h);
-    if (interior) {
-        constexpr int V = IN_W / 4;
-        const float* base = in + (size_t)(y0 - R) * pitch + (x0 - RP);
-        for (int idx = tid; idx < IN_H * V; idx += NT) {
-            const int r = idx / V, c4 = idx - r * V;
-            const float* g = base + (size_t)r * pitch + 4 * c4;
-            const unsigned s = (unsigned)__cvta_generic_to_shared(sIn + r * IP + 4 * c4);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(g));
-        }
-        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
-    } else {
-        // edge tile: mirror boundary. One warp per row (row index reflected once per warp),
-        // lanes across columns with a single-reflection fast path.
-        const int lane = tid & 31, wid = tid >> 5;
-        for (int r = wid; r < IN_H; r += NT / 32) {
-            const int gy = symmetrized(y0 - R + r, h);
-            const float* __restrict__ srow = in + (size_t)gy * pitch;
-            for (int c = lane; c < IN_W; c += 32) {
-                int gx = x0 - RP + c;
-                if (gx < 0) gx = -1 - gx;
-                else if (gx >= w) gx = 2 * w - 1 - gx;
-                if (gx < 0 || gx >= w) gx = symmetrized(x0 - RP + c, w);
-                const unsigned s = (unsigned)__cvta_generic_to_shared(sIn + r * IP + c);
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(srow + gx));
+    // ---- asynchronous load of one input tile with halo -----------------------------------
+    auto issueLoad = [&](int tile, float* sIn) {
+        const int f = tile / tilesPerFrame;
+        const int tr = tile - f * tilesPerFrame;
+        const int ty = tr / tilesX, tx = tr - ty * tilesX;
+        const int x0 = tx * TX, y0 = ty * TY;
+        const float* __restrict__ in = a.in + (size_t)f * a.inFrameStride;
+        const bool interior = (x0 - RP >= 0) && (x0 + TX + RP <= w) && (y0 - R >= 0) &&
+                              (y0 + TY + R <= h);
+        if (interior) {
+            constexpr int V = IN_W / 4;
+            const float* base = in + (size_t)(y0 - R) * pitch + (x0 - RP);
+            for (int idx = tid; idx < IN_H * V; idx += NT) {
+                const int r = idx / V, c4 = idx - r * V;
+                const float* g = base + (size_t)r * pitch + 4 * c4;
+                const unsigned s = (unsigned)__cvta_generic_to_shared(sIn + r * IP + 4 * c4);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(g));
             }
-        }
-        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
-    }
-    __syncthreads();
-
-    // ---- X pass: one row, 8 consecutive outputs per thread ---------------------------------
-    {
-        constexpr int SEGS = TX / C::XSEG;
-        constexpr int NV = (C::XSEG + 2 * RP) / 4;
-        for (int t = tid; t < IN_H * SEGS; t += NT) {
-            const int seg = t / IN_H, r = t - seg * IN_H;
-            const float4* src = reinterpret_cast<const float4*>(sIn + r * IP + seg * C::XSEG);
-            float v[NV * 4];
-#pragma unroll
-            for (int k = 0; k < NV; k++) {
-                const float4 q = src[k];
-                v[4 * k + 0] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
-            }
-            float acc[C::XSEG];
-#pragma unroll
-            for (int k = 0; k < C::XSEG; k++) acc[k] = 0.0f;
-#pragma unroll
-            for (int i = 0; i < NTAPS; i++) {
-                const float wi = taps.w[i];
-#pragma unroll
-                for (int k = 0; k < C::XSEG; k++) acc[k] = fmaf(wi, v[k + (RP - R) + i], acc[k]);
-            }
-            float4* dst = reinterpret_cast<float4*>(sTmp + r * TP + seg * C::XSEG);
-            dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-            dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-        }
-    }
-    __syncthreads();
-
-    // ---- Y pass: 4 adjacent columns x RY rows per thread, streaming over the X-pass rows -----
-    // Row k of the X-pass result feeds output row q with tap i = k - q, so walking k upwards
-    // accumulates every output in ascending tap order (the spec's order) while only the RY
-    // float4 accumulators and one float4 of input are live. LDS.128 / STG.128 throughout.
-    {
-        constexpr int RY = C::RY;
-        constexpr int CGS = TX / 4;
-        static_assert(CGS * (TY / RY) == NT, "one Y-pass task per thread");
-        float* __restrict__ out = a.out + (size_t)f * a.outFrameStride;
-        float* __restrict__ dog = DOG ? a.dog + (size_t)f * a.dogFrameStride : nullptr;
-        float* __restrict__ half = HALF ? a.half + (size_t)f * a.halfFrameStride : nullptr;
-        const int yb = tid / CGS, cg = tid - yb * CGS;
-        const int gx = x0 + 4 * cg;
-        float4 acc[RY];
-#pragma unroll
-        for (int q = 0; q < RY; q++) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int k = 0; k < RY + 2 * R; k++) {
-            const float4 v = *reinterpret_cast<const float4*>(sTmp + (yb * RY + k) * TP + 4 * cg);
-#pragma unroll
-            for (int q = 0; q < RY; q++) {
-                const int i = k - q;
-                if (i >= 0 && i < NTAPS) {
-                    const float wi = taps.w[i];
-                    acc[q].x = fmaf(wi, v.x, acc[q].x);
-                    acc[q].y = fmaf(wi, v.y, acc[q].y);
-                    acc[q].z = fmaf(wi, v.z, acc[q].z);
-                    acc[q].w = fmaf(wi, v.w, acc[q].w);
+        } else {
+            // edge tile: mirror boundary. One warp per row (row index reflected once per warp),
+            // lanes across columns with a single-reflection fast path.
+            const int lane = tid & 31, wid = tid >> 5;
+            for (int r = wid; r < IN_H; r += NT / 32) {
+                const int gy = symmetrized(y0 - R + r, h);
+                const float* __restrict__ srow = in + (size_t)gy * pitch;
+                for (int c = lane; c < IN_W; c += 32) {
+                    int gx = x0 - RP + c;
+                    if (gx < 0) gx = -1 - gx;
+                    else if (gx >= w) gx = 2 * w - 1 - gx;
+                    if (gx < 0 || gx >= w) gx = symmetrized(x0 - RP + c, w);
+                    const unsigned s = (unsigned)__cvta_generic_to_shared(sIn + r * IP + c);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(srow + gx));
                 }
             }
         }
-        const bool full = (x0 + TX <= w) && (y0 + TY <= h);   // CTA-uniform
+    };
+
+    int tile = blockIdx.x;
+    if (tile >= nTiles) return;
+    issueLoad(tile, smem);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    for (int buf = 0; tile < nTiles; tile += gridDim.x, buf ^= 1) {
+        float* sIn = smem + (C::NBUF == 2 ? buf : 0) * (IN_H * IP);
+        if (C::NBUF == 2) {
+            if (tile + (int)gridDim.x < nTiles) issueLoad(tile + gridDim.x, smem + (buf ^ 1) * (IN_H * IP));
+            asm volatile("cp.async.commit_group;\ncp.async.wait_group 1;\n" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        }
+        __syncthreads();
+
+        const int f = tile / tilesPerFrame;
+        const int tr = tile - f * tilesPerFrame;
+        const int ty = tr / tilesX, tx = tr - ty * tilesX;
+        const int x0 = tx * TX, y0 = ty * TY;
+
+        // ---- X pass: one row, 8 consecutive outputs per thread -----------------------------
+        {
+            constexpr int SEGS = TX / C::XSEG;
+            constexpr int NV = (C::XSEG + 2 * RP) / 4;
+            for (int t = tid; t < IN_H * SEGS; t += NT) {
+                const int seg = t / IN_H, r = t - seg * IN_H;
+                const float4* src = reinterpret_cast<const float4*>(sIn + r * IP + seg * C::XSEG);
+                float v[NV * 4];
 #pragma unroll
-        for (int q = 0; q < RY; q++) {
-            const int gy = y0 + yb * RY + q;
-            const size_t o = (size_t)gy * pitch + gx;
-            float4 d4;
-            if (DOG) {
-                const float4 c = *reinterpret_cast<const float4*>(sIn + (yb * RY + q + R) * IP + RP + 4 * cg);
-                d4 = make_float4(acc[q].x - c.x, acc[q].y - c.y, acc[q].z - c.z, acc[q].w - c.w);
+                for (int k = 0; k < NV; k++) {
+                    const float4 q = src[k];
+                    v[4 * k + 0] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+                }
+                float acc[C::XSEG];
+#pragma unroll
+                for (int k = 0; k < C::XSEG; k++) acc[k] = 0.0f;
+#pragma unroll
+                for (int i = 0; i < NTAPS; i++) {
+                    const float wi = taps.w[i];
+#pragma unroll
+                    for (int k = 0; k < C::XSEG; k++) acc[k] = fmaf(wi, v[k + (RP - R) + i], acc[k]);
+                }
+                float4* dst = reinterpret_cast<float4*>(sTmp + r * TP + seg * C::XSEG);
+                dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
             }
-            if (full) {
-                *reinterpret_cast<float4*>(out + o) = acc[q];
-                if (DOG) *reinterpret_cast<float4*>(dog + o) = d4;
-            } else if (gy < h) {
-                const float av[4] = {acc[q].x, acc[q].y, acc[q].z, acc[q].w};
-                const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+        }
+        __syncthreads();
+
+        // ---- Y pass: 4 adjacent columns x RY rows per thread, streaming over X-pass rows -------
+        // Row k of the X-pass result feeds output row q with tap i = k - q, so walking k upwards
+        // accumulates every output in ascending tap order (the spec's order) while only the RY
+        // accumulator quads and one float4 of input are live. Packed fp32x2 FMAs (FFMA2),
+        // LDS.128 / STG.128 throughout.
+        {
+            constexpr int RY = C::RY;
+            constexpr int CGS = TX / 4;
+            static_assert(CGS * (TY / RY) == NT, "one Y-pass task per thread");
+            float* __restrict__ out = a.out + (size_t)f * a.outFrameStride;
+            float* __restrict__ dog = DOG ? a.dog + (size_t)f * a.dogFrameStride : nullptr;
+            float* __restrict__ half = HALF ? a.half + (size_t)f * a.halfFrameStride : nullptr;
+            const int yb = tid / CGS, cg = tid - yb * CGS;
+            const int gx = x0 + 4 * cg;
+            f32x2 accA[RY], accB[RY];   // columns (0,1) and (2,3) of each output row
 #pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    if (gx + e < w) {
-                        out[o + e] = av[e];
-                        if (DOG) dog[o + e] = dv[e];
+            for (int q = 0; q < RY; q++) accA[q] = accB[q] = pack2(0.0f, 0.0f);
+#pragma unroll
+            for (int k = 0; k < RY + 2 * R; k++) {
+                const float4 v = *reinterpret_cast<const float4*>(sTmp + (yb * RY + k) * TP + 4 * cg);
+                const f32x2 vA = pack2(v.x, v.y), vB = pack2(v.z, v.w);
+#pragma unroll
+                for (int q = 0; q < RY; q++) {
+                    const int i = k - q;
+                    if (i >= 0 && i < NTAPS) {
+                        const f32x2 wi = pack2(taps.w[i], taps.w[i]);
+                        accA[q] = fma2(wi, vA, accA[q]);
+                        accB[q] = fma2(wi, vB, accB[q]);
                     }
                 }
             }
-            if (HALF && (gy & 1) == 0 && (gy >> 1) < a.halfH && gy < h) {
-                float* hrow = half + (size_t)(gy >> 1) * a.halfPitch + (gx >> 1);
-                if ((gx >> 1) < a.halfW && gx < w) hrow[0] = acc[q].x;
-                if ((gx >> 1) + 1 < a.halfW && gx + 2 < w) hrow[1] = acc[q].z;
+            float4 acc[RY];
+#pragma unroll
+            for (int q = 0; q < RY; q++) {
+                unpack2(accA[q], acc[q].x, acc[q].y);
+                unpack2(accB[q], acc[q].z, acc[q].w);
             }
+            const bool full = (x0 + TX <= w) && (y0 + TY <= h);   // CTA-uniform
+#pragma unroll
+            for (int q = 0; q < RY; q++) {
+                const int gy = y0 + yb * RY + q;
+                const size_t o = (size_t)gy * pitch + gx;
+                float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (DOG) {
+                    const float4 c = *reinterpret_cast<const float4*>(sIn + (yb * RY + q + R) * IP + RP + 4 * cg);
+                    d4 = make_float4(acc[q].x - c.x, acc[q].y - c.y, acc[q].z - c.z, acc[q].w - c.w);
+                }
+                if (full) {
+                    *reinterpret_cast<float4*>(out + o) = acc[q];
+                    if (DOG) *reinterpret_cast<float4*>(dog + o) = d4;
+                } else if (gy < h) {
+                    const float av[4] = {acc[q].x, acc[q].y, acc[q].z, acc[q].w};
+                    const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        if (gx + e < w) {
+                            out[o + e] = av[e];
+                            if (DOG) dog[o + e] = dv[e];
+                        }
+                    }
+                }
+                if (HALF && (gy & 1) == 0 && (gy >> 1) < a.halfH && gy < h) {
+                    float* hrow = half + (size_t)(gy >> 1) * a.halfPitch + (gx >> 1);
+                    if ((gx >> 1) < a.halfW && gx < w) hrow[0] = acc[q].x;
+                    if ((gx >> 1) + 1 < a.halfW && gx + 2 < w) hrow[1] = acc[q].z;
+                }
+            }
+        }
+        __syncthreads();   // sTmp and this input buffer are reused by the next iterations
+        if (C::NBUF == 1 && tile + (int)gridDim.x < nTiles) {
+            issueLoad(tile + gridDim.x, smem);
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
         }
     }
 }
@@ -273,16 +330,25 @@ static cudaError_t launchBlurCfg(const BlurArgs& a, const Taps& taps, cudaStream
     static_assert(C::IN_W % 4 == 0 && C::IP % 8 == 4 && C::TP % 8 == 4, "bank layout");
     static_assert(TX % C::XSEG == 0 && C::RY >= 1 && TY % C::RY == 0, "tile shape");
     const int smemBytes = C::SMEM_FLOATS * (int)sizeof(float);
-    static unsigned long long configured = 0;  // per-device bit: the attribute is per device
+    static int ctasPerSm[64] = {};   // per device: resident CTAs per SM for this instantiation
+    static int smCount[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (!((configured >> (dev & 63)) & 1ull)) {
-        cudaError_t e = cudaFuncSetAttribute(blurKernel<NTAPS, TX, TY, NT, DOG, HALF>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes);
-        if (e != cudaSuccess) return e;
-        configured |= 1ull << (dev & 63);
+    dev &= 63;
+    if (ctasPerSm[dev] == 0) {
+        auto kernel = blurKernel<NTAPS, TX, TY, NT, DOG, HALF>;
+        SIFT_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes));
+        int n = 0, sms = 0;
+        SIFT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, NT, smemBytes));
+        SIFT_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        if (n < 1) return cudaErrorLaunchOutOfResources;
+        smCount[dev] = sms;
+        ctasPerSm[dev] = n;
     }
-    dim3 grid((a.w + TX - 1) / TX, (a.h + TY - 1) / TY, a.frames);
+    const long nTiles = (long)((a.w + TX - 1) / TX) * ((a.h + TY - 1) / TY) * a.frames;
+    // one tile per CTA unless the grid would exceed what a launch may carry; with NBUF == 2 the
+    // grid is the resident set and CTAs loop with the next tile's copies in flight
+    const int grid = (int)std::min<long>(nTiles, C::NBUF == 2 ? (long)smCount[dev] * ctasPerSm[dev] : 2147483647L);
     blurKernel<NTAPS, TX, TY, NT, DOG, HALF><<<grid, NT, smemBytes, st>>>(a, taps);
     return cudaGetLastError();
 }
