@@ -58,6 +58,7 @@ struct SiftContext {
     int* dNOri = nullptr;
     float* dOriTmp = nullptr;
     int* dOriOffset = nullptr;
+    int* dDescKp = nullptr;
     SiftDescriptor* dDesc = nullptr;
     Counters* dCounters = nullptr;
 
@@ -329,6 +330,7 @@ int sift_create(const SiftConfig* cfg, int device, SiftContext** out) {
     A(devAlloc(c, &c->dOriTmp, (size_t)c->capKp * kOriBins));
     A(devAlloc(c, &c->dOriOffset, (size_t)c->capKp + kScanChunk + 1));
     A(devAlloc(c, &c->dDesc, (size_t)c->capDesc));
+    A(devAlloc(c, &c->dDescKp, (size_t)c->capDesc));
     A(devAlloc(c, &c->dCounters, 1));
     if (e == cudaSuccess) A(cudaMemset(c->dMask, 0, maskWords * sizeof(uint32_t)));
     if (e == cudaSuccess) A(cudaMemset(c->dSegStarts, 0, 3 * (size_t)(c->nSegs + 1) * sizeof(int)));
@@ -515,7 +517,7 @@ int runDescribe(SiftContext* c, int nSegs) {
     cudaStream_t st = c->stream;
     const bool T = c->stageTiming;
     CTX_TRY(c, launchDescribe(c->P, c->dKps, c->dKpSeg, c->capKp, c->dSegStarts + (c->nSegs + 1),
-                              c->dNOri, c->dOriTmp, c->dOriOffset, c->dBlockSums, c->dDesc,
+                              c->dNOri, c->dOriTmp, c->dOriOffset, c->dDescKp, c->dBlockSums, c->dDesc,
                               c->capDesc, c->dSegStarts + 2 * (c->nSegs + 1), nSegs, c->dCounters,
                               c->smCount, st, T ? c->ev[5] : nullptr));
     c->launches += 6;

@@ -116,7 +116,7 @@ cudaError_t launchRefine(const EngineParams& P, const Candidate* cands, int capC
 // describe.cu
 cudaError_t launchDescribe(const EngineParams& P, const SiftKeypoint* kps, const int* kpSeg,
                            int capKeypoints, const int* segKpStart, int* nOri, float* oriTmp,
-                           int* oriOffset, int* blockSums, SiftDescriptor* desc,
+                           int* oriOffset, int* descKp, int* blockSums, SiftDescriptor* desc,
                            int capDescriptors, int* segDescStart, int nSegs, Counters* counters,
                            int smCount, cudaStream_t stream, cudaEvent_t afterOrientation);
 

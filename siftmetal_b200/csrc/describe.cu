@@ -172,7 +172,8 @@ struct OriCount {
 // Phase C for orientation counts: exclusive offsets per keypoint (+ one past the end).
 __global__ void __launch_bounds__(kScanThreads)
 oriOffsetsKernel(const int* __restrict__ nOri, const Counters* __restrict__ counters,
-                 const int* __restrict__ blockOffsets, int* __restrict__ oriOffset) {
+                 const int* __restrict__ blockOffsets, int* __restrict__ oriOffset,
+                 int* __restrict__ descKp, int capDescriptors) {
     __shared__ int sh[9];
     const int n = counters->nKeypoints;
     const int i0 = blockIdx.x * kScanChunk + threadIdx.x * kScanItemsPerThread;
@@ -188,6 +189,8 @@ oriOffsetsKernel(const int* __restrict__ nOri, const Counters* __restrict__ coun
 #pragma unroll
     for (int k = 0; k < kScanItemsPerThread; k++) {
         if ((i0 + k) <= n) oriOffset[i0 + k] = pos;
+        for (int t = 0; t < v[k]; t++)   // owner of each descriptor: no search in the descriptor kernel
+            if (pos + t < capDescriptors) descKp[pos + t] = i0 + k;
         pos += v[k];
     }
 }
@@ -205,39 +208,29 @@ __global__ void descSegmentStartsKernel(const int* __restrict__ segKpStart,
 // Descriptor. One warp per (keypoint, theta). The reference walks the whole (2·radius+1)^2
 // window and lets addValue drop what falls outside the 4x4 grid (SIFTDescriptor.metal:53-79);
 // only samples inside the rotated square |rx|, |ry| < 2.5 can contribute, so each window row's
-// contributing span is computed analytically (widened by one pixel, then culled by the same
+// contributing span is computed analytically (widened by < 1 pixel, then culled by the same
 // test the reference's cell bounds imply) and the lanes walk the flattened spans densely.
 // Window radius, sample coordinates and centre truncation follow the spec's exact sequences;
 // per-sample weights use FMA / reciprocal / ex2.approx — continuous quantities within the ±1
 // tolerance of the quantised features.
 constexpr int kDescWarps = 2;      // 2 warps x 16 KB of lane-private histograms = 32 KB per CTA
 constexpr int kDescMaxSide = 128;  // 2·radius+1; radius <= 39 for detected keypoints
+constexpr int kDescBins = 128;
 
 __global__ void __launch_bounds__(kDescWarps * 32)
 descriptorKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __restrict__ kps,
                  const int* __restrict__ kpSeg, const int* __restrict__ segKpStart,
                  const Counters* __restrict__ counters, const int* __restrict__ oriOffset,
-                 const float* __restrict__ oriTmp, SiftDescriptor* __restrict__ desc,
-                 int capacity) {
+                 const float* __restrict__ oriTmp, const int* __restrict__ descKp,
+                 SiftDescriptor* __restrict__ desc, int capacity) {
     extern __shared__ __align__(16) float sDesc[];  // [warp][128 bins][32 lanes]
-    __shared__ int sRowStart[kDescWarps][kDescMaxSide + 1];
-    __shared__ int sRowLo[kDescWarps][kDescMaxSide];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    float* hist = sDesc + wid * (128 * 32);
-    int* rowStart = sRowStart[wid];
-    int* rowLo = sRowLo[wid];
+    float* hist = sDesc + wid * (kDescBins * 32);
     const int nKp = counters->nKeypoints;
     int nDesc = oriOffset[nKp];
     if (nDesc > capacity) nDesc = capacity;
     for (int d = blockIdx.x * kDescWarps + wid; d < nDesc; d += gridDim.x * kDescWarps) {
-        // keypoint owning descriptor d: last k with oriOffset[k] <= d
-        int lo = 0, hi = nKp;
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (oriOffset[mid] <= d) lo = mid;
-            else hi = mid;
-        }
-        const int k = lo;
+        const int k = descKp[d];   // keypoint owning descriptor d
         const SiftKeypoint kp = kps[k];
         const int frame = kpSeg[k] / kOctaves;
         const float theta = oriTmp[(size_t)k * kOriBins + (d - oriOffset[k])];
@@ -256,93 +249,77 @@ descriptorKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __r
         int radius = (int)__fadd_rn(
             __fmul_rn(__fmul_rn(__fmul_rn(hw, sqrtf(2.0f)), 5.0f), 0.5f), 0.5f);
         radius = max(0, min(radius, (kDescMaxSide - 1) / 2));
-        const int side = 2 * radius + 1;
         const float a = cosT / hw, b = sinT / hw;   // rx = j a - i b, ry = j b + i a
 
-        // contributing span of every window row (y offset i): the x offsets j with |rx| < 2.5 and
-        // |ry| < 2.5. Lanes then walk x fastest, so a warp's gathers are contiguous in memory.
-        int cnt[kDescMaxSide / 32];
-#pragma unroll
-        for (int q = 0; q < kDescMaxSide / 32; q++) {
-            const int ii = q * 32 + lane;
-            int c = 0;
-            if (ii < side) {
-                const float fi = (float)(ii - radius);
-                float lo1 = -1e30f, hi1 = 1e30f, lo2 = -1e30f, hi2 = 1e30f;
-                bool empty = false;
-                if (fabsf(a) > 1e-6f) {   // j a in (i b - 2.5, i b + 2.5)
-                    const float p = (fi * b - 2.5f) / a, q2 = (fi * b + 2.5f) / a;
-                    lo1 = fminf(p, q2); hi1 = fmaxf(p, q2);
-                } else if (!(fabsf(fi * b) < 2.5f + 1e-3f)) empty = true;
-                if (fabsf(b) > 1e-6f) {   // j b in (-2.5 - i a, 2.5 - i a)
-                    const float p = (-2.5f - fi * a) / b, q2 = (2.5f - fi * a) / b;
-                    lo2 = fminf(p, q2); hi2 = fmaxf(p, q2);
-                } else if (!(fabsf(fi * a) < 2.5f + 1e-3f)) empty = true;
-                // image: sample y = trunc(py + i) in [0, h); sample x = trunc(px + j) in [0, w)
-                const float cyf = py + fi;
-                if (cyf < 0.0f || (int)cyf >= o.h) empty = true;
-                // widened by < 1 on each side by the floor / ceil; the loop culls exactly
-                const float flo = fmaxf(fmaxf(fmaxf(lo1, lo2), -(float)radius), -px);
-                const float fhi = fminf(fminf(fminf(hi1, hi2), (float)radius), (float)o.w - px);
-                const int jlo = (int)floorf(flo), jhi = (int)ceilf(fhi);
-                c = (empty || jhi < jlo) ? 0 : jhi - jlo + 1;
-                rowLo[ii] = jlo;
-            }
-            cnt[q] = c;
-        }
-        int base = 0;
-#pragma unroll
-        for (int q = 0; q < kDescMaxSide / 32; q++) {
-            int inc = cnt[q];
-#pragma unroll
-            for (int dd = 1; dd < 32; dd <<= 1) {
-                const int nb = __shfl_up_sync(0xffffffffu, inc, dd);
-                if (lane >= dd) inc += nb;
-            }
-            const int ii = q * 32 + lane;
-            if (ii < side) rowStart[ii] = base + inc - cnt[q];
-            base += __shfl_sync(0xffffffffu, inc, 31);
-        }
-        const int total = base;
-        if (lane == 0) rowStart[side] = total;
+        // Contributing span of window row i (y offset): x offsets j with |rx| < 2.5 and |ry| < 2.5,
+        //   |j a - i b| < 2.5  ->  j in (i s1 - c1, i s1 + c1),  s1 =  b / a, c1 = 2.5 / |a|
+        //   |j b + i a| < 2.5  ->  j in (i s2 - c2, i s2 + c2),  s2 = -a / b, c2 = 2.5 / |b|
+        // intersected with the window and the plane. Both lines are linear in i, so every lane
+        // derives the bounds of the row it is in with two FMAs per side — no tables, no dependent
+        // shared-memory look-ups. (|a|, |b| are floored at 1e-6 for the span only: it stays a
+        // superset; the exact cull below uses the true a, b.) Lanes walk x fastest, so a warp's
+        // gathers are contiguous in memory.
+        const float ae = copysignf(fmaxf(fabsf(a), 1e-6f), a), be = copysignf(fmaxf(fabsf(b), 1e-6f), b);
+        const float s1 = b / ae, c1 = 2.5f / fabsf(ae);
+        const float s2 = -a / be, c2 = 2.5f / fabsf(be);
+        // sample (x, y) = (trunc(px + j), trunc(py + i)) = (ipx + j, ipy + i) wherever px + j >= 0:
+        // px, py are multiples of 1/delta and small, so the float sums of the spec are exact
+        const int ipx = (int)floorf(px), ipy = (int)floorf(py);
+        const float xlo = fmaxf(-(float)radius, (float)(-ipx)), xhi = fminf((float)radius, (float)(o.w - 1 - ipx));
+        const int iMin = max(-radius, -ipy);
+        const int iMax = min(radius, o.h - 1 - ipy);
+
 #pragma unroll 8
         for (int bb = 0; bb < 128; bb++) hist[bb * 32 + lane] = 0.0f;
-        __syncwarp();
 
-        int row = 0;
-        // four gathers in flight per lane (latency-bound loop); accumulation afterwards, in order
-        for (int base = 0; base < total; base += 128) {
+        // lane state: row i, first x offset jlo of the row's span, span length n, position pos,
+        // gradient row pointer (already offset by ipx)
+        int i = iMin, jlo = 0, n = 0, pos = lane;
+        const float2* __restrict__ grow = g;
+        auto rowBounds = [&]() {
+            const float fi = (float)i;
+            const float lo = fmaxf(fmaxf(fmaf(fi, s1, -c1), fmaf(fi, s2, -c2)), xlo);
+            const float hi = fminf(fminf(fmaf(fi, s1, c1), fmaf(fi, s2, c2)), xhi);
+            jlo = (int)ceilf(lo - 1.0f);                 // widened by < 1 on each side, still in the plane
+            jlo = max(jlo, -ipx);
+            n = max(min((int)floorf(hi + 1.0f), o.w - 1 - ipx) - jlo + 1, 0);
+            grow = g + (size_t)(ipy + min(i, iMax)) * o.pitch + ipx;
+        };
+        auto settle = [&]() {   // move to the row that contains position pos
+            while (i <= iMax && pos >= n) {
+                pos -= n;
+                i++;
+                rowBounds();
+            }
+        };
+        rowBounds();
+        settle();
+        char* const hl = reinterpret_cast<char*>(hist + lane);
+        while (__any_sync(0xffffffffu, i <= iMax)) {
+            // phase 1: four samples per lane, coordinates + gather issued back to back
             float2 gm[4];
             float bxs[4], bys[4], r2s[4];
             bool ok[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const int idx = base + u * 32 + lane;
-                ok[u] = false;
-                if (idx < total) {
-                    while (idx >= rowStart[row + 1]) row++;
-                    const int j = rowLo[row] + (idx - rowStart[row]);   // x offset
-                    const float fj = (float)j, fi = (float)(row - radius);
-                    const float rx = fj * a - fi * b;
-                    const float ry = fj * b + fi * a;
-                    const float bx = rx + 1.5f, by = ry + 1.5f;
-                    // addValue drops cells outside [0, 4): nothing lands unless -1 < b < 4
-                    if (bx > -1.0f && bx < 4.0f && by > -1.0f && by < 4.0f) {
-                        const float cxf = __fadd_rn(px, fj), cyf = __fadd_rn(py, fi);
-                        const int sx = (int)cxf, sy = (int)cyf;
-                        if (cxf >= 0.0f && cyf >= 0.0f && sx < o.w && sy < o.h) {
-                            ok[u] = true;
-                            gm[u] = __ldg(g + (size_t)sy * o.pitch + sx);
-                            bxs[u] = bx;
-                            bys[u] = by;
-                            r2s[u] = rx * rx + ry * ry;
-                        }
-                    }
-                }
+                const int j = jlo + pos;
+                const float fj = (float)j, fi = (float)i;
+                const float rx = fj * a - fi * b;
+                const float ry = fj * b + fi * a;
+                // addValue drops cells outside [0, 4): nothing lands unless -1 < rx + 1.5 < 4, same in y
+                ok[u] = (i <= iMax) && fabsf(rx) < 2.5f && fabsf(ry) < 2.5f;
+                gm[u] = __ldg(grow + (ok[u] ? j : -ipx));
+                bxs[u] = rx + 1.5f;
+                bys[u] = ry + 1.5f;
+                r2s[u] = rx * rx + ry * ry;
+                pos += 32;
+                settle();
             }
+            // phase 2: trilinear accumulation (addFeature, SIFTDescriptor.metal:82-117). Two base
+            // addresses per sample (one per orientation bin); the four cells are immediate
+            // offsets; loads / stores of cells outside the 4x4 grid are predicated off.
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                if (!ok[u]) continue;
                 const float bx = bxs[u], by = bys[u];
                 // orientation relative to theta, wrapped to [0, 1) turns, then 8 bins
                 float turn = (gm[u].x - theta) * (1.0f / kTau);
@@ -350,34 +327,40 @@ descriptorKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __r
                 const float bin = turn * 8.0f;
                 const int bi = (int)bin;                   // bin >= 0: truncation = floor
                 const float fb = bin - (float)bi;
-                const int b0 = bi & 7, b1 = (bi + 1) & 7;
-                const float w = __expf(-r2s[u] * 0.125f);
-                const float val = gm[u].y * w;
-                const int x0 = __float2int_rd(bx), y0 = __float2int_rd(by);
+                const float val = gm[u].y * __expf(-r2s[u] * 0.125f);
+                const int x0 = __float2int_rd(bx), y0 = __float2int_rd(by);   // in [-1, 3] when ok
                 const float fxw = bx - (float)x0, fyw = by - (float)y0;
-                // trilinear spread (addFeature, :82-117). ceil = floor + 1 except on exact
-                // integers, where the reference adds a zero weight to the floor cell — same sums.
+                // ceil = floor + 1 except on exact integers, where the reference adds a zero
+                // weight to the floor cell — same sums either way.
                 const float vx0 = val * (1.0f - fxw), vx1 = val * fxw;
                 const float v00 = vx0 * (1.0f - fyw), v01 = vx0 * fyw;
                 const float v10 = vx1 * (1.0f - fyw), v11 = vx1 * fyw;
-                const bool okx0 = (x0 >= 0), okx1 = (x0 < 3), oky0 = (y0 >= 0), oky1 = (y0 < 3);
-                float* h00 = hist + ((y0 * 4 + x0) * 8) * 32 + lane;   // cell (x0, y0), bin 0
-                float* h10 = h00 + 8 * 32;                              // (x0+1, y0)
-                float* h01 = h00 + 4 * 8 * 32;                          // (x0, y0+1)
-                float* h11 = h01 + 8 * 32;                              // (x0+1, y0+1)
-                const int o0 = b0 * 32, o1 = b1 * 32;
+                const bool okx0 = ok[u] && (x0 >= 0), okx1 = ok[u] && (x0 < 3);
+                const bool oky0 = (y0 >= 0), oky1 = (y0 < 3);
+                const bool c00 = okx0 && oky0, c10 = okx1 && oky0, c01 = okx0 && oky1, c11 = okx1 && oky1;
+                const int cellB = (y0 * 4 + x0) * (8 * 32 * 4);                 // bytes: cell (x0, y0), bin 0
+                float* const p0 = reinterpret_cast<float*>(hl + cellB + (bi & 7) * 128);
+                float* const p1 = reinterpret_cast<float*>(hl + cellB + ((bi + 1) & 7) * 128);
+                constexpr int DX = 8 * 32, DY = 32 * 32;                        // floats to cell x+1 / y+1
                 const float g0 = 1.0f - fb;
                 // the eight addresses are distinct: load all, add, store all
-                float t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0, t6 = 0, t7 = 0;
-                const bool c00 = okx0 && oky0, c10 = okx1 && oky0, c01 = okx0 && oky1, c11 = okx1 && oky1;
-                if (c00) { t0 = h00[o0]; t1 = h00[o1]; }
-                if (c10) { t2 = h10[o0]; t3 = h10[o1]; }
-                if (c01) { t4 = h01[o0]; t5 = h01[o1]; }
-                if (c11) { t6 = h11[o0]; t7 = h11[o1]; }
-                if (c00) { h00[o0] = t0 + v00 * g0; h00[o1] = t1 + v00 * fb; }
-                if (c10) { h10[o0] = t2 + v10 * g0; h10[o1] = t3 + v10 * fb; }
-                if (c01) { h01[o0] = t4 + v01 * g0; h01[o1] = t5 + v01 * fb; }
-                if (c11) { h11[o0] = t6 + v11 * g0; h11[o1] = t7 + v11 * fb; }
+                float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f, t4 = 0.f, t5 = 0.f, t6 = 0.f, t7 = 0.f;
+                if (c00) t0 = p0[0];
+                if (c00) t1 = p1[0];
+                if (c10) t2 = p0[DX];
+                if (c10) t3 = p1[DX];
+                if (c01) t4 = p0[DY];
+                if (c01) t5 = p1[DY];
+                if (c11) t6 = p0[DY + DX];
+                if (c11) t7 = p1[DY + DX];
+                if (c00) p0[0] = fmaf(v00, g0, t0);
+                if (c00) p1[0] = fmaf(v00, fb, t1);
+                if (c10) p0[DX] = fmaf(v10, g0, t2);
+                if (c10) p1[DX] = fmaf(v10, fb, t3);
+                if (c01) p0[DY] = fmaf(v01, g0, t4);
+                if (c01) p1[DY] = fmaf(v01, fb, t5);
+                if (c11) p0[DY + DX] = fmaf(v11, g0, t6);
+                if (c11) p1[DY + DX] = fmaf(v11, fb, t7);
             }
         }
         __syncwarp();
@@ -426,7 +409,7 @@ descriptorKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __r
 
 cudaError_t launchDescribe(const EngineParams& P, const SiftKeypoint* kps, const int* kpSeg,
                            int capKeypoints, const int* segKpStart, int* nOri, float* oriTmp,
-                           int* oriOffset, int* blockSums, SiftDescriptor* desc,
+                           int* oriOffset, int* descKp, int* blockSums, SiftDescriptor* desc,
                            int capDescriptors, int* segDescStart, int nSegs, Counters* counters,
                            int smCount, cudaStream_t st, cudaEvent_t afterOrientation) {
     orientationKernel<<<smCount * 4, kOriWarps * 32, 0, st>>>(P, kps, kpSeg, counters, nOri, oriTmp);
@@ -437,7 +420,8 @@ cudaError_t launchDescribe(const EngineParams& P, const SiftKeypoint* kps, const
     SIFT_CUDA_TRY(cudaGetLastError());
     SIFT_CUDA_TRY(launchScanOffsets(blockSums, nBlocks, &counters->nDescriptors, capDescriptors,
                                     &counters->overflow, 4, st));
-    oriOffsetsKernel<<<nBlocks, kScanThreads, 0, st>>>(nOri, counters, blockSums, oriOffset);
+    oriOffsetsKernel<<<nBlocks, kScanThreads, 0, st>>>(nOri, counters, blockSums, oriOffset, descKp,
+                                                       capDescriptors);
     SIFT_CUDA_TRY(cudaGetLastError());
     descSegmentStartsKernel<<<(nSegs + 1 + 127) / 128, 128, 0, st>>>(segKpStart, oriOffset,
                                                                    segDescStart, nSegs);
@@ -445,7 +429,7 @@ cudaError_t launchDescribe(const EngineParams& P, const SiftKeypoint* kps, const
     if (afterOrientation) SIFT_CUDA_TRY(cudaEventRecord(afterOrientation, st));
 
     static unsigned long long configured = 0;
-    const int smemBytes = kDescWarps * 128 * 32 * (int)sizeof(float);
+    const int smemBytes = kDescWarps * kDescBins * 32 * (int)sizeof(float);
     int dev = 0;
     cudaGetDevice(&dev);
     if (!((configured >> (dev & 63)) & 1ull)) {
@@ -454,7 +438,7 @@ cudaError_t launchDescribe(const EngineParams& P, const SiftKeypoint* kps, const
         configured |= 1ull << (dev & 63);
     }
     descriptorKernel<<<smCount * 6, kDescWarps * 32, smemBytes, st>>>(
-        P, kps, kpSeg, segKpStart, counters, oriOffset, oriTmp, desc, capDescriptors);
+        P, kps, kpSeg, segKpStart, counters, oriOffset, oriTmp, descKp, desc, capDescriptors);
     return cudaGetLastError();
 }
 
