@@ -350,7 +350,11 @@ def main():
             "roofline": {
                 "bound": "hbm", "kernel": "blurKernel<NTAPS,64,64> octave 0 (5 launches/step: 11,15,17,21,27 taps)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src,
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture
+                # in profiles/r1/SUMMARY.md (mean of the 5 octave-0 launches, 1080p, cold cache; part
+                # of the 66 MB written per launch is still in the 126 MB L2 when the kernel ends)
+                "traffic": 48.6e6 * (n_local / len(chunks)) if (w, h) == (1920, 1080) else None,
+                "peak_source": peak_src,
                 "bytes_per_launch": bytes_per_launch, "avg_launch_ms": blur_avg_s * 1000,
                 "per_tap_launch_ms": [float(x) / (K * len(chunks)) for x in blur_ms],
             },

@@ -235,6 +235,12 @@ int64_t sift_debug_candidates(SiftContext* context, int32_t frame, int32_t octav
 int sift_debug_math(int device, int32_t op, const float* a, const float* b, float* out,
                     int64_t n);
 
+/* Tuning aid: times `iters` back-to-back launches of the octave-0 blur of scale `scale` (0..4 =
+ * 11,15,17,21,27 taps) on the planes left by the last execute, with CUDA events; `mode` 0 normal,
+ * 1 without the FMA loops, 2 without the stores, 3 neither. Mean ms per launch in *out_ms. */
+int sift_debug_blur_bench(SiftContext* context, int32_t scale, int32_t mode, int32_t iters,
+                          float* out_ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,6 +77,7 @@ def load_library():
     L.sift_debug_candidates.argtypes = [vp, i32, i32, vp, i64]
     L.sift_debug_candidates.restype = i64
     L.sift_debug_math.argtypes = [C.c_int, i32, vp, vp, vp, i64]
+    L.sift_debug_blur_bench.argtypes = [vp, i32, i32, i32, C.POINTER(C.c_float)]
     _lib = L
     return L
 
@@ -86,7 +87,7 @@ EXPORTED_SYMBOLS = (
     "sift_detect_and_describe_batch sift_batch_upload sift_batch_set_device_input "
     "sift_batch_execute sift_batch_download sift_status_string sift_last_error_string "
     "sift_set_stage_timing sift_last_timings sift_debug_download sift_debug_candidates "
-    "sift_debug_math"
+    "sift_debug_math sift_debug_blur_bench"
 ).split()
 
 
@@ -229,6 +230,11 @@ class Engine:
 
     def set_stage_timing(self, enabled):
         self._check(self.L.sift_set_stage_timing(self.ctx, int(enabled)))
+
+    def blur_bench(self, scale, mode=0, iters=20):
+        ms = C.c_float()
+        self._check(self.L.sift_debug_blur_bench(self.ctx, scale, mode, iters, C.byref(ms)))
+        return ms.value
 
     def plane(self, what, octave=0, slice=0, frame=0):
         if what == _abi.PLANE_GRAY:

@@ -749,6 +749,32 @@ int64_t sift_debug_candidates(SiftContext* c, int32_t frame, int32_t octave, int
     return n;
 }
 
+int sift_debug_blur_bench(SiftContext* c, int32_t scale, int32_t mode, int32_t iters, float* outMs) {
+    if (!c || !outMs || scale < 0 || scale >= kGaussians - 1 || iters < 1) return SIFT_ERR_INVALID_ARGUMENT;
+    if (!c->executed) return fail(c, SIFT_ERR_NOT_DETECTED, "blur bench before execute");
+    CTX_TRY(c, cudaSetDevice(c->device));
+    const OctaveDev& q = c->P.oct[0];
+    BlurArgs a{};
+    a.in = q.G + (size_t)scale * q.plane;
+    a.out = q.G + (size_t)(scale + 1) * q.plane;
+    a.dog = q.D + (size_t)scale * q.plane;
+    a.w = q.w; a.h = q.h; a.pitch = q.pitch;
+    a.inFrameStride = a.outFrameStride = kGaussians * q.plane;
+    a.dogFrameStride = kDogs * q.plane;
+    a.frames = c->curFrames;
+    a.debugMode = mode;
+    CTX_TRY(c, launchBlur(a, c->taps[scale], c->ntaps[scale], c->stream));
+    CTX_TRY(c, cudaEventRecord(c->evBlur0[0], c->stream));
+    for (int i = 0; i < iters; i++) CTX_TRY(c, launchBlur(a, c->taps[scale], c->ntaps[scale], c->stream));
+    CTX_TRY(c, cudaEventRecord(c->evBlur0[1], c->stream));
+    CTX_TRY(c, cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    CTX_TRY(c, cudaEventElapsedTime(&ms, c->evBlur0[0], c->evBlur0[1]));
+    *outMs = ms / iters;
+    c->executed = false;   // planes were overwritten in debug modes: force a fresh execute
+    return SIFT_OK;
+}
+
 int sift_debug_math(int device, int32_t op, const float* a, const float* b, float* out, int64_t n) {
     if (!a || !out || n < 0) return SIFT_ERR_INVALID_ARGUMENT;
     int count = 0;

@@ -92,6 +92,7 @@ struct BlurArgs {
     int halfW, halfH, halfPitch;
     size_t halfFrameStride;
     int frames;
+    int debugMode;   // 0 normal; 1 skip the X/Y FMA loops; 2 skip the stores; 3 both (tuning only)
 };
 cudaError_t launchBlur(const BlurArgs& a, const Taps& taps, int ntaps, cudaStream_t st);
 cudaError_t launchGradient(const OctaveDev& o, int frames, cudaStream_t st);
