@@ -333,6 +333,15 @@ int sift_create(const SiftConfig* cfg, int device, SiftContext** out) {
     A(devAlloc(c, &c->dDescKp, (size_t)c->capDesc));
     A(devAlloc(c, &c->dCounters, 1));
     if (e == cudaSuccess) A(cudaMemset(c->dMask, 0, maskWords * sizeof(uint32_t)));
+    // row padding (columns w..pitch) is read by the extrema kernel's full-warp loads and masked
+    // afterwards: give it defined contents once
+    for (int o = 0; o < kOctaves && e == cudaSuccess; o++) {
+        OctaveDev& q = c->P.oct[o];
+        A(cudaMemset(q.G, 0, B * kGaussians * q.plane * sizeof(float)));
+        A(cudaMemset(q.D, 0, B * kDogs * q.plane * sizeof(float)));
+        A(cudaMemset(q.grad, 0, B * kScales * q.plane * sizeof(float2)));
+    }
+    if (e == cudaSuccess) A(cudaMemset(c->dScaled, 0, B * c->P.oct[0].plane * sizeof(float)));
     if (e == cudaSuccess) A(cudaMemset(c->dSegStarts, 0, 3 * (size_t)(c->nSegs + 1) * sizeof(int)));
     A(cudaMallocHost(&c->hCounters, sizeof(Counters)));
     A(cudaMallocHost(&c->hSegStarts, 3 * (size_t)(c->nSegs + 1) * sizeof(int)));
