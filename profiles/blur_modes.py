@@ -6,8 +6,8 @@ from siftmetal_b200.synth import pink_noise_bgra
 w, h = 1920, 1080
 eng = Engine(w, h)
 img = pink_noise_bgra(w, h, 0)
-names = {0: "normal", 1: "no FMA loops", 2: "no stores", 3: "no FMA, no stores"}
-for mode in (0, 1, 2, 3):
+names = {0: "normal", 1: "no FMA loops", 2: "no stores", 3: "no FMA, no stores", 4: "tile load only"}
+for mode in (0, 1, 2, 3, 4):
     row = []
     for scale in range(5):
         eng.detect_and_describe([img])

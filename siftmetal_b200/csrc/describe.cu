@@ -98,9 +98,15 @@ orientationKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 if (ok[u]) {
-                    // bin index: discontinuous → the spec's exact sequence
-                    const float t = __fdiv_rn(gm[u].x, kTau);
-                    int bin = (int)roundf(__fmul_rn(t, (float)kOriBins));
+                    // bin index = round((ori / tau) * 36), a discontinuous quantity that must equal
+                    // the spec's. One multiply gives it to within 5e-6; only when that estimate
+                    // sits within 1e-4 of a rounding boundary (k + 0.5) is the exact sequence
+                    // (IEEE divide, multiply, round-half-away) evaluated — same result always.
+                    const float est = gm[u].x * ((float)kOriBins / kTau);
+                    float rb = rintf(est);
+                    if (fabsf(fabsf(est - rb) - 0.5f) < 1e-4f)
+                        rb = roundf(__fmul_rn(__fdiv_rn(gm[u].x, kTau), (float)kOriBins));
+                    int bin = (int)rb;
                     if (bin < 0) bin += kOriBins;
                     if (bin >= kOriBins) bin -= kOriBins;
                     hist[bin * 32 + lane] += wgt[u] * gm[u].y;

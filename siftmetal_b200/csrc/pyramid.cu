@@ -128,13 +128,15 @@ cudaError_t launchGrayUpsample(const uint8_t* bgra, int pitchBytes, int64_t fram
 //
 // One CTA per TX x TY output tile (tiles of all frames in one linear grid). The input tile with
 // halo (rows TY + 2R, columns TX + 2RP, RP = R rounded up to 4 so that rows stay 16-byte aligned
-// with global memory) arrives by cp.async; a second buffer holds the X-pass result (rows
-// TY + 2R, columns TX). (BlurCfg::NBUF = 2 turns the kernel into persistent CTAs with the next
-// tile's copies in flight during the current tile's FMAs; measured slower on B200 because the
-// doubled shared memory leaves 2 instead of 3 CTAs per SM.) All row pitches are 4 * odd floats: 8 lanes on 8 consecutive rows issuing
-// LDS.128 / STS.128 hit 8 distinct 4-bank groups, so the row-per-lane X pass is conflict-free;
-// the Y pass reads float4 columns with consecutive lanes on consecutive groups, also
-// conflict-free.
+// with global memory) arrives by cp.async in NG row groups, each its own commit group, and the
+// X pass of group g starts as soon as that group has landed — the remaining groups' HBM/L2
+// latency hides behind it (a CTA is otherwise bound by the latency of its own tile load). A
+// second buffer holds the X-pass result (rows TY + 2R, columns TX). Row pitches are 4 * odd
+// floats: 8 lanes on 8 consecutive rows issuing LDS.128 / STS.128 hit 8 distinct 4-bank groups,
+// so the row-per-lane X pass is conflict-free; the Y pass reads float2 columns with consecutive
+// lanes on consecutive pairs, also conflict-free.
+// (Measured alternatives — persistent CTAs with a double-buffered input, march-down strips,
+// 128x64 tiles — were all slower on B200; see profiles/r1/SUMMARY.md.)
 template <int NTAPS, int TX, int TY, int NT>
 struct BlurCfg {
     static constexpr int RY = TX * TY / (2 * NT);   // Y pass: 2 columns x RY rows per thread
@@ -144,48 +146,58 @@ struct BlurCfg {
     static constexpr int IN_H = TY + 2 * R;
     static constexpr int IP = (IN_W % 8 == 4) ? IN_W : IN_W + 4;  // IN_W is a multiple of 4
     static constexpr int TP = (TX % 8 == 4) ? TX : TX + 4;
-    static constexpr int NBUF = 1;   // input buffers (2 = persistent CTAs with prefetch; measured slower: fewer resident warps)
-    static constexpr int SMEM_FLOATS = NBUF * IN_H * IP + IN_H * TP;
-    static constexpr int XSEG = 8;   // outputs per thread in the X pass
+    static constexpr int SMEM_FLOATS = IN_H * IP + IN_H * TP;
+    static constexpr int XSEG = 8;                   // outputs per thread in the X pass
+    static constexpr int NG = 3;                     // row groups of the pipelined tile load
+    static constexpr int GH = (IN_H + NG - 1) / NG;  // rows per group
 };
+
+template <int N>
+__device__ __forceinline__ void cpAsyncWaitGroup() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
 
 template <int NTAPS, int TX, int TY, int NT, bool DOG, bool HALF>
 __global__ void __launch_bounds__(NT)
 blurKernel(const BlurArgs a, const __grid_constant__ Taps taps) {
     using C = BlurCfg<NTAPS, TX, TY, NT>;
     constexpr int R = C::R, RP = C::RP, IN_W = C::IN_W, IN_H = C::IN_H, IP = C::IP, TP = C::TP;
+    constexpr int NG = C::NG, GH = C::GH;
     extern __shared__ __align__(16) float smem[];
-    float* sTmp = smem + C::NBUF * IN_H * IP;
+    float* const sIn = smem;
+    float* const sTmp = smem + IN_H * IP;
 
     const int tid = threadIdx.x;
     const int w = a.w, h = a.h, pitch = a.pitch;
     const int tilesX = (w + TX - 1) / TX, tilesY = (h + TY - 1) / TY;
     const int tilesPerFrame = tilesX * tilesY;
-    const int nTiles = tilesPerFrame * a.frames;
+    const int tile = blockIdx.x;
+    const int f = tile / tilesPerFrame;
+    const int tr = tile - f * tilesPerFrame;
+    const int ty = tr / tilesX, tx = tr - ty * tilesX;
+    const int x0 = tx * TX, y0 = ty * TY;
+    const float* __restrict__ in = a.in + (size_t)f * a.inFrameStride;
 
-    // ---- asynchronous load of one input tile with halo -----------------------------------
-    auto issueLoad = [&](int tile, float* sIn) {
-        const int f = tile / tilesPerFrame;
-        const int tr = tile - f * tilesPerFrame;
-        const int ty = tr / tilesX, tx = tr - ty * tilesX;
-        const int x0 = tx * TX, y0 = ty * TY;
-        const float* __restrict__ in = a.in + (size_t)f * a.inFrameStride;
-        const bool interior = (x0 - RP >= 0) && (x0 + TX + RP <= w) && (y0 - R >= 0) &&
-                              (y0 + TY + R <= h);
+    // ---- asynchronous load of the input tile with halo, NG row groups ----------------------
+    const bool interior = (x0 - RP >= 0) && (x0 + TX + RP <= w) && (y0 - R >= 0) &&
+                          (y0 + TY + R <= h);
+#pragma unroll
+    for (int g = 0; g < NG; g++) {
+        const int rBeg = g * GH, rEnd = min(rBeg + GH, IN_H);
         if (interior) {
             constexpr int V = IN_W / 4;
-            const float* base = in + (size_t)(y0 - R) * pitch + (x0 - RP);
-            for (int idx = tid; idx < IN_H * V; idx += NT) {
+            const float* base = in + (size_t)(y0 - R + rBeg) * pitch + (x0 - RP);
+            for (int idx = tid; idx < (rEnd - rBeg) * V; idx += NT) {
                 const int r = idx / V, c4 = idx - r * V;
-                const float* g = base + (size_t)r * pitch + 4 * c4;
-                const unsigned s = (unsigned)__cvta_generic_to_shared(sIn + r * IP + 4 * c4);
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(g));
+                const float* gp = base + (size_t)r * pitch + 4 * c4;
+                const unsigned s = (unsigned)__cvta_generic_to_shared(sIn + (rBeg + r) * IP + 4 * c4);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gp));
             }
         } else {
             // edge tile: mirror boundary. One warp per row (row index reflected once per warp),
             // lanes across columns with a single-reflection fast path.
             const int lane = tid & 31, wid = tid >> 5;
-            for (int r = wid; r < IN_H; r += NT / 32) {
+            for (int r = rBeg + wid; r < rEnd; r += NT / 32) {
                 const int gy = symmetrized(y0 - R + r, h);
                 const float* __restrict__ srow = in + (size_t)gy * pitch;
                 for (int c = lane; c < IN_W; c += 32) {
@@ -198,127 +210,114 @@ blurKernel(const BlurArgs a, const __grid_constant__ Taps taps) {
                 }
             }
         }
-    };
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    }
 
-    int tile = blockIdx.x;
-    if (tile >= nTiles) return;
-    issueLoad(tile, smem);
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
-    for (int buf = 0; tile < nTiles; tile += gridDim.x, buf ^= 1) {
-        float* sIn = smem + (C::NBUF == 2 ? buf : 0) * (IN_H * IP);
-        if (C::NBUF == 2) {
-            if (tile + (int)gridDim.x < nTiles) issueLoad(tile + gridDim.x, smem + (buf ^ 1) * (IN_H * IP));
-            asm volatile("cp.async.commit_group;\ncp.async.wait_group 1;\n" ::: "memory");
-        } else {
-            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-        }
+    if (a.debugMode & 4) {   // tuning: tile load only
+        cpAsyncWaitGroup<0>();
         __syncthreads();
-
-        const int f = tile / tilesPerFrame;
-        const int tr = tile - f * tilesPerFrame;
-        const int ty = tr / tilesX, tx = tr - ty * tilesX;
-        const int x0 = tx * TX, y0 = ty * TY;
-
-        // ---- X pass: one row, 8 consecutive outputs per thread -----------------------------
-        {
-            constexpr int SEGS = TX / C::XSEG;
-            constexpr int NV = (C::XSEG + 2 * RP) / 4;
-            for (int t = tid; t < IN_H * SEGS; t += NT) {
-                const int seg = t / IN_H, r = t - seg * IN_H;
-                const float4* src = reinterpret_cast<const float4*>(sIn + r * IP + seg * C::XSEG);
-                float v[NV * 4];
+        if (sIn[tid] == 1.2345e30f) a.out[0] = 1.0f;
+        return;
+    }
+    // ---- X pass, group by group: one row, 8 consecutive outputs per task --------------------
 #pragma unroll
-                for (int k = 0; k < NV; k++) {
-                    const float4 q = src[k];
-                    v[4 * k + 0] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
-                }
-                float acc[C::XSEG];
+    for (int g = 0; g < NG; g++) {
+        if (g == 0) cpAsyncWaitGroup<NG - 1>();
+        else if (g == 1) cpAsyncWaitGroup<NG - 2>();
+        else cpAsyncWaitGroup<0>();
+        __syncthreads();
+        const int rBeg = g * GH, rows = min(rBeg + GH, IN_H) - rBeg;
+        constexpr int SEGS = TX / C::XSEG;
+        constexpr int NV = (C::XSEG + 2 * RP) / 4;
+        for (int t = tid; t < rows * SEGS; t += NT) {
+            const int seg = t / rows, r = rBeg + (t - seg * rows);
+            const float4* src = reinterpret_cast<const float4*>(sIn + r * IP + seg * C::XSEG);
+            float v[NV * 4];
 #pragma unroll
-                for (int k = 0; k < C::XSEG; k++) acc[k] = 0.0f;
-                if (!(a.debugMode & 1)) {
-#pragma unroll
-                    for (int i = 0; i < NTAPS; i++) {
-                        const float wi = taps.w[i];
-#pragma unroll
-                        for (int k = 0; k < C::XSEG; k++) acc[k] = fmaf(wi, v[k + (RP - R) + i], acc[k]);
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < C::XSEG; k++) acc[k] = v[k + RP];
-                }
-                float4* dst = reinterpret_cast<float4*>(sTmp + r * TP + seg * C::XSEG);
-                dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-                dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            for (int k = 0; k < NV; k++) {
+                const float4 q = src[k];
+                v[4 * k + 0] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
             }
-        }
-        __syncthreads();
-
-        // ---- Y pass: 2 adjacent columns x RY rows per thread, streaming over X-pass rows -------
-        // Row k of the X-pass result feeds output row q with tap i = k - q, so walking k upwards
-        // accumulates every output in ascending tap order (the spec's order) while only the RY
-        // accumulator pairs and one float2 of input are live: (RY + 2R) LDS.64 per 2 RY outputs
-        // keeps the pass off the shared-memory bandwidth limit (4-column quads with RY = 4 were
-        // measured smem-bound). Packed fp32x2 FMAs (FFMA2) on the column pair.
-        {
-            constexpr int RY = C::RY;
-            constexpr int CGS = TX / 2;
-            static_assert(CGS * (TY / RY) == NT, "one Y-pass task per thread");
-            float* __restrict__ out = a.out + (size_t)f * a.outFrameStride;
-            float* __restrict__ dog = DOG ? a.dog + (size_t)f * a.dogFrameStride : nullptr;
-            float* __restrict__ half = HALF ? a.half + (size_t)f * a.halfFrameStride : nullptr;
-            const int yb = tid / CGS, cg = tid - yb * CGS;
-            const int gx = x0 + 2 * cg;
-            f32x2 acc2[RY];
+            float acc[C::XSEG];
 #pragma unroll
-            for (int q = 0; q < RY; q++) acc2[q] = pack2(0.0f, 0.0f);
+            for (int k = 0; k < C::XSEG; k++) acc[k] = 0.0f;
             if (!(a.debugMode & 1)) {
 #pragma unroll
-                for (int k = 0; k < RY + 2 * R; k++) {
-                    const float2 v = *reinterpret_cast<const float2*>(sTmp + (yb * RY + k) * TP + 2 * cg);
-                    const f32x2 v2 = pack2(v.x, v.y);
+                for (int i = 0; i < NTAPS; i++) {
+                    const float wi = taps.w[i];
 #pragma unroll
-                    for (int q = 0; q < RY; q++) {
-                        const int i = k - q;
-                        if (i >= 0 && i < NTAPS) acc2[q] = fma2(pack2(taps.w[i], taps.w[i]), v2, acc2[q]);
-                    }
+                    for (int k = 0; k < C::XSEG; k++) acc[k] = fmaf(wi, v[k + (RP - R) + i], acc[k]);
                 }
             } else {
 #pragma unroll
+                for (int k = 0; k < C::XSEG; k++) acc[k] = v[k + RP];
+            }
+            float4* dst = reinterpret_cast<float4*>(sTmp + r * TP + seg * C::XSEG);
+            dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        }
+    }
+    __syncthreads();
+
+    // ---- Y pass: 2 adjacent columns x RY rows per thread, streaming over X-pass rows -------
+    // Row k of the X-pass result feeds output row q with tap i = k - q, so walking k upwards
+    // accumulates every output in ascending tap order (the spec's order) while only the RY
+    // accumulator pairs and one float2 of input are live: (RY + 2R) LDS.64 per 2 RY outputs.
+    // Packed fp32x2 FMAs (FFMA2) on the column pair.
+    {
+        constexpr int RY = C::RY;
+        constexpr int CGS = TX / 2;
+        static_assert(CGS * (TY / RY) == NT, "one Y-pass task per thread");
+        float* __restrict__ out = a.out + (size_t)f * a.outFrameStride;
+        float* __restrict__ dog = DOG ? a.dog + (size_t)f * a.dogFrameStride : nullptr;
+        float* __restrict__ half = HALF ? a.half + (size_t)f * a.halfFrameStride : nullptr;
+        const int yb = tid / CGS, cg = tid - yb * CGS;
+        const int gx = x0 + 2 * cg;
+        f32x2 acc2[RY];
+#pragma unroll
+        for (int q = 0; q < RY; q++) acc2[q] = pack2(0.0f, 0.0f);
+        if (!(a.debugMode & 1)) {
+#pragma unroll
+            for (int k = 0; k < RY + 2 * R; k++) {
+                const float2 v = *reinterpret_cast<const float2*>(sTmp + (yb * RY + k) * TP + 2 * cg);
+                const f32x2 v2 = pack2(v.x, v.y);
+#pragma unroll
                 for (int q = 0; q < RY; q++) {
-                    const float2 v = *reinterpret_cast<const float2*>(sTmp + (yb * RY + q + R) * TP + 2 * cg);
-                    acc2[q] = pack2(v.x, v.y);
+                    const int i = k - q;
+                    if (i >= 0 && i < NTAPS) acc2[q] = fma2(pack2(taps.w[i], taps.w[i]), v2, acc2[q]);
                 }
             }
-            const bool full = (x0 + TX <= w) && (y0 + TY <= h);   // CTA-uniform
-            const bool noStore = (a.debugMode & 2) != 0;
+        } else {
 #pragma unroll
             for (int q = 0; q < RY; q++) {
-                float2 r;
-                unpack2(acc2[q], r.x, r.y);
-                const int gy = y0 + yb * RY + q;
-                const size_t o = (size_t)gy * pitch + gx;
-                float2 d2 = make_float2(0.f, 0.f);
-                if (DOG) {
-                    const float2 c = *reinterpret_cast<const float2*>(sIn + (yb * RY + q + R) * IP + RP + 2 * cg);
-                    d2 = make_float2(r.x - c.x, r.y - c.y);
-                }
-                if (noStore) {
-                    if (r.x == 1.2345e30f) out[o] = d2.x;   // keeps the computation alive
-                } else if (full) {
-                    *reinterpret_cast<float2*>(out + o) = r;
-                    if (DOG) *reinterpret_cast<float2*>(dog + o) = d2;
-                } else if (gy < h) {
-                    if (gx < w) { out[o] = r.x; if (DOG) dog[o] = d2.x; }
-                    if (gx + 1 < w) { out[o + 1] = r.y; if (DOG) dog[o + 1] = d2.y; }
-                }
-                if (HALF && (gy & 1) == 0 && (gy >> 1) < a.halfH && gy < h && (gx >> 1) < a.halfW && gx < w)
-                    half[(size_t)(gy >> 1) * a.halfPitch + (gx >> 1)] = r.x;   // gx is even
+                const float2 v = *reinterpret_cast<const float2*>(sTmp + (yb * RY + q + R) * TP + 2 * cg);
+                acc2[q] = pack2(v.x, v.y);
             }
         }
-        __syncthreads();   // sTmp and this input buffer are reused by the next iterations
-        if (C::NBUF == 1 && tile + (int)gridDim.x < nTiles) {
-            issueLoad(tile + gridDim.x, smem);
-            asm volatile("cp.async.commit_group;\n" ::: "memory");
+        const bool full = (x0 + TX <= w) && (y0 + TY <= h);   // CTA-uniform
+        const bool noStore = (a.debugMode & 2) != 0;
+#pragma unroll
+        for (int q = 0; q < RY; q++) {
+            float2 r;
+            unpack2(acc2[q], r.x, r.y);
+            const int gy = y0 + yb * RY + q;
+            const size_t o = (size_t)gy * pitch + gx;
+            float2 d2 = make_float2(0.f, 0.f);
+            if (DOG) {
+                const float2 c = *reinterpret_cast<const float2*>(sIn + (yb * RY + q + R) * IP + RP + 2 * cg);
+                d2 = make_float2(r.x - c.x, r.y - c.y);
+            }
+            if (noStore) {
+                if (r.x == 1.2345e30f) out[o] = d2.x;   // keeps the computation alive
+            } else if (full) {
+                *reinterpret_cast<float2*>(out + o) = r;
+                if (DOG) *reinterpret_cast<float2*>(dog + o) = d2;
+            } else if (gy < h) {
+                if (gx < w) { out[o] = r.x; if (DOG) dog[o] = d2.x; }
+                if (gx + 1 < w) { out[o + 1] = r.y; if (DOG) dog[o + 1] = d2.y; }
+            }
+            if (HALF && (gy & 1) == 0 && (gy >> 1) < a.halfH && gy < h && (gx >> 1) < a.halfW && gx < w)
+                half[(size_t)(gy >> 1) * a.halfPitch + (gx >> 1)] = r.x;   // gx is even
         }
     }
 }
@@ -327,28 +326,19 @@ template <int NTAPS, int TX, int TY, int NT, bool DOG, bool HALF>
 static cudaError_t launchBlurCfg(const BlurArgs& a, const Taps& taps, cudaStream_t st) {
     using C = BlurCfg<NTAPS, TX, TY, NT>;
     static_assert(C::IN_W % 4 == 0 && C::IP % 8 == 4 && C::TP % 8 == 4, "bank layout");
-    static_assert(TX % C::XSEG == 0 && C::RY >= 1 && TY % C::RY == 0, "tile shape");
+    static_assert(TX % C::XSEG == 0 && C::RY >= 1 && TY % C::RY == 0 && C::NG == 3, "tile shape");
     const int smemBytes = C::SMEM_FLOATS * (int)sizeof(float);
-    static int ctasPerSm[64] = {};   // per device: resident CTAs per SM for this instantiation
-    static int smCount[64] = {};
+    static unsigned long long configured = 0;  // per-device bit: the attribute is per device
     int dev = 0;
     cudaGetDevice(&dev);
-    dev &= 63;
-    if (ctasPerSm[dev] == 0) {
-        auto kernel = blurKernel<NTAPS, TX, TY, NT, DOG, HALF>;
-        SIFT_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes));
-        int n = 0, sms = 0;
-        SIFT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, NT, smemBytes));
-        SIFT_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        if (n < 1) return cudaErrorLaunchOutOfResources;
-        smCount[dev] = sms;
-        ctasPerSm[dev] = n;
+    if (!((configured >> (dev & 63)) & 1ull)) {
+        SIFT_CUDA_TRY(cudaFuncSetAttribute(blurKernel<NTAPS, TX, TY, NT, DOG, HALF>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes));
+        configured |= 1ull << (dev & 63);
     }
     const long nTiles = (long)((a.w + TX - 1) / TX) * ((a.h + TY - 1) / TY) * a.frames;
-    // one tile per CTA unless the grid would exceed what a launch may carry; with NBUF == 2 the
-    // grid is the resident set and CTAs loop with the next tile's copies in flight
-    const int grid = (int)std::min<long>(nTiles, C::NBUF == 2 ? (long)smCount[dev] * ctasPerSm[dev] : 2147483647L);
-    blurKernel<NTAPS, TX, TY, NT, DOG, HALF><<<grid, NT, smemBytes, st>>>(a, taps);
+    if (nTiles > 2147483647L) return cudaErrorInvalidValue;
+    blurKernel<NTAPS, TX, TY, NT, DOG, HALF><<<(unsigned)nTiles, NT, smemBytes, st>>>(a, taps);
     return cudaGetLastError();
 }
 
