@@ -772,9 +772,21 @@ int sift_debug_blur_bench(SiftContext* c, int32_t scale, int32_t mode, int32_t i
     a.dogFrameStride = kDogs * q.plane;
     a.frames = c->curFrames;
     a.debugMode = mode;
+    const bool dual = (mode & 8) != 0;   // tuning: the same launches split over two streams
+    a.debugMode = mode & 7;
+    cudaStream_t s2 = c->octStream[1];
     CTX_TRY(c, launchBlur(a, c->taps[scale], c->ntaps[scale], c->stream));
+    CTX_TRY(c, cudaStreamSynchronize(c->stream));
     CTX_TRY(c, cudaEventRecord(c->evBlur0[0], c->stream));
-    for (int i = 0; i < iters; i++) CTX_TRY(c, launchBlur(a, c->taps[scale], c->ntaps[scale], c->stream));
+    if (dual) {
+        CTX_TRY(c, cudaStreamWaitEvent(s2, c->evBlur0[0], 0));
+        for (int i = 0; i < iters; i++)
+            CTX_TRY(c, launchBlur(a, c->taps[scale], c->ntaps[scale], (i & 1) ? s2 : c->stream));
+        CTX_TRY(c, cudaEventRecord(c->evSeeded[0], s2));
+        CTX_TRY(c, cudaStreamWaitEvent(c->stream, c->evSeeded[0], 0));
+    } else {
+        for (int i = 0; i < iters; i++) CTX_TRY(c, launchBlur(a, c->taps[scale], c->ntaps[scale], c->stream));
+    }
     CTX_TRY(c, cudaEventRecord(c->evBlur0[1], c->stream));
     CTX_TRY(c, cudaStreamSynchronize(c->stream));
     float ms = 0;
