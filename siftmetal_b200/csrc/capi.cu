@@ -7,6 +7,7 @@
 // path: without a usable sm_100 device every compute entry point fails.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -27,6 +28,15 @@ struct SiftContext {
     // octave o-1 has produced Gaussian slice 3 (fork / join around the main stream)
     cudaStream_t octStream[kOctaves]{};
 
+    // Large octaves are split into two row bands that run as independent chains of blur launches
+    // (each band recomputes the few halo rows the later scales need, so there is no dependency
+    // between the bands): the fixed cost of a launch — latency, first wave's exposed tile load,
+    // partial last wave — of one chain hides under the other chain's work.
+    static constexpr int kMaxBands = 4;
+    int nBands = 2;                                   // SIFTCUDA_BANDS overrides (tuning)
+    cudaStream_t bandStream[kMaxBands]{};             // [0] unused: band 0 runs on the octave stream
+    cudaEvent_t evBandFork = nullptr;
+    cudaEvent_t evBandSeeded[kMaxBands]{}, evBandDone[kMaxBands]{};
     cudaEvent_t evSeeded[kOctaves]{};   // octave o's slice 3 (and octave o+1's slice 0) written
     cudaEvent_t evOctDone[kOctaves]{};
     SiftInfo info{};
@@ -84,6 +94,7 @@ struct SiftContext {
     cudaEvent_t evBlur0[kGaussians]{};
     SiftTimings timings{};
     int launches = 0;
+    bool bandedOctave0 = false;
 
     std::string lastError;
 };
@@ -157,6 +168,12 @@ void destroy(SiftContext* c) {
         if (o > 0 && c->octStream[o]) cudaStreamDestroy(c->octStream[o]);
 
     }
+    for (int b = 1; b < SiftContext::kMaxBands; b++) {
+        if (c->bandStream[b]) cudaStreamDestroy(c->bandStream[b]);
+        if (c->evBandSeeded[b]) cudaEventDestroy(c->evBandSeeded[b]);
+        if (c->evBandDone[b]) cudaEventDestroy(c->evBandDone[b]);
+    }
+    if (c->evBandFork) cudaEventDestroy(c->evBandFork);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -351,6 +368,13 @@ int sift_create(const SiftConfig* cfg, int device, SiftContext** out) {
     for (auto& evn : c->ev) A(cudaEventCreate(&evn));
     for (auto& evn : c->evBlur0) A(cudaEventCreate(&evn));
     c->octStream[0] = c->stream;
+    A(cudaEventCreateWithFlags(&c->evBandFork, cudaEventDisableTiming));
+    for (int b = 1; b < SiftContext::kMaxBands; b++) {
+        A(cudaStreamCreateWithFlags(&c->bandStream[b], cudaStreamNonBlocking));
+        A(cudaEventCreateWithFlags(&c->evBandSeeded[b], cudaEventDisableTiming));
+        A(cudaEventCreateWithFlags(&c->evBandDone[b], cudaEventDisableTiming));
+    }
+    if (const char* nb = getenv("SIFTCUDA_BANDS")) c->nBands = std::max(1, std::min(SiftContext::kMaxBands, atoi(nb)));
     for (int o = 0; o < kOctaves; o++) {
         if (o > 0) A(cudaStreamCreateWithFlags(&c->octStream[o], cudaStreamNonBlocking));
         A(cudaEventCreateWithFlags(&c->evSeeded[o], cudaEventDisableTiming));
@@ -466,28 +490,60 @@ int runDetect(SiftContext* c) {
         cudaStream_t so = c->octStream[o];
         if (o > 0) {
             CTX_TRY(c, cudaStreamWaitEvent(so, c->evSeeded[o - 1], 0));
+            if (o == 1 && c->bandedOctave0)
+                for (int b = 1; b < c->nBands; b++) CTX_TRY(c, cudaStreamWaitEvent(so, c->evBandSeeded[b], 0));
             forked[o] = true;
         }
-        for (int s = 0; s < kGaussians - 1; s++) {
-            if (T && o == 0) CTX_TRY(c, cudaEventRecord(c->evBlur0[s], so));
-            BlurArgs a{};
-            a.in = q.G + (size_t)s * q.plane;
-            a.out = q.G + (size_t)(s + 1) * q.plane;
-            a.dog = q.D + (size_t)s * q.plane;
-            a.w = q.w; a.h = q.h; a.pitch = q.pitch;
-            a.inFrameStride = a.outFrameStride = kGaussians * q.plane;
-            a.dogFrameStride = kDogs * q.plane;
-            if (s + 1 == kScales && o + 1 < kOctaves && c->P.oct[o + 1].w >= 1 && c->P.oct[o + 1].h >= 1) {
-                const OctaveDev& nx = c->P.oct[o + 1];
-                a.half = nx.G;
-                a.halfW = nx.w; a.halfH = nx.h; a.halfPitch = nx.pitch;
-                a.halfFrameStride = kGaussians * nx.plane;
-            }
-            a.frames = F;
-            CTX_TRY(c, launchBlur(a, c->taps[s], c->ntaps[s], so));
-            c->launches++;
-            if (s + 1 == kScales) CTX_TRY(c, cudaEventRecord(c->evSeeded[o], so));
+        // two row bands for a plane with many tiles (octave 0 of a large single frame); batches
+        // already have enough independent work per launch
+        const long tiles = (long)((q.w + 63) / 64) * ((q.h + 63) / 64) * F;
+        const int nb = c->nBands;
+        const bool banded = (o == 0) && (F == 1) && nb > 1 && tiles >= 8L * c->smCount && q.h >= 256 * nb;
+        if (T && o == 0) CTX_TRY(c, cudaEventRecord(c->evBlur0[0], so));
+        if (banded) {
+            CTX_TRY(c, cudaEventRecord(c->evBandFork, so));
+            for (int b = 1; b < nb; b++) CTX_TRY(c, cudaStreamWaitEvent(c->bandStream[b], c->evBandFork, 0));
         }
+        for (int band = 0; band < (banded ? nb : 1); band++) {
+            cudaStream_t sb = band == 0 ? so : c->bandStream[band];
+            // band rows [r0, r1), boundaries on multiples of the tile height
+            const int r0 = banded ? (int)(((long)q.h * band / nb + 63) / 64 * 64) : 0;
+            const int r1 = banded ? (band + 1 == nb ? q.h : (int)(((long)q.h * (band + 1) / nb + 63) / 64 * 64)) : q.h;
+            for (int s = 0; s < kGaussians - 1; s++) {
+                if (T && o == 0 && !banded && s > 0) CTX_TRY(c, cudaEventRecord(c->evBlur0[s], sb));
+                BlurArgs a{};
+                a.in = q.G + (size_t)s * q.plane;
+                a.out = q.G + (size_t)(s + 1) * q.plane;
+                a.dog = q.D + (size_t)s * q.plane;
+                a.w = q.w; a.h = q.h; a.pitch = q.pitch;
+                a.inFrameStride = a.outFrameStride = kGaussians * q.plane;
+                a.dogFrameStride = kDogs * q.plane;
+                if (banded) {
+                    // rows the later scales of this band still need: sum of their radii
+                    int halo = 0;
+                    for (int t = s + 1; t < kGaussians - 1; t++) halo += c->ntaps[t] / 2;
+                    a.yBegin = std::max(0, r0 - halo);
+                    a.yEnd = std::min(q.h, r1 + halo);
+                }
+                if (s + 1 == kScales && o + 1 < kOctaves && c->P.oct[o + 1].w >= 1 && c->P.oct[o + 1].h >= 1) {
+                    const OctaveDev& nx = c->P.oct[o + 1];
+                    a.half = nx.G;
+                    a.halfW = nx.w; a.halfH = nx.h; a.halfPitch = nx.pitch;
+                    a.halfFrameStride = kGaussians * nx.plane;
+                }
+                a.frames = F;
+                CTX_TRY(c, launchBlur(a, c->taps[s], c->ntaps[s], sb));
+                c->launches++;
+                if (s + 1 == kScales) CTX_TRY(c, cudaEventRecord(band == 0 ? c->evSeeded[o] : c->evBandSeeded[band], sb));
+            }
+        }
+        if (banded) {   // join: gradient and extrema need every row
+            for (int b = 1; b < nb; b++) {
+                CTX_TRY(c, cudaEventRecord(c->evBandDone[b], c->bandStream[b]));
+                CTX_TRY(c, cudaStreamWaitEvent(so, c->evBandDone[b], 0));
+            }
+        }
+        if (o == 0) c->bandedOctave0 = banded;
         if (T && o == 0) CTX_TRY(c, cudaEventRecord(c->evBlur0[kGaussians - 1], so));
         // (running the gradient beside blur s = 3, 4 on a side stream was measured: no gain, the
         // stage is throughput-bound, and it blurs the per-launch timing of the blur kernel)
@@ -561,9 +617,13 @@ int finish(SiftContext* c, bool withDescribe) {
         for (int i = 0; i < last; i++) cudaEventElapsedTime(&t.stage_ms[i], c->ev[i], c->ev[i + 1]);
         cudaEventElapsedTime(&t.total_ms, c->ev[0], c->ev[last]);
         cudaEventElapsedTime(&t.blur_octave0_ms, c->evBlur0[0], c->evBlur0[kGaussians - 1]);
-        for (int s = 0; s < kGaussians - 1; s++)
-            cudaEventElapsedTime(&t.blur_octave0_launch_ms[s], c->evBlur0[s], c->evBlur0[s + 1]);
+        for (int s = 0; s < kGaussians - 1; s++)   // per-scale split only without row bands
+            t.blur_octave0_launch_ms[s] = c->bandedOctave0 ? t.blur_octave0_ms / (kGaussians - 1) : 0.0f;
+        if (!c->bandedOctave0)
+            for (int s = 0; s < kGaussians - 1; s++)
+                cudaEventElapsedTime(&t.blur_octave0_launch_ms[s], c->evBlur0[s], c->evBlur0[s + 1]);
         t.blur_octave0_launches = kGaussians - 1;
+        cudaGetLastError();   // an unrecorded timing event must not poison the next launch check
     }
     if (c->hCounters->overflow) {
         char buf[160];
@@ -774,7 +834,7 @@ int sift_debug_blur_bench(SiftContext* c, int32_t scale, int32_t mode, int32_t i
     a.debugMode = mode;
     const bool dual = (mode & 8) != 0;   // tuning: the same launches split over two streams
     a.debugMode = mode & 7;
-    cudaStream_t s2 = c->octStream[1];
+    cudaStream_t s2 = c->octStream[1];   // any second stream
     CTX_TRY(c, launchBlur(a, c->taps[scale], c->ntaps[scale], c->stream));
     CTX_TRY(c, cudaStreamSynchronize(c->stream));
     CTX_TRY(c, cudaEventRecord(c->evBlur0[0], c->stream));

@@ -92,6 +92,7 @@ struct BlurArgs {
     int halfW, halfH, halfPitch;
     size_t halfFrameStride;
     int frames;
+    int yBegin, yEnd;  // output rows [yBegin, yEnd) of the plane (0, 0 = all rows): row bands
     int debugMode;   // 0 normal; 1 skip the X/Y FMA loops; 2 skip the stores; 3 both (tuning only)
 };
 cudaError_t launchBlur(const BlurArgs& a, const Taps& taps, int ntaps, cudaStream_t st);

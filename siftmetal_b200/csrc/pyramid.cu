@@ -169,13 +169,16 @@ blurKernel(const BlurArgs a, const __grid_constant__ Taps taps) {
 
     const int tid = threadIdx.x;
     const int w = a.w, h = a.h, pitch = a.pitch;
-    const int tilesX = (w + TX - 1) / TX, tilesY = (h + TY - 1) / TY;
+    // output rows [yB, yE): the whole plane, or one row band of it (bands of one plane run as
+    // independent launches on separate streams; the mirror boundary still refers to the plane)
+    const int yB = a.yBegin, yE = a.yEnd > 0 ? a.yEnd : h;
+    const int tilesX = (w + TX - 1) / TX, tilesY = (yE - yB + TY - 1) / TY;
     const int tilesPerFrame = tilesX * tilesY;
     const int tile = blockIdx.x;
     const int f = tile / tilesPerFrame;
     const int tr = tile - f * tilesPerFrame;
     const int ty = tr / tilesX, tx = tr - ty * tilesX;
-    const int x0 = tx * TX, y0 = ty * TY;
+    const int x0 = tx * TX, y0 = yB + ty * TY;
     const float* __restrict__ in = a.in + (size_t)f * a.inFrameStride;
 
     // ---- asynchronous load of the input tile with halo, NG row groups ----------------------
@@ -294,7 +297,7 @@ blurKernel(const BlurArgs a, const __grid_constant__ Taps taps) {
                 acc2[q] = pack2(v.x, v.y);
             }
         }
-        const bool full = (x0 + TX <= w) && (y0 + TY <= h);   // CTA-uniform
+        const bool full = (x0 + TX <= w) && (y0 + TY <= yE);   // CTA-uniform
         const bool noStore = (a.debugMode & 2) != 0;
 #pragma unroll
         for (int q = 0; q < RY; q++) {
@@ -312,11 +315,11 @@ blurKernel(const BlurArgs a, const __grid_constant__ Taps taps) {
             } else if (full) {
                 *reinterpret_cast<float2*>(out + o) = r;
                 if (DOG) *reinterpret_cast<float2*>(dog + o) = d2;
-            } else if (gy < h) {
+            } else if (gy < yE) {
                 if (gx < w) { out[o] = r.x; if (DOG) dog[o] = d2.x; }
                 if (gx + 1 < w) { out[o + 1] = r.y; if (DOG) dog[o + 1] = d2.y; }
             }
-            if (HALF && (gy & 1) == 0 && (gy >> 1) < a.halfH && gy < h && (gx >> 1) < a.halfW && gx < w)
+            if (HALF && (gy & 1) == 0 && (gy >> 1) < a.halfH && gy < yE && (gx >> 1) < a.halfW && gx < w)
                 half[(size_t)(gy >> 1) * a.halfPitch + (gx >> 1)] = r.x;   // gx is even
         }
     }
@@ -336,8 +339,9 @@ static cudaError_t launchBlurCfg(const BlurArgs& a, const Taps& taps, cudaStream
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes));
         configured |= 1ull << (dev & 63);
     }
-    const long nTiles = (long)((a.w + TX - 1) / TX) * ((a.h + TY - 1) / TY) * a.frames;
-    if (nTiles > 2147483647L) return cudaErrorInvalidValue;
+    const int rows = (a.yEnd > 0 ? a.yEnd : a.h) - a.yBegin;
+    const long nTiles = (long)((a.w + TX - 1) / TX) * ((rows + TY - 1) / TY) * a.frames;
+    if (nTiles > 2147483647L || rows < 1) return cudaErrorInvalidValue;
     blurKernel<NTAPS, TX, TY, NT, DOG, HALF><<<(unsigned)nTiles, NT, smemBytes, st>>>(a, taps);
     return cudaGetLastError();
 }
@@ -355,7 +359,8 @@ static cudaError_t launchBlurFlags(const BlurArgs& a, const Taps& taps, cudaStre
 // tile, so smaller tiles on more SMs finish sooner.
 template <int NTAPS>
 static cudaError_t launchBlurT(const BlurArgs& a, const Taps& taps, cudaStream_t st) {
-    const long tiles64 = (long)((a.w + 63) / 64) * ((a.h + 63) / 64) * a.frames;
+    const int rows = (a.yEnd > 0 ? a.yEnd : a.h) - a.yBegin;
+    const long tiles64 = (long)((a.w + 63) / 64) * ((rows + 63) / 64) * a.frames;
     if (tiles64 >= 2 * 148) return launchBlurFlags<NTAPS, 64, 64, 256>(a, taps, st);
     return launchBlurFlags<NTAPS, 32, 32, 128>(a, taps, st);
 }
