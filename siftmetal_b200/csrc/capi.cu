@@ -484,9 +484,11 @@ int runDetect(SiftContext* c) {
     // stream once octave o has written slice 3, so the small octaves (launch-latency bound) run
     // under the large kernels of octaves 0 and 1 instead of after them.
     bool forked[kOctaves] = {};
+    static const int dbgMaxOctave = getenv("SIFTCUDA_DEBUG_MAX_OCTAVE") ? atoi(getenv("SIFTCUDA_DEBUG_MAX_OCTAVE")) : kOctaves;
+    static const int dbgSkip = getenv("SIFTCUDA_DEBUG_SKIP") ? atoi(getenv("SIFTCUDA_DEBUG_SKIP")) : 0;  // 1 gradient, 2 extrema
     for (int o = 0; o < kOctaves; o++) {
         const OctaveDev& q = c->P.oct[o];
-        if (q.w < 1 || q.h < 1) continue;
+        if (q.w < 1 || q.h < 1 || o > dbgMaxOctave) continue;
         cudaStream_t so = c->octStream[o];
         if (o > 0) {
             CTX_TRY(c, cudaStreamWaitEvent(so, c->evSeeded[o - 1], 0));
@@ -547,9 +549,9 @@ int runDetect(SiftContext* c) {
         if (T && o == 0) CTX_TRY(c, cudaEventRecord(c->evBlur0[kGaussians - 1], so));
         // (running the gradient beside blur s = 3, 4 on a side stream was measured: no gain, the
         // stage is throughput-bound, and it blurs the per-launch timing of the blur kernel)
-        CTX_TRY(c, launchGradient(q, F, so));
+        if (!(dbgSkip & 1)) CTX_TRY(c, launchGradient(q, F, so));
         c->launches++;
-        if (q.w >= 3 && q.h >= 3) {
+        if (q.w >= 3 && q.h >= 3 && !(dbgSkip & 2)) {
             CTX_TRY(c, launchExtremaMask(c->P, o, c->dMask, F, so));
             c->launches++;
         }
