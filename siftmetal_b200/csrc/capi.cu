@@ -367,6 +367,8 @@ int sift_create(const SiftConfig* cfg, int device, SiftContext** out) {
     A(cudaMallocHost(&c->hKpSeg, std::max<size_t>((size_t)c->capKp * sizeof(int), 64)));
     for (auto& evn : c->ev) A(cudaEventCreate(&evn));
     for (auto& evn : c->evBlur0) A(cudaEventCreate(&evn));
+    int prioLow = 0, prioHigh = 0;
+    cudaDeviceGetStreamPriorityRange(&prioLow, &prioHigh);
     c->octStream[0] = c->stream;
     A(cudaEventCreateWithFlags(&c->evBandFork, cudaEventDisableTiming));
     for (int b = 1; b < SiftContext::kMaxBands; b++) {
@@ -376,7 +378,10 @@ int sift_create(const SiftConfig* cfg, int device, SiftContext** out) {
     }
     if (const char* nb = getenv("SIFTCUDA_BANDS")) c->nBands = std::max(1, std::min(SiftContext::kMaxBands, atoi(nb)));
     for (int o = 0; o < kOctaves; o++) {
-        if (o > 0) A(cudaStreamCreateWithFlags(&c->octStream[o], cudaStreamNonBlocking));
+        // smaller octaves form a long dependent chain of tiny launches: give their streams a higher
+        // priority so that their CTAs are placed ahead of the big octave-0 kernels' when SM slots
+        // free up (the chain is latency-critical, octave 0 is throughput-bound)
+        if (o > 0) A(cudaStreamCreateWithPriority(&c->octStream[o], cudaStreamNonBlocking, prioHigh));
         A(cudaEventCreateWithFlags(&c->evSeeded[o], cudaEventDisableTiming));
         A(cudaEventCreateWithFlags(&c->evOctDone[o], cudaEventDisableTiming));
 
