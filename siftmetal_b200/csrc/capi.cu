@@ -381,7 +381,7 @@ int sift_create(const SiftConfig* cfg, int device, SiftContext** out) {
         // smaller octaves form a long dependent chain of tiny launches: give their streams a higher
         // priority so that their CTAs are placed ahead of the big octave-0 kernels' when SM slots
         // free up (the chain is latency-critical, octave 0 is throughput-bound)
-        if (o > 0) A(cudaStreamCreateWithPriority(&c->octStream[o], cudaStreamNonBlocking, prioHigh));
+        if (o > 0) A(cudaStreamCreateWithPriority(&c->octStream[o], cudaStreamNonBlocking, std::max(prioHigh, prioLow - o)));
         A(cudaEventCreateWithFlags(&c->evSeeded[o], cudaEventDisableTiming));
         A(cudaEventCreateWithFlags(&c->evOctDone[o], cudaEventDisableTiming));
 
