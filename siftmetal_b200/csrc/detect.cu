@@ -125,10 +125,63 @@ extremaMaskKernel(const OctaveDev o, float softThreshold, uint32_t* __restrict__
     }
 }
 
+// Small planes (deep octaves): one thread per pixel, every load independent. The marching
+// kernel above serialises >= 8 dependent row steps per warp, which is pure latency on a plane of a
+// few thousand pixels at the end of the octave chain; this form finishes in one memory round trip.
+__global__ void __launch_bounds__(256)
+extremaMaskSmallKernel(const OctaveDev o, float softThreshold, uint32_t* __restrict__ mask,
+                  int blocksPerFrame) {
+    const int x = blockIdx.x * 256 + threadIdx.x;
+    const int y = blockIdx.y;
+    const int f = blockIdx.z;
+    const int lane = threadIdx.x & 31;
+    const int xw = x >> 5;
+    if (xw >= o.maskRowWords) return;  // whole warp exits together (x is warp-aligned)
+    const float* __restrict__ D = o.D + (size_t)f * kDogs * o.plane;
+    uint32_t* __restrict__ m =
+        mask + ((size_t)f * blocksPerFrame + o.maskBlockStart) * (size_t)kScanChunk;
+    const bool inside = (x >= 1) && (x <= o.w - 2) && (y >= 1) && (y <= o.h - 2);
+    const size_t c = (size_t)y * o.pitch + x;
+#pragma unroll
+    for (int s = 1; s <= kScales; s++) {
+        bool cand = false;
+        if (inside) {
+            const float* __restrict__ p = D + (size_t)s * o.plane + c;
+            const float v = __ldg(p);
+            if (!(fabsf(v) <= softThreshold)) {
+                float mn = +1000.0f, mx = -1000.0f;
+#pragma unroll
+                for (int ds = -1; ds <= 1; ds++) {
+#pragma unroll
+                    for (int dy = -1; dy <= 1; dy++) {
+#pragma unroll
+                        for (int dx = -1; dx <= 1; dx++) {
+                            if (ds == 0 && dy == 0 && dx == 0) continue;       // the centre
+                            if (ds == -1 && dy == -1 && dx == -1) continue;    // neighbour 0
+                            const float nv = __ldg(p + (ptrdiff_t)ds * (ptrdiff_t)o.plane +
+                                                   (ptrdiff_t)dy * o.pitch + dx);
+                            mn = fminf(mn, nv);
+                            mx = fmaxf(mx, nv);
+                        }
+                    }
+                }
+                cand = (v < mn) || (v > mx);
+            }
+        }
+        const uint32_t word = __ballot_sync(0xffffffffu, cand);
+        if (lane == 0) m[((size_t)(s - 1) * o.h + y) * o.maskRowWords + xw] = word;
+    }
+}
+
 cudaError_t launchExtremaMask(const EngineParams& P, int octave, uint32_t* mask, int frames,
                               cudaStream_t st) {
     const OctaveDev& o = P.oct[octave];
     if (o.w < 3 || o.h < 3) return cudaSuccess;
+    if ((long)o.w * o.h * frames <= 96 * 1024) {
+        dim3 grid((o.maskRowWords * 32 + 255) / 256, o.h, frames);
+        extremaMaskSmallKernel<<<grid, 256, 0, st>>>(o, P.dogThreshold * 0.8f, mask, P.blocksPerFrame);
+        return cudaGetLastError();
+    }
     // rows per warp (multiple of 3): long strips amortise the 2-row halo on large planes; small
     // planes get short strips so that the serial row loop does not bound the launch
     const int gx = (o.maskRowWords + kExtWarps - 1) / kExtWarps;
