@@ -13,9 +13,9 @@ Default workload = BASELINE.json configs[1]: a single 1920×1080 frame per step 
              the library on its own stream, summed over the K steps; max over ranks)
   e2e        frames/s through the C-ABI call with HOST (pinned) buffers: H2D of the frames and
              D2H of keypoints + descriptors inside the timed region
-  roofline   the dominant kernel (octave-0 Gaussian blur + DoG, 5 launches per step):
-             algorithmic bytes (12 B per octave-0 pixel per launch: read G[s], write G[s+1],
-             write DoG[s]) ÷ its mean launch time from CUDA events, against the measured HBM peak
+  roofline   the dominant kernel (octave-0 Gaussian blur + DoG, 5 scales per step):
+             algorithmic bytes (12 B per octave-0 pixel per scale: read G[s], write G[s+1],
+             write DoG[s]) ÷ its mean time per scale from CUDA events, against the measured HBM peak
   cpu_baseline   the C++ oracle (a port of the reference's kernels + host stages; the Swift/Metal
              reference cannot run on Linux) on the host cores, bounded sample
 
@@ -348,7 +348,10 @@ def main():
                 "model_B_bytes_per_frame": model_b_bytes, "peak_GBps": peak,
             },
             "roofline": {
-                "bound": "hbm", "kernel": "blurKernel<NTAPS,64,64> octave 0 (5 launches/step: 11,15,17,21,27 taps)",
+                "bound": "hbm",
+                "kernel": "blurKernel<NTAPS,64,64,256> octave 0: 5 scales (11,15,17,21,27 taps) per step; on a large "
+                          "single frame each scale runs as 2 concurrent row-band launches, and avg_launch_ms is the "
+                          "CUDA-event time of the whole 5-scale section / 5 (one scale of the full plane)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture
                 # in profiles/r1/SUMMARY.md (mean of the 5 octave-0 launches, 1080p, cold cache; part
