@@ -58,23 +58,32 @@ struct SiftContext {
     float* dScaled = nullptr;
     int pitch2 = 0;
     uint32_t* dMask = nullptr;
-    int* dBlockSums = nullptr;
-    Candidate* dCands = nullptr;
-    SiftKeypoint* dKpTmp = nullptr;
-    uint32_t* dFlagWords = nullptr;
-    SiftKeypoint* dKps = nullptr;
-    int* dKpSeg = nullptr;
-    int* dSegStarts = nullptr;  // [3][nSegs + 1]: candidates, keypoints, descriptors
-    int* dNOri = nullptr;
-    float* dOriTmp = nullptr;
-    int* dOriOffset = nullptr;
-    int* dDescKp = nullptr;
-    SiftDescriptor* dDesc = nullptr;
-    Counters* dCounters = nullptr;
+    // Device lists + their bookkeeping. Two sets: on a single large frame octave 0 is compacted,
+    // refined and described from set 0 as soon as its extrema mask exists, while the deeper
+    // octaves (a long latency-bound chain of small launches) are still running; they follow from
+    // set 1. Batches and the two-step API use set 0 alone.
+    struct ListSet {
+        int* dBlockSums = nullptr;
+        Candidate* dCands = nullptr;
+        SiftKeypoint* dKpTmp = nullptr;
+        uint32_t* dFlagWords = nullptr;
+        SiftKeypoint* dKps = nullptr;
+        int* dKpSeg = nullptr;
+        int* dSegStarts = nullptr;  // [3][nSegs + 1]: candidates, keypoints, descriptors
+        int* dNOri = nullptr;
+        float* dOriTmp = nullptr;
+        int* dOriOffset = nullptr;
+        int* dDescKp = nullptr;
+        SiftDescriptor* dDesc = nullptr;
+        Counters* dCounters = nullptr;
+        Counters* hCounters = nullptr;   // pinned
+        int* hSegStarts = nullptr;       // pinned
+    } L[2];
+    bool split = false;              // results of the last call live in both sets
+    bool candSplit = false;          // the last detect put octaves >= 1 in set 1 (debug taps)
+    cudaEvent_t evB[5]{};            // stage boundaries of set 1's pass
 
     // pinned host memory
-    Counters* hCounters = nullptr;
-    int* hSegStarts = nullptr;
     SiftKeypoint* hKps = nullptr;
     SiftDescriptor* hDesc = nullptr;
     int* hKpSeg = nullptr;
@@ -153,8 +162,12 @@ void destroy(SiftContext* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (void* p : c->allocations) cudaFree(p);
-    if (c->hCounters) cudaFreeHost(c->hCounters);
-    if (c->hSegStarts) cudaFreeHost(c->hSegStarts);
+    for (int k = 0; k < 2; k++) {
+        if (c->L[k].hCounters) cudaFreeHost(c->L[k].hCounters);
+        if (c->L[k].hSegStarts) cudaFreeHost(c->L[k].hSegStarts);
+    }
+    for (auto& e : c->evB)
+        if (e) cudaEventDestroy(e);
     if (c->hKps) cudaFreeHost(c->hKps);
     if (c->hDesc) cudaFreeHost(c->hDesc);
     if (c->hKpSeg) cudaFreeHost(c->hKpSeg);
@@ -336,19 +349,21 @@ int sift_create(const SiftConfig* cfg, int device, SiftContext** out) {
     const size_t flagWords = (size_t)c->capCand / 32 + 64;
     const size_t nBlockSums = std::max({B * (size_t)c->P.blocksPerFrame, (size_t)c->capCand / 256 + 2,
                                         (size_t)c->capKp / kScanChunk + 2}) + 16;
-    A(devAlloc(c, &c->dBlockSums, nBlockSums));
-    A(devAlloc(c, &c->dCands, (size_t)c->capCand));
-    A(devAlloc(c, &c->dKpTmp, (size_t)c->capCand));
-    A(devAlloc(c, &c->dFlagWords, flagWords));
-    A(devAlloc(c, &c->dKps, (size_t)c->capKp));
-    A(devAlloc(c, &c->dKpSeg, (size_t)c->capKp));
-    A(devAlloc(c, &c->dSegStarts, 3 * (size_t)(c->nSegs + 1)));
-    A(devAlloc(c, &c->dNOri, (size_t)c->capKp + kScanChunk));
-    A(devAlloc(c, &c->dOriTmp, (size_t)c->capKp * kOriBins));
-    A(devAlloc(c, &c->dOriOffset, (size_t)c->capKp + kScanChunk + 1));
-    A(devAlloc(c, &c->dDesc, (size_t)c->capDesc));
-    A(devAlloc(c, &c->dDescKp, (size_t)c->capDesc));
-    A(devAlloc(c, &c->dCounters, 1));
+    for (int k = 0; k < 2; k++) {   // set 1 only ever holds one frame's deeper octaves
+        A(devAlloc(c, &c->L[k].dBlockSums, nBlockSums));
+        A(devAlloc(c, &c->L[k].dCands, (size_t)c->capCand));
+        A(devAlloc(c, &c->L[k].dKpTmp, (size_t)c->capCand));
+        A(devAlloc(c, &c->L[k].dFlagWords, flagWords));
+        A(devAlloc(c, &c->L[k].dKps, (size_t)c->capKp));
+        A(devAlloc(c, &c->L[k].dKpSeg, (size_t)c->capKp));
+        A(devAlloc(c, &c->L[k].dSegStarts, 3 * (size_t)(c->nSegs + 1)));
+        A(devAlloc(c, &c->L[k].dNOri, (size_t)c->capKp + kScanChunk));
+        A(devAlloc(c, &c->L[k].dOriTmp, (size_t)c->capKp * kOriBins));
+        A(devAlloc(c, &c->L[k].dOriOffset, (size_t)c->capKp + kScanChunk + 1));
+        A(devAlloc(c, &c->L[k].dDesc, (size_t)c->capDesc));
+        A(devAlloc(c, &c->L[k].dDescKp, (size_t)c->capDesc));
+        A(devAlloc(c, &c->L[k].dCounters, 1));
+    }
     if (e == cudaSuccess) A(cudaMemset(c->dMask, 0, maskWords * sizeof(uint32_t)));
     // row padding (columns w..pitch) is read by the extrema kernel's full-warp loads and masked
     // afterwards: give it defined contents once
@@ -359,9 +374,17 @@ int sift_create(const SiftConfig* cfg, int device, SiftContext** out) {
         A(cudaMemset(q.grad, 0, B * kScales * q.plane * sizeof(float2)));
     }
     if (e == cudaSuccess) A(cudaMemset(c->dScaled, 0, B * c->P.oct[0].plane * sizeof(float)));
-    if (e == cudaSuccess) A(cudaMemset(c->dSegStarts, 0, 3 * (size_t)(c->nSegs + 1) * sizeof(int)));
-    A(cudaMallocHost(&c->hCounters, sizeof(Counters)));
-    A(cudaMallocHost(&c->hSegStarts, 3 * (size_t)(c->nSegs + 1) * sizeof(int)));
+    for (int k = 0; k < 2 && e == cudaSuccess; k++)
+        A(cudaMemset(c->L[k].dSegStarts, 0, 3 * (size_t)(c->nSegs + 1) * sizeof(int)));
+    for (int k = 0; k < 2; k++) {
+        A(cudaMallocHost(&c->L[k].hCounters, sizeof(Counters)));
+        A(cudaMallocHost(&c->L[k].hSegStarts, 3 * (size_t)(c->nSegs + 1) * sizeof(int)));
+        if (e == cudaSuccess) {
+            memset(c->L[k].hCounters, 0, sizeof(Counters));
+            memset(c->L[k].hSegStarts, 0, 3 * (size_t)(c->nSegs + 1) * sizeof(int));
+        }
+    }
+    for (auto& evn : c->evB) A(cudaEventCreate(&evn));
     A(cudaMallocHost(&c->hKps, std::max<size_t>((size_t)c->capKp * sizeof(SiftKeypoint), 64)));
     A(cudaMallocHost(&c->hDesc, std::max<size_t>((size_t)c->capDesc * sizeof(SiftDescriptor), 64)));
     A(cudaMallocHost(&c->hKpSeg, std::max<size_t>((size_t)c->capKp * sizeof(int), 64)));
@@ -457,14 +480,47 @@ int sift_batch_set_device_input(SiftContext* c, const void* dev, int32_t n, int3
 
 namespace {
 
+// Mask blocks [blockBegin, blockBegin + nBlocks) → ordered candidates → refined keypoints of
+// list set k (SIFTOctave.getKeypoints :198-203, interpolateKeypoints :205-288).
+int postDetect(SiftContext* c, int k, int blockBegin, int nBlocks, int nSegs, cudaEvent_t afterCompaction,
+               cudaEvent_t afterRefine) {
+    SiftContext::ListSet& L = c->L[k];
+    cudaStream_t st = c->stream;
+    CTX_TRY(c, launchCandidateCompaction(c->P, c->dMask, L.dBlockSums, L.dCands, c->capCand, blockBegin,
+                                         nBlocks, L.dCounters, st));
+    CTX_TRY(c, launchCandidateSegmentStarts(L.dCands, &L.dCounters->nCandidates, L.dSegStarts, nSegs, st));
+    c->launches += 4;
+    if (afterCompaction) CTX_TRY(c, cudaEventRecord(afterCompaction, st));
+    CTX_TRY(c, launchRefine(c->P, L.dCands, c->capCand, L.dKpTmp, L.dFlagWords, L.dBlockSums, L.dKps, L.dKpSeg,
+                            c->capKp, nullptr, L.dSegStarts + (c->nSegs + 1), nSegs, L.dCounters, c->smCount, st));
+    c->launches += 5;
+    if (afterRefine) CTX_TRY(c, cudaEventRecord(afterRefine, st));
+    return SIFT_OK;
+}
+
+// getDescriptors (SIFT.swift:207-238) over the keypoints of list set k.
+int describeSet(SiftContext* c, int k, int nSegs, const int* kpIndexBase, cudaEvent_t afterOrientation,
+                cudaEvent_t afterDescriptor) {
+    SiftContext::ListSet& L = c->L[k];
+    cudaStream_t st = c->stream;
+    CTX_TRY(c, launchDescribe(c->P, L.dKps, L.dKpSeg, c->capKp, L.dSegStarts + (c->nSegs + 1), L.dNOri, L.dOriTmp,
+                              L.dOriOffset, L.dDescKp, L.dBlockSums, L.dDesc, c->capDesc,
+                              L.dSegStarts + 2 * (c->nSegs + 1), nSegs, L.dCounters, kpIndexBase, c->smCount, st,
+                              afterOrientation));
+    c->launches += 6;
+    if (afterDescriptor) CTX_TRY(c, cudaEventRecord(afterDescriptor, st));
+    return SIFT_OK;
+}
+
 // findKeypoints + getKeypointsFromOctaves + interpolateKeypoints (SIFT.swift:154-202), all
 // frames of the batch at once, no host synchronisation inside.
-int runDetect(SiftContext* c) {
+int runDetect(SiftContext* c, bool withDescribe) {
     const int F = c->curFrames;
     cudaStream_t st = c->stream;
     const bool T = c->stageTiming;
     c->launches = 0;
-    CTX_TRY(c, cudaMemsetAsync(c->dCounters, 0, sizeof(Counters), st));
+    CTX_TRY(c, cudaMemsetAsync(c->L[0].dCounters, 0, sizeof(Counters), st));
+    CTX_TRY(c, cudaMemsetAsync(c->L[1].dCounters, 0, sizeof(Counters), st));
     if (T) CTX_TRY(c, cudaEventRecord(c->ev[0], st));
     // DifferenceOfGaussians.encodeSeedTexture (:357-389)
     const OctaveDev& o0 = c->P.oct[0];
@@ -561,59 +617,82 @@ int runDetect(SiftContext* c) {
             c->launches++;
         }
         if (o > 0) CTX_TRY(c, cudaEventRecord(c->evOctDone[o], so));
+        if (o == 0) {
+            // Single large frame: octave 0 holds most of the keypoints and is complete long before
+            // the chain of deeper octaves. Compact / refine / describe it now from list set 0; the
+            // (throughput-bound) orientation and descriptor kernels then run over the
+            // (latency-bound) tail of the small octaves, which follow from set 1 after the join.
+            // Measured at 1080p: with prioritised octave streams octave 0 is itself the critical
+            // path (0.47 ms), so the split only adds a second set of scan launches (788 vs 846
+            // frames/s). Off unless SIFTCUDA_SPLIT=1.
+            static const bool wantSplit = getenv("SIFTCUDA_SPLIT") && atoi(getenv("SIFTCUDA_SPLIT")) != 0;
+            c->split = wantSplit && c->bandedOctave0 && c->P.oct[1].maskBlockStart > 0;
+            c->candSplit = c->split;
+            if (c->split) {
+                if (T) CTX_TRY(c, cudaEventRecord(c->ev[2], st));
+                int r = postDetect(c, 0, 0, c->P.oct[1].maskBlockStart, kOctaves, T ? c->ev[3] : nullptr,
+                                   T ? c->ev[4] : nullptr);
+                if (r != SIFT_OK) return r;
+                if (withDescribe) {
+                    r = describeSet(c, 0, kOctaves, nullptr, T ? c->ev[5] : nullptr, T ? c->ev[6] : nullptr);
+                    if (r != SIFT_OK) return r;
+                }
+            }
+        }
     }
     for (int o = 1; o < kOctaves; o++)
         if (forked[o]) CTX_TRY(c, cudaStreamWaitEvent(st, c->evOctDone[o], 0));
-    if (T) CTX_TRY(c, cudaEventRecord(c->ev[2], st));
-    // SIFTOctave.getKeypoints (:198-203): mask → ordered candidate list
-    CTX_TRY(c, launchCandidateCompaction(c->P, c->dMask, c->dBlockSums, c->dCands, c->capCand,
-                                         nullptr, c->dCounters, F, st));
-    CTX_TRY(c, launchCandidateSegmentStarts(c->dCands, &c->dCounters->nCandidates, c->dSegStarts,
-                                            F * kOctaves, st));
-    c->launches += 4;
-    if (T) CTX_TRY(c, cudaEventRecord(c->ev[3], st));
-    // interpolateKeypoints (SIFTOctave.swift:205-288)
-    CTX_TRY(c, launchRefine(c->P, c->dCands, c->capCand, c->dKpTmp, c->dFlagWords, c->dBlockSums,
-                            c->dKps, c->dKpSeg, c->capKp, nullptr,
-                            c->dSegStarts + (c->nSegs + 1), F * kOctaves, c->dCounters,
-                            c->smCount, st));
-    c->launches += 5;
-    if (T) CTX_TRY(c, cudaEventRecord(c->ev[4], st));
+    const int nSegs = F * kOctaves;
+    if (c->split) {
+        if (T) CTX_TRY(c, cudaEventRecord(c->evB[0], st));
+        const int b1 = c->P.oct[1].maskBlockStart;
+        int r = postDetect(c, 1, b1, c->P.blocksPerFrame - b1, kOctaves, T ? c->evB[1] : nullptr,
+                           T ? c->evB[2] : nullptr);
+        if (r != SIFT_OK) return r;
+        if (withDescribe) {
+            r = describeSet(c, 1, kOctaves, &c->L[0].dCounters->nKeypoints, T ? c->evB[3] : nullptr,
+                            T ? c->evB[4] : nullptr);
+            if (r != SIFT_OK) return r;
+        }
+    } else {
+        if (T) CTX_TRY(c, cudaEventRecord(c->ev[2], st));
+        int r = postDetect(c, 0, 0, c->P.blocksPerFrame * F, nSegs, T ? c->ev[3] : nullptr, T ? c->ev[4] : nullptr);
+        if (r != SIFT_OK) return r;
+        if (withDescribe) {
+            r = describeSet(c, 0, nSegs, nullptr, T ? c->ev[5] : nullptr, T ? c->ev[6] : nullptr);
+            if (r != SIFT_OK) return r;
+        }
+    }
     c->executed = true;
-    c->described = false;
+    c->described = withDescribe;
     return SIFT_OK;
 }
 
-// getDescriptors (SIFT.swift:207-238) over the keypoints currently in dKps.
-int runDescribe(SiftContext* c, int nSegs) {
-    cudaStream_t st = c->stream;
-    const bool T = c->stageTiming;
-    CTX_TRY(c, launchDescribe(c->P, c->dKps, c->dKpSeg, c->capKp, c->dSegStarts + (c->nSegs + 1),
-                              c->dNOri, c->dOriTmp, c->dOriOffset, c->dDescKp, c->dBlockSums, c->dDesc,
-                              c->capDesc, c->dSegStarts + 2 * (c->nSegs + 1), nSegs, c->dCounters,
-                              c->smCount, st, T ? c->ev[5] : nullptr));
-    c->launches += 6;
-    if (T) CTX_TRY(c, cudaEventRecord(c->ev[6], st));
-    c->described = true;
-    return SIFT_OK;
-}
-
-// D2H of the small bookkeeping block, stream drain, timing read-out, overflow check.
+// D2H of the small bookkeeping blocks, stream drain, timing read-out, overflow check.
 int finish(SiftContext* c, bool withDescribe) {
     cudaStream_t st = c->stream;
-    CTX_TRY(c, cudaMemcpyAsync(c->hCounters, c->dCounters, sizeof(Counters), cudaMemcpyDeviceToHost, st));
-    CTX_TRY(c, cudaMemcpyAsync(c->hSegStarts, c->dSegStarts, 3 * (size_t)(c->nSegs + 1) * sizeof(int),
-                               cudaMemcpyDeviceToHost, st));
+    const int nSets = c->split ? 2 : 1;
+    const size_t segInts = 3 * (size_t)(c->nSegs + 1);
+    for (int k = 0; k < nSets; k++) {
+        CTX_TRY(c, cudaMemcpyAsync(c->L[k].hCounters, c->L[k].dCounters, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+        CTX_TRY(c, cudaMemcpyAsync(c->L[k].hSegStarts, c->L[k].dSegStarts, segInts * sizeof(int),
+                                   cudaMemcpyDeviceToHost, st));
+    }
     CTX_TRY(c, cudaStreamSynchronize(st));
     const int nSegs = c->curFrames * kOctaves;
-    const int* candStart = c->hSegStarts;
-    const int* kpStart = c->hSegStarts + (c->nSegs + 1);
-    const int* descStart = c->hSegStarts + 2 * (c->nSegs + 1);
-    const int nDesc = c->hCounters->nDescriptors;
-    for (int s = 0; s < nSegs; s++) {
-        c->candCounts[s] = candStart[s + 1] - candStart[s];
-        c->kpCounts[s] = kpStart[s + 1] - kpStart[s];
-        c->descCounts[s] = withDescribe ? std::min(descStart[s + 1], nDesc) - std::min(descStart[s], nDesc) : 0;
+    int overflow = 0;
+    for (int s = 0; s < nSegs; s++) c->candCounts[s] = c->kpCounts[s] = c->descCounts[s] = 0;
+    for (int k = 0; k < nSets; k++) {
+        const int* candStart = c->L[k].hSegStarts;
+        const int* kpStart = c->L[k].hSegStarts + (c->nSegs + 1);
+        const int* descStart = c->L[k].hSegStarts + 2 * (c->nSegs + 1);
+        const int nDesc = c->L[k].hCounters->nDescriptors;
+        for (int s = 0; s < nSegs; s++) {
+            c->candCounts[s] += candStart[s + 1] - candStart[s];
+            c->kpCounts[s] += kpStart[s + 1] - kpStart[s];
+            if (withDescribe) c->descCounts[s] += std::min(descStart[s + 1], nDesc) - std::min(descStart[s], nDesc);
+        }
+        overflow |= c->L[k].hCounters->overflow;
     }
     SiftTimings& t = c->timings;
     memset(&t, 0, sizeof t);
@@ -623,6 +702,19 @@ int finish(SiftContext* c, bool withDescribe) {
         const int last = withDescribe ? SIFT_STAGE_COUNT : 4;
         for (int i = 0; i < last; i++) cudaEventElapsedTime(&t.stage_ms[i], c->ev[i], c->ev[i + 1]);
         cudaEventElapsedTime(&t.total_ms, c->ev[0], c->ev[last]);
+        if (c->split) {
+            // second pass (octaves >= 1): its stages are added to the first pass's; the wait for
+            // the deeper octaves between the passes, if any, counts as pyramid time
+            const int lastB = withDescribe ? 4 : 2;
+            float ms = 0;
+            cudaEventElapsedTime(&ms, c->ev[last], c->evB[0]);
+            t.stage_ms[SIFT_STAGE_PYRAMID] += ms;
+            for (int i = 0; i < lastB; i++) {
+                cudaEventElapsedTime(&ms, c->evB[i], c->evB[i + 1]);
+                t.stage_ms[SIFT_STAGE_EXTREMA + i] += ms;
+            }
+            cudaEventElapsedTime(&t.total_ms, c->ev[0], c->evB[lastB]);
+        }
         cudaEventElapsedTime(&t.blur_octave0_ms, c->evBlur0[0], c->evBlur0[kGaussians - 1]);
         for (int s = 0; s < kGaussians - 1; s++)   // per-scale split only without row bands
             t.blur_octave0_launch_ms[s] = c->bandedOctave0 ? t.blur_octave0_ms / (kGaussians - 1) : 0.0f;
@@ -632,10 +724,10 @@ int finish(SiftContext* c, bool withDescribe) {
         t.blur_octave0_launches = kGaussians - 1;
         cudaGetLastError();   // an unrecorded timing event must not poison the next launch check
     }
-    if (c->hCounters->overflow) {
+    if (overflow) {
         char buf[160];
         snprintf(buf, sizeof buf, "list capacity exceeded (mask %d: 1 candidates, 2 keypoints, 4 descriptors)",
-                 c->hCounters->overflow);
+                 overflow);
         return fail(c, SIFT_ERR_CAPACITY, buf);
     }
     return SIFT_OK;
@@ -649,9 +741,7 @@ int sift_batch_execute(SiftContext* c) {
     if (!c) return SIFT_ERR_INVALID_ARGUMENT;
     if (!c->curInput || c->curFrames < 1) return fail(c, SIFT_ERR_INVALID_ARGUMENT, "no input set");
     CTX_TRY(c, cudaSetDevice(c->device));
-    int r = runDetect(c);
-    if (r != SIFT_OK) return r;
-    r = runDescribe(c, c->curFrames * kOctaves);
+    const int r = runDetect(c, true);
     if (r != SIFT_OK) return r;
     return finish(c, true);
 }
@@ -660,14 +750,21 @@ int sift_batch_download(SiftContext* c, SiftBatchResult* out) {
     if (!c || !out) return SIFT_ERR_INVALID_ARGUMENT;
     if (!c->executed) return fail(c, SIFT_ERR_NOT_DETECTED, "download before execute");
     CTX_TRY(c, cudaSetDevice(c->device));
-    const int64_t nKp = std::min(c->hCounters->nKeypoints, c->capKp);
-    const int64_t nDesc = c->described ? std::min(c->hCounters->nDescriptors, c->capDesc) : 0;
-    if (nKp > 0)
-        CTX_TRY(c, cudaMemcpyAsync(c->hKps, c->dKps, (size_t)nKp * sizeof(SiftKeypoint),
-                                   cudaMemcpyDeviceToHost, c->stream));
-    if (nDesc > 0)
-        CTX_TRY(c, cudaMemcpyAsync(c->hDesc, c->dDesc, (size_t)nDesc * sizeof(SiftDescriptor),
-                                   cudaMemcpyDeviceToHost, c->stream));
+    // list sets are concatenated in order: set 0, then (split mode) set 1 = the deeper octaves
+    int64_t nKp = 0, nDesc = 0;
+    for (int k = 0; k < (c->split ? 2 : 1); k++) {
+        const int64_t nk = std::min(c->L[k].hCounters->nKeypoints, c->capKp);
+        const int64_t nd = c->described ? std::min(c->L[k].hCounters->nDescriptors, c->capDesc) : 0;
+        if (nKp + nk > c->capKp || nDesc + nd > c->capDesc) return fail(c, SIFT_ERR_CAPACITY, "result arrays too small");
+        if (nk > 0)
+            CTX_TRY(c, cudaMemcpyAsync(c->hKps + nKp, c->L[k].dKps, (size_t)nk * sizeof(SiftKeypoint),
+                                       cudaMemcpyDeviceToHost, c->stream));
+        if (nd > 0)
+            CTX_TRY(c, cudaMemcpyAsync(c->hDesc + nDesc, c->L[k].dDesc, (size_t)nd * sizeof(SiftDescriptor),
+                                       cudaMemcpyDeviceToHost, c->stream));
+        nKp += nk;
+        nDesc += nd;
+    }
     CTX_TRY(c, cudaStreamSynchronize(c->stream));
     out->n_frames = c->curFrames;
     out->keypoint_counts = c->kpCounts.data();
@@ -696,7 +793,7 @@ int sift_detect(SiftContext* c, const void* bgra8, int32_t pitchBytes,
     const void* imgs[1] = {bgra8};
     int r = sift_batch_upload(c, imgs, 1, pitchBytes);
     if (r != SIFT_OK) return r;
-    r = runDetect(c);
+    r = runDetect(c, false);
     if (r != SIFT_OK) return r;
     const int re = finish(c, false);
     if (re != SIFT_OK && re != SIFT_ERR_CAPACITY) return re;
@@ -722,7 +819,7 @@ int sift_describe(SiftContext* c, const SiftKeypoint* kps, const int32_t counts[
     if (n > 0 && !kps) return SIFT_ERR_INVALID_ARGUMENT;
     // keypoints may alias our own pinned result buffer (the usual detect → describe flow)
     if (n > 0 && kps != c->hKps) memcpy(c->hKps, kps, (size_t)n * sizeof(SiftKeypoint));
-    int* kpStart = c->hSegStarts + (c->nSegs + 1);
+    int* kpStart = c->L[0].hSegStarts + (c->nSegs + 1);
     int k = 0;
     for (int o = 0; o < kOctaves; o++) {
         kpStart[o] = k;
@@ -733,22 +830,24 @@ int sift_describe(SiftContext* c, const SiftKeypoint* kps, const int32_t counts[
     }
     for (int s = kOctaves; s <= c->nSegs; s++) kpStart[s] = k;
     cudaStream_t st = c->stream;
-    c->hCounters->nKeypoints = (int)n;
-    c->hCounters->nDescriptors = 0;
-    c->hCounters->overflow = 0;
-    CTX_TRY(c, cudaMemcpyAsync(c->dCounters, c->hCounters, sizeof(Counters), cudaMemcpyHostToDevice, st));
+    c->L[0].hCounters->nKeypoints = (int)n;
+    c->L[0].hCounters->nDescriptors = 0;
+    c->L[0].hCounters->overflow = 0;
+    CTX_TRY(c, cudaMemcpyAsync(c->L[0].dCounters, c->L[0].hCounters, sizeof(Counters), cudaMemcpyHostToDevice, st));
     if (n > 0) {
-        CTX_TRY(c, cudaMemcpyAsync(c->dKps, c->hKps, (size_t)n * sizeof(SiftKeypoint), cudaMemcpyHostToDevice, st));
-        CTX_TRY(c, cudaMemcpyAsync(c->dKpSeg, c->hKpSeg, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
+        CTX_TRY(c, cudaMemcpyAsync(c->L[0].dKps, c->hKps, (size_t)n * sizeof(SiftKeypoint), cudaMemcpyHostToDevice, st));
+        CTX_TRY(c, cudaMemcpyAsync(c->L[0].dKpSeg, c->hKpSeg, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
     }
-    CTX_TRY(c, cudaMemcpyAsync(c->dSegStarts + (c->nSegs + 1), kpStart, (size_t)(c->nSegs + 1) * sizeof(int),
+    CTX_TRY(c, cudaMemcpyAsync(c->L[0].dSegStarts + (c->nSegs + 1), kpStart, (size_t)(c->nSegs + 1) * sizeof(int),
                                cudaMemcpyHostToDevice, st));
     const bool T = c->stageTiming;
     c->launches = 0;
     if (T) CTX_TRY(c, cudaEventRecord(c->ev[4], st));
     const int savedFrames = c->curFrames;
     c->curFrames = 1;
-    int r = runDescribe(c, kOctaves);
+    c->split = false;   // caller-supplied keypoints all live in list set 0
+    int r = describeSet(c, 0, kOctaves, nullptr, T ? c->ev[5] : nullptr, T ? c->ev[6] : nullptr);
+    c->described = true;
     if (r != SIFT_OK) { c->curFrames = savedFrames; return r; }
     // bookkeeping without touching the detect-stage events
     const bool savedT = c->stageTiming;
@@ -810,12 +909,13 @@ int64_t sift_debug_candidates(SiftContext* c, int32_t frame, int32_t octave, int
         return -(int64_t)SIFT_ERR_INVALID_ARGUMENT;
     if (cudaSetDevice(c->device) != cudaSuccess) return -(int64_t)SIFT_ERR_CUDA;
     const int seg = frame * kOctaves + octave;
-    const int nAll = std::min(c->hCounters->nCandidates, c->capCand);
-    const int a = std::min(c->hSegStarts[seg], nAll), b = std::min(c->hSegStarts[seg + 1], nAll);
+    const SiftContext::ListSet& L = c->L[(c->candSplit && octave >= 1) ? 1 : 0];
+    const int nAll = std::min(L.hCounters->nCandidates, c->capCand);
+    const int a = std::min(L.hSegStarts[seg], nAll), b = std::min(L.hSegStarts[seg + 1], nAll);
     const int n = b - a;
     if (!dst || n <= 0) return n;
     std::vector<Candidate> tmp((size_t)n);
-    if (cudaMemcpy(tmp.data(), c->dCands + a, (size_t)n * sizeof(Candidate), cudaMemcpyDeviceToHost) != cudaSuccess)
+    if (cudaMemcpy(tmp.data(), L.dCands + a, (size_t)n * sizeof(Candidate), cudaMemcpyDeviceToHost) != cudaSuccess)
         return -(int64_t)SIFT_ERR_CUDA;
     for (int i = 0; i < n && i < capTriples; i++) {
         dst[3 * i + 0] = (int32_t)(tmp[i].xys & 0x7fff);

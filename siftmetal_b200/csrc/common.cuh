@@ -103,7 +103,7 @@ cudaError_t launchExtremaMask(const EngineParams& P, int octave, uint32_t* mask,
                               cudaStream_t st);
 cudaError_t launchCandidateCompaction(const EngineParams& P, const uint32_t* mask,
                                       int* blockSums, Candidate* cands, int capCandidates,
-                                      int* segCandCount, Counters* counters, int frames,
+                                      int blockBegin, int nBlocks, Counters* counters,
                                       cudaStream_t st);
 cudaError_t launchSegmentStarts(const int* kpSeg, const int* nPtr, int* segStart, int nSegs,
                                 cudaStream_t st);
@@ -120,7 +120,8 @@ cudaError_t launchDescribe(const EngineParams& P, const SiftKeypoint* kps, const
                            int capKeypoints, const int* segKpStart, int* nOri, float* oriTmp,
                            int* oriOffset, int* descKp, int* blockSums, SiftDescriptor* desc,
                            int capDescriptors, int* segDescStart, int nSegs, Counters* counters,
-                           int smCount, cudaStream_t stream, cudaEvent_t afterOrientation);
+                           const int* kpIndexBase, int smCount, cudaStream_t stream,
+                           cudaEvent_t afterOrientation);
 
 // math debug (capi.cu → describe.cu)
 cudaError_t launchMathDebug(int op, const float* a, const float* b, float* out, int64_t n,

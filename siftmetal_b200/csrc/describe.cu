@@ -232,7 +232,7 @@ descriptorKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __r
                  const int* __restrict__ kpSeg, const int* __restrict__ segKpStart,
                  const Counters* __restrict__ counters, const int* __restrict__ oriOffset,
                  const float* __restrict__ oriTmp, const int* __restrict__ descKp,
-                 SiftDescriptor* __restrict__ desc, int capacity) {
+                 SiftDescriptor* __restrict__ desc, int capacity, const int* __restrict__ kpIndexBase) {
     extern __shared__ __align__(16) float sDesc[];  // [warp][128 bins][16 copies]
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     float* hist = sDesc + wid * (kDescBins * kDescCopies);
@@ -420,7 +420,9 @@ descriptorKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __r
         uint32_t* dst = reinterpret_cast<uint32_t*>(out->features);
         dst[lane] = reinterpret_cast<const uint32_t*>(bytes)[lane];
         if (lane == 0) {
-            out->keypoint = k - segKpStart[frame * kOctaves];
+            // index in the frame's keypoint array; kpIndexBase: keypoints of this frame that live in
+            // an earlier list (octave 0 is compacted separately on single large frames)
+            out->keypoint = k - segKpStart[frame * kOctaves] + (kpIndexBase ? *kpIndexBase : 0);
             out->theta = theta;
         }
         __syncwarp();
@@ -431,7 +433,8 @@ cudaError_t launchDescribe(const EngineParams& P, const SiftKeypoint* kps, const
                            int capKeypoints, const int* segKpStart, int* nOri, float* oriTmp,
                            int* oriOffset, int* descKp, int* blockSums, SiftDescriptor* desc,
                            int capDescriptors, int* segDescStart, int nSegs, Counters* counters,
-                           int smCount, cudaStream_t st, cudaEvent_t afterOrientation) {
+                           const int* kpIndexBase, int smCount, cudaStream_t st,
+                           cudaEvent_t afterOrientation) {
     orientationKernel<<<smCount * 4, kOriWarps * 32, 0, st>>>(P, kps, kpSeg, counters, nOri, oriTmp);
     SIFT_CUDA_TRY(cudaGetLastError());
     const int nBlocks = (capKeypoints + 1 + kScanChunk - 1) / kScanChunk;
@@ -458,7 +461,7 @@ cudaError_t launchDescribe(const EngineParams& P, const SiftKeypoint* kps, const
         configured |= 1ull << (dev & 63);
     }
     descriptorKernel<<<smCount * 6, kDescWarps * 32, smemBytes, st>>>(
-        P, kps, kpSeg, segKpStart, counters, oriOffset, oriTmp, descKp, desc, capDescriptors);
+        P, kps, kpSeg, segKpStart, counters, oriOffset, oriTmp, descKp, desc, capDescriptors, kpIndexBase);
     return cudaGetLastError();
 }
 

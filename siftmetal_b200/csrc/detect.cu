@@ -254,9 +254,9 @@ struct MaskPopc {
 __global__ void __launch_bounds__(kScanThreads)
 scatterCandidatesKernel(const __grid_constant__ EngineParams P, const uint32_t* __restrict__ mask,
                         const int* __restrict__ blockOffsets, Candidate* __restrict__ cands,
-                        int capacity) {
+                        int capacity, int blockBegin) {
     __shared__ int sh[9];
-    const int b = blockIdx.x;
+    const int b = blockBegin + blockIdx.x;   // global mask block; blockOffsets is indexed locally
     const int frame = b / P.blocksPerFrame;
     const int fb = b - frame * P.blocksPerFrame;
     int oc = 0;
@@ -274,7 +274,7 @@ scatterCandidatesKernel(const __grid_constant__ EngineParams P, const uint32_t* 
         s += __popc(words[k]);
     }
     int total;
-    int pos = blockOffsets[b] + blockExclusiveScan256(s, sh, &total);
+    int pos = blockOffsets[blockIdx.x] + blockExclusiveScan256(s, sh, &total);
     if (s == 0) return;
     const int seg = frame * kOctaves + oc;
 #pragma unroll
@@ -302,17 +302,16 @@ scatterCandidatesKernel(const __grid_constant__ EngineParams P, const uint32_t* 
 
 cudaError_t launchCandidateCompaction(const EngineParams& P, const uint32_t* mask,
                                       int* blockSums, Candidate* cands, int capCandidates,
-                                      int* segCandCount, Counters* counters, int frames,
+                                      int blockBegin, int nBlocks, Counters* counters,
                                       cudaStream_t st) {
-    (void)segCandCount;
-    const int nBlocks = P.blocksPerFrame * frames;
-    MaskPopc v{mask};
+    if (nBlocks < 1) return cudaSuccess;
+    MaskPopc v{mask + (size_t)blockBegin * kScanChunk};
     scanBlockSumsKernel<<<nBlocks, kScanThreads, 0, st>>>(v, blockSums);
     SIFT_CUDA_TRY(cudaGetLastError());
     SIFT_CUDA_TRY(launchScanOffsets(blockSums, nBlocks, &counters->nCandidates, capCandidates,
                                     &counters->overflow, 1, st));
     scatterCandidatesKernel<<<nBlocks, kScanThreads, 0, st>>>(P, mask, blockSums, cands,
-                                                              capCandidates);
+                                                              capCandidates, blockBegin);
     return cudaGetLastError();
 }
 

@@ -262,3 +262,30 @@ def test_full_size_properties_1080p():
     assert np.array_equal(a.keypoint_counts[0], ocounts)
     assert np.array_equal(k["scaledX"], okps["scaledX"]) and np.array_equal(k["scaledY"], okps["scaledY"])
     assert np.all(np.abs(k["absoluteX"] - okps["absoluteX"]) <= POS_TOL)
+
+
+def test_split_list_mode_matches(monkeypatch):
+    """SIFTCUDA_SPLIT=1 (octave 0 compacted and described ahead of the deeper octaves, from a
+    second list set) must give the same result arrays as the default single pass."""
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, '.');"
+        "from siftmetal_b200 import Engine; from siftmetal_b200.synth import pink_noise_bgra;"
+        "img = pink_noise_bgra(1920, 1080, 5); e = Engine(1920, 1080); r = e.detect_and_describe([img]);"
+        "c = sum(len(e.candidates(o)) for o in range(7));"
+        "np.savez(sys.argv[1], k=r.keypoints, d=r.descriptors, kc=r.keypoint_counts, dc=r.descriptor_counts, c=c)"
+    )
+    outs = []
+    for flag in ("0", "1"):
+        path = f"/tmp/sift_split_{flag}.npz"
+        env = dict(os.environ, SIFTCUDA_SPLIT=flag)
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=env,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        outs.append(np.load(path))
+    a, b = outs
+    assert int(a["c"]) == int(b["c"])
+    for key in ("k", "d", "kc", "dc"):
+        assert np.array_equal(a[key], b[key]), key
