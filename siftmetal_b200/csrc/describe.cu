@@ -219,21 +219,75 @@ __global__ void descSegmentStartsKernel(const int* __restrict__ segKpStart,
 // Window radius, sample coordinates and centre truncation follow the spec's exact sequences;
 // per-sample weights use FMA / reciprocal / ex2.approx — continuous quantities within the ±1
 // tolerance of the quantised features.
-constexpr int kDescCopies = 32;    // histogram copies per warp. 16 = lanes l and l + 16 share one and
-                                   // update it in two half-warp rounds (8 KB per warp, twice the
-                                   // resident warps): measured equal (472 vs 463 us at 1080p) — the
-                                   // kernel is instruction-bound, so the simpler lane-private form stays
-constexpr int kDescWarps = 64 / kDescCopies;   // 32 KB of histograms per CTA
+constexpr int kDescCopies = 32;    // lane-private histogram copies (16 KB per warp). Sharing one copy
+                                   // between lanes l and l + 16 in two half-warp rounds (8 KB, twice
+                                   // the resident warps) measured equal: 472 vs 463 us at 1080p
+constexpr int kDescWarps = 2;      // 32 KB of histograms per CTA
 constexpr int kDescMaxSide = 128;  // 2·radius+1; radius <= 39 for detected keypoints
 constexpr int kDescBins = 128;
+constexpr int kDescDefaultWalk = 0;
 
+// Trilinear accumulation of one sample into the lane's histogram copy (addFeature,
+// SIFTDescriptor.metal:82-117). Two base addresses per sample (one per orientation bin); the
+// four cells are immediate offsets; loads / stores of cells outside the 4x4 grid are predicated off.
+__device__ __forceinline__ void descAccumulate(char* const hl, const float2 gm, const float bx,
+                                               const float by, const float r2, const bool ok,
+                                               const float theta) {
+    // orientation relative to theta, wrapped to [0, 1) turns, then 8 bins
+    float turn = (gm.x - theta) * (1.0f / kTau);
+    turn -= floorf(turn);
+    const float bin = turn * 8.0f;
+    const int bi = (int)bin;                   // bin >= 0: truncation = floor
+    const float fb = bin - (float)bi;
+    const float val = gm.y * __expf(-r2 * 0.125f);
+    const int x0 = __float2int_rd(bx), y0 = __float2int_rd(by);   // in [-1, 3] when ok
+    const float fxw = bx - (float)x0, fyw = by - (float)y0;
+    // ceil = floor + 1 except on exact integers, where the reference adds a zero weight to the
+    // floor cell — same sums either way.
+    const float vx0 = val * (1.0f - fxw), vx1 = val * fxw;
+    const float v00 = vx0 * (1.0f - fyw), v01 = vx0 * fyw;
+    const float v10 = vx1 * (1.0f - fyw), v11 = vx1 * fyw;
+    const bool okx0 = ok && (x0 >= 0), okx1 = ok && (x0 < 3);
+    const bool oky0 = (y0 >= 0), oky1 = (y0 < 3);
+    const bool c00 = okx0 && oky0, c10 = okx1 && oky0, c01 = okx0 && oky1, c11 = okx1 && oky1;
+    const int cellB = (y0 * 4 + x0) * (8 * kDescCopies * 4);        // bytes: cell (x0, y0), bin 0
+    float* const p0 = reinterpret_cast<float*>(hl + cellB + (bi & 7) * (kDescCopies * 4));
+    float* const p1 = reinterpret_cast<float*>(hl + cellB + ((bi + 1) & 7) * (kDescCopies * 4));
+    constexpr int DX = 8 * kDescCopies, DY = 32 * kDescCopies;      // floats to cell x+1 / y+1
+    const float g0 = 1.0f - fb;
+    // the eight addresses of a lane are distinct and private: load all, add, store all
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f, t4 = 0.f, t5 = 0.f, t6 = 0.f, t7 = 0.f;
+    if (c00) t0 = p0[0];
+    if (c00) t1 = p1[0];
+    if (c10) t2 = p0[DX];
+    if (c10) t3 = p1[DX];
+    if (c01) t4 = p0[DY];
+    if (c01) t5 = p1[DY];
+    if (c11) t6 = p0[DY + DX];
+    if (c11) t7 = p1[DY + DX];
+    if (c00) p0[0] = fmaf(v00, g0, t0);
+    if (c00) p1[0] = fmaf(v00, fb, t1);
+    if (c10) p0[DX] = fmaf(v10, g0, t2);
+    if (c10) p1[DX] = fmaf(v10, fb, t3);
+    if (c01) p0[DY] = fmaf(v01, g0, t4);
+    if (c01) p1[DY] = fmaf(v01, fb, t5);
+    if (c11) p0[DY + DX] = fmaf(v11, g0, t6);
+    if (c11) p1[DY + DX] = fmaf(v11, fb, t7);
+}
+
+// WALK = 0: lanes walk the flattened spans densely (x fastest, stride 32): every lane slot is a
+//           sample, but a lane changes row almost every step and re-derives that row's bounds.
+// WALK = C (4, 8, 16): the warp is a (32 / C)-row x C-column tile marching along C-wide chunks
+//           of 32 / C rows at a time: bounds once per row group, control flow uniform and
+//           branch-free per sample, at the price of idle lane slots at the ragged span ends.
+template <int WALK>
 __global__ void __launch_bounds__(kDescWarps * 32)
 descriptorKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __restrict__ kps,
                  const int* __restrict__ kpSeg, const int* __restrict__ segKpStart,
                  const Counters* __restrict__ counters, const int* __restrict__ oriOffset,
                  const float* __restrict__ oriTmp, const int* __restrict__ descKp,
                  SiftDescriptor* __restrict__ desc, int capacity, const int* __restrict__ kpIndexBase) {
-    extern __shared__ __align__(16) float sDesc[];  // [warp][128 bins][16 copies]
+    extern __shared__ __align__(16) float sDesc[];  // [warp][128 bins][32 copies]
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     float* hist = sDesc + wid * (kDescBins * kDescCopies);
     const int nKp = counters->nKeypoints;
@@ -282,104 +336,86 @@ descriptorKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __r
 #pragma unroll 8
         for (int bb = 0; bb < 128 * kDescCopies / 32; bb++) hist[bb * 32 + lane] = 0.0f;
         __syncwarp();
+        char* const hl = reinterpret_cast<char*>(hist + lane);
 
-        // lane state: row i, first x offset jlo of the row's span, span length n, position pos,
-        // gradient row pointer (already offset by ipx)
-        int i = iMin, jlo = 0, n = 0, pos = lane;
-        const float2* __restrict__ grow = g;
-        auto rowBounds = [&]() {
-            const float fi = (float)i;
-            const float lo = fmaxf(fmaxf(fmaf(fi, s1, -c1), fmaf(fi, s2, -c2)), xlo);
-            const float hi = fminf(fminf(fmaf(fi, s1, c1), fmaf(fi, s2, c2)), xhi);
-            jlo = (int)ceilf(lo - 1.0f);                 // widened by < 1 on each side, still in the plane
-            jlo = max(jlo, -ipx);
-            n = max(min((int)floorf(hi + 1.0f), o.w - 1 - ipx) - jlo + 1, 0);
-            grow = g + (size_t)(ipy + min(i, iMax)) * o.pitch + ipx;
-        };
-        auto settle = [&]() {   // move to the row that contains position pos
-            while (i <= iMax && pos >= n) {
-                pos -= n;
-                i++;
-                rowBounds();
+        if constexpr (WALK == 0) {
+            // lane state: row i, first x offset jlo of the row's span, span length n, position pos,
+            // gradient row pointer (already offset by ipx)
+            int i = iMin, jlo = 0, n = 0, pos = lane;
+            const float2* __restrict__ grow = g;
+            auto rowBounds = [&]() {
+                const float fi = (float)i;
+                const float lo = fmaxf(fmaxf(fmaf(fi, s1, -c1), fmaf(fi, s2, -c2)), xlo);
+                const float hi = fminf(fminf(fmaf(fi, s1, c1), fmaf(fi, s2, c2)), xhi);
+                jlo = (int)ceilf(lo - 1.0f);                 // widened by < 1 on each side, still in the plane
+                jlo = max(jlo, -ipx);
+                n = max(min((int)floorf(hi + 1.0f), o.w - 1 - ipx) - jlo + 1, 0);
+                grow = g + (size_t)(ipy + min(i, iMax)) * o.pitch + ipx;
+            };
+            auto settle = [&]() {   // move to the row that contains position pos
+                while (i <= iMax && pos >= n) {
+                    pos -= n;
+                    i++;
+                    rowBounds();
+                }
+            };
+            rowBounds();
+            settle();
+            while (__any_sync(0xffffffffu, i <= iMax)) {
+                // phase 1: four samples per lane, coordinates + gather issued back to back
+                float2 gm[4];
+                float bxs[4], bys[4], r2s[4];
+                bool ok[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int j = jlo + pos;
+                    const float fj = (float)j, fi = (float)i;
+                    const float rx = fj * a - fi * b;
+                    const float ry = fj * b + fi * a;
+                    // addValue drops cells outside [0, 4): nothing lands unless -1 < rx + 1.5 < 4, same in y
+                    ok[u] = (i <= iMax) && fabsf(rx) < 2.5f && fabsf(ry) < 2.5f;
+                    gm[u] = __ldg(grow + (ok[u] ? j : -ipx));
+                    bxs[u] = rx + 1.5f;
+                    bys[u] = ry + 1.5f;
+                    r2s[u] = rx * rx + ry * ry;
+                    pos += 32;
+                    settle();
+                }
+                // phase 2: trilinear accumulation
+#pragma unroll
+                for (int u = 0; u < 4; u++) descAccumulate(hl, gm[u], bxs[u], bys[u], r2s[u], ok[u], theta);
             }
-        };
-        rowBounds();
-        settle();
-        char* const hl = reinterpret_cast<char*>(hist + (lane & (kDescCopies - 1)));
-        const bool firstHalf = lane < kDescCopies;
-        (void)firstHalf;
-        while (__any_sync(0xffffffffu, i <= iMax)) {
-            // phase 1: four samples per lane, coordinates + gather issued back to back
-            float2 gm[4];
-            float bxs[4], bys[4], r2s[4];
-            bool ok[4];
+        } else {
+            constexpr int TC = WALK, TR = 32 / WALK;   // tile columns / rows
+            const int lr = lane / TC, lc = lane % TC;
+            for (int ig = iMin; ig <= iMax; ig += TR) {
+                const int i = ig + lr;
+                const float fi = (float)i;
+                const float lo = fmaxf(fmaxf(fmaf(fi, s1, -c1), fmaf(fi, s2, -c2)), xlo);
+                const float hi = fminf(fminf(fmaf(fi, s1, c1), fmaf(fi, s2, c2)), xhi);
+                const int jlo = max((int)ceilf(lo - 1.0f), -ipx) + lc;   // this lane's first x offset
+                const int jhi = (i <= iMax) ? min((int)floorf(hi + 1.0f), o.w - 1 - ipx) : -(1 << 20);
+                const int chunks = __reduce_max_sync(0xffffffffu, max(jhi - jlo + TC, 0)) / TC;
+                const float2* __restrict__ grow = g + (size_t)(ipy + min(i, iMax)) * o.pitch + ipx;
+                const float fib = fi * b, fia = fi * a;
+                for (int c = 0; c < chunks; c += 2) {
+                    float2 gm[2];
+                    float bxs[2], bys[2], r2s[2];
+                    bool ok[2];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int j = jlo + pos;
-                const float fj = (float)j, fi = (float)i;
-                const float rx = fj * a - fi * b;
-                const float ry = fj * b + fi * a;
-                // addValue drops cells outside [0, 4): nothing lands unless -1 < rx + 1.5 < 4, same in y
-                ok[u] = (i <= iMax) && fabsf(rx) < 2.5f && fabsf(ry) < 2.5f;
-                gm[u] = __ldg(grow + (ok[u] ? j : -ipx));
-                bxs[u] = rx + 1.5f;
-                bys[u] = ry + 1.5f;
-                r2s[u] = rx * rx + ry * ry;
-                pos += 32;
-                settle();
-            }
-            // phase 2: trilinear accumulation (addFeature, SIFTDescriptor.metal:82-117). Two base
-            // addresses per sample (one per orientation bin); the four cells are immediate
-            // offsets; loads / stores of cells outside the 4x4 grid are predicated off.
+                    for (int u = 0; u < 2; u++) {
+                        const int j = jlo + (c + u) * TC;
+                        const float fj = (float)j;
+                        const float rx = fj * a - fib;
+                        const float ry = fj * b + fia;
+                        ok[u] = (j <= jhi) && fabsf(rx) < 2.5f && fabsf(ry) < 2.5f;
+                        gm[u] = __ldg(grow + (ok[u] ? j : -ipx));
+                        bxs[u] = rx + 1.5f;
+                        bys[u] = ry + 1.5f;
+                        r2s[u] = rx * rx + ry * ry;
+                    }
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const float bx = bxs[u], by = bys[u];
-                // orientation relative to theta, wrapped to [0, 1) turns, then 8 bins
-                float turn = (gm[u].x - theta) * (1.0f / kTau);
-                turn -= floorf(turn);
-                const float bin = turn * 8.0f;
-                const int bi = (int)bin;                   // bin >= 0: truncation = floor
-                const float fb = bin - (float)bi;
-                const float val = gm[u].y * __expf(-r2s[u] * 0.125f);
-                const int x0 = __float2int_rd(bx), y0 = __float2int_rd(by);   // in [-1, 3] when ok
-                const float fxw = bx - (float)x0, fyw = by - (float)y0;
-                // ceil = floor + 1 except on exact integers, where the reference adds a zero
-                // weight to the floor cell — same sums either way.
-                const float vx0 = val * (1.0f - fxw), vx1 = val * fxw;
-                const float v00 = vx0 * (1.0f - fyw), v01 = vx0 * fyw;
-                const float v10 = vx1 * (1.0f - fyw), v11 = vx1 * fyw;
-                const bool okx0 = ok[u] && (x0 >= 0), okx1 = ok[u] && (x0 < 3);
-                const bool oky0 = (y0 >= 0), oky1 = (y0 < 3);
-                const bool c00 = okx0 && oky0, c10 = okx1 && oky0, c01 = okx0 && oky1, c11 = okx1 && oky1;
-                const int cellB = (y0 * 4 + x0) * (8 * kDescCopies * 4);        // bytes: cell (x0, y0), bin 0
-                float* const p0 = reinterpret_cast<float*>(hl + cellB + (bi & 7) * (kDescCopies * 4));
-                float* const p1 = reinterpret_cast<float*>(hl + cellB + ((bi + 1) & 7) * (kDescCopies * 4));
-                constexpr int DX = 8 * kDescCopies, DY = 32 * kDescCopies;      // floats to cell x+1 / y+1
-                const float g0 = 1.0f - fb;
-                // Two half-warp rounds (lanes l and l + 16 share a copy). Within a round the eight
-                // addresses of a lane are distinct and private: load all, add, store all.
-#pragma unroll
-                for (int round = 0; round < 32 / kDescCopies; round++) {
-                    const bool mine = (kDescCopies == 32) || ((round == 0) == firstHalf);
-                    const bool d00 = c00 && mine, d10 = c10 && mine, d01 = c01 && mine, d11 = c11 && mine;
-                    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f, t4 = 0.f, t5 = 0.f, t6 = 0.f, t7 = 0.f;
-                    if (d00) t0 = p0[0];
-                    if (d00) t1 = p1[0];
-                    if (d10) t2 = p0[DX];
-                    if (d10) t3 = p1[DX];
-                    if (d01) t4 = p0[DY];
-                    if (d01) t5 = p1[DY];
-                    if (d11) t6 = p0[DY + DX];
-                    if (d11) t7 = p1[DY + DX];
-                    if (d00) p0[0] = fmaf(v00, g0, t0);
-                    if (d00) p1[0] = fmaf(v00, fb, t1);
-                    if (d10) p0[DX] = fmaf(v10, g0, t2);
-                    if (d10) p1[DX] = fmaf(v10, fb, t3);
-                    if (d01) p0[DY] = fmaf(v01, g0, t4);
-                    if (d01) p1[DY] = fmaf(v01, fb, t5);
-                    if (d11) p0[DY + DX] = fmaf(v11, g0, t6);
-                    if (d11) p1[DY + DX] = fmaf(v11, fb, t7);
-                    if (kDescCopies < 32) __syncwarp();
+                    for (int u = 0; u < 2; u++) descAccumulate(hl, gm[u], bxs[u], bys[u], r2s[u], ok[u], theta);
                 }
             }
         }
@@ -451,18 +487,20 @@ cudaError_t launchDescribe(const EngineParams& P, const SiftKeypoint* kps, const
     SIFT_CUDA_TRY(cudaGetLastError());
     if (afterOrientation) SIFT_CUDA_TRY(cudaEventRecord(afterOrientation, st));
 
-    static unsigned long long configured = 0;
     const int smemBytes = kDescWarps * kDescBins * kDescCopies * (int)sizeof(float);
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!((configured >> (dev & 63)) & 1ull)) {
-        SIFT_CUDA_TRY(cudaFuncSetAttribute(descriptorKernel,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes));
-        configured |= 1ull << (dev & 63);
+    static const int walk = getenv("SIFTCUDA_DESC_WALK") ? atoi(getenv("SIFTCUDA_DESC_WALK")) : kDescDefaultWalk;
+    auto launch = [&](auto kernel) -> cudaError_t {
+        SIFT_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes));
+        kernel<<<smCount * 6, kDescWarps * 32, smemBytes, st>>>(
+            P, kps, kpSeg, segKpStart, counters, oriOffset, oriTmp, descKp, desc, capDescriptors, kpIndexBase);
+        return cudaGetLastError();
+    };
+    switch (walk) {
+        case 4: return launch(descriptorKernel<4>);
+        case 8: return launch(descriptorKernel<8>);
+        case 16: return launch(descriptorKernel<16>);
+        default: return launch(descriptorKernel<0>);
     }
-    descriptorKernel<<<smCount * 6, kDescWarps * 32, smemBytes, st>>>(
-        P, kps, kpSeg, segKpStart, counters, oriOffset, oriTmp, descKp, desc, capDescriptors, kpIndexBase);
-    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------
