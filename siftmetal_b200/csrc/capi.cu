@@ -79,6 +79,15 @@ struct SiftContext {
         Counters* hCounters = nullptr;   // pinned
         int* hSegStarts = nullptr;       // pinned
     } L[2];
+    // Host-resident results (the fused host-buffer entry points): the descriptor kernel stores its
+    // 136-byte records straight into the pinned result array over PCIe while it runs, and the
+    // keypoints leave on a copy stream as soon as refinement has counted them — no D2H pass after
+    // the last kernel.
+    bool wantHostOut = false;        // request for the next runDetect / describe
+    bool descOnHost = false;         // last describe wrote c->hDesc directly
+    bool kpsOnHost = false;          // last detect's keypoints were already copied to c->hKps
+    cudaStream_t copyStream = nullptr;
+    cudaEvent_t evRefined = nullptr, evKpCopied = nullptr;
     bool split = false;              // results of the last call live in both sets
     bool candSplit = false;          // the last detect put octaves >= 1 in set 1 (debug taps)
     cudaEvent_t evB[5]{};            // stage boundaries of set 1's pass
@@ -187,6 +196,9 @@ void destroy(SiftContext* c) {
         if (c->evBandDone[b]) cudaEventDestroy(c->evBandDone[b]);
     }
     if (c->evBandFork) cudaEventDestroy(c->evBandFork);
+    if (c->evRefined) cudaEventDestroy(c->evRefined);
+    if (c->evKpCopied) cudaEventDestroy(c->evKpCopied);
+    if (c->copyStream) cudaStreamDestroy(c->copyStream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -394,6 +406,9 @@ int sift_create(const SiftConfig* cfg, int device, SiftContext** out) {
     cudaDeviceGetStreamPriorityRange(&prioLow, &prioHigh);
     c->octStream[0] = c->stream;
     A(cudaEventCreateWithFlags(&c->evBandFork, cudaEventDisableTiming));
+    A(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
+    A(cudaEventCreateWithFlags(&c->evRefined, cudaEventDisableTiming));
+    A(cudaEventCreateWithFlags(&c->evKpCopied, cudaEventDisableTiming));
     for (int b = 1; b < SiftContext::kMaxBands; b++) {
         A(cudaStreamCreateWithFlags(&c->bandStream[b], cudaStreamNonBlocking));
         A(cudaEventCreateWithFlags(&c->evBandSeeded[b], cudaEventDisableTiming));
@@ -503,8 +518,9 @@ int describeSet(SiftContext* c, int k, int nSegs, const int* kpIndexBase, cudaEv
                 cudaEvent_t afterDescriptor) {
     SiftContext::ListSet& L = c->L[k];
     cudaStream_t st = c->stream;
+    c->descOnHost = c->wantHostOut && !c->split;   // pinned memory is device-addressable (UVA)
     CTX_TRY(c, launchDescribe(c->P, L.dKps, L.dKpSeg, c->capKp, L.dSegStarts + (c->nSegs + 1), L.dNOri, L.dOriTmp,
-                              L.dOriOffset, L.dDescKp, L.dBlockSums, L.dDesc, c->capDesc,
+                              L.dOriOffset, L.dDescKp, L.dBlockSums, c->descOnHost ? c->hDesc : L.dDesc, c->capDesc,
                               L.dSegStarts + 2 * (c->nSegs + 1), nSegs, L.dCounters, kpIndexBase, c->smCount, st,
                               afterOrientation));
     c->launches += 6;
@@ -519,6 +535,7 @@ int runDetect(SiftContext* c, bool withDescribe) {
     cudaStream_t st = c->stream;
     const bool T = c->stageTiming;
     c->launches = 0;
+    c->kpsOnHost = c->descOnHost = false;
     CTX_TRY(c, cudaMemsetAsync(c->L[0].dCounters, 0, sizeof(Counters), st));
     CTX_TRY(c, cudaMemsetAsync(c->L[1].dCounters, 0, sizeof(Counters), st));
     if (T) CTX_TRY(c, cudaEventRecord(c->ev[0], st));
@@ -658,6 +675,11 @@ int runDetect(SiftContext* c, bool withDescribe) {
         if (T) CTX_TRY(c, cudaEventRecord(c->ev[2], st));
         int r = postDetect(c, 0, 0, c->P.blocksPerFrame * F, nSegs, T ? c->ev[3] : nullptr, T ? c->ev[4] : nullptr);
         if (r != SIFT_OK) return r;
+        if (c->wantHostOut) {   // keypoint count for the early copy (earlyKeypointCopy)
+            CTX_TRY(c, cudaMemcpyAsync(c->L[0].hCounters, c->L[0].dCounters, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+            CTX_TRY(c, cudaEventRecord(c->evRefined, st));
+            c->kpsOnHost = true;
+        }
         if (withDescribe) {
             r = describeSet(c, 0, nSegs, nullptr, T ? c->ev[5] : nullptr, T ? c->ev[6] : nullptr);
             if (r != SIFT_OK) return r;
@@ -665,6 +687,20 @@ int runDetect(SiftContext* c, bool withDescribe) {
     }
     c->executed = true;
     c->described = withDescribe;
+    return SIFT_OK;
+}
+
+// Host-output mode: while the orientation and descriptor kernels (already queued) run, wait for
+// the refined-keypoint count and send the keypoints home on the copy stream.
+int earlyKeypointCopy(SiftContext* c) {
+    if (!c->kpsOnHost) return SIFT_OK;
+    CTX_TRY(c, cudaEventSynchronize(c->evRefined));
+    const int64_t nk = std::min(c->L[0].hCounters->nKeypoints, c->capKp);
+    if (nk > 0) {
+        CTX_TRY(c, cudaMemcpyAsync(c->hKps, c->L[0].dKps, (size_t)nk * sizeof(SiftKeypoint), cudaMemcpyDeviceToHost,
+                                   c->copyStream));
+    }
+    CTX_TRY(c, cudaEventRecord(c->evKpCopied, c->copyStream));
     return SIFT_OK;
 }
 
@@ -679,6 +715,7 @@ int finish(SiftContext* c, bool withDescribe) {
                                    cudaMemcpyDeviceToHost, st));
     }
     CTX_TRY(c, cudaStreamSynchronize(st));
+    if (c->kpsOnHost) CTX_TRY(c, cudaEventSynchronize(c->evKpCopied));
     const int nSegs = c->curFrames * kOctaves;
     int overflow = 0;
     for (int s = 0; s < nSegs; s++) c->candCounts[s] = c->kpCounts[s] = c->descCounts[s] = 0;
@@ -741,6 +778,7 @@ int sift_batch_execute(SiftContext* c) {
     if (!c) return SIFT_ERR_INVALID_ARGUMENT;
     if (!c->curInput || c->curFrames < 1) return fail(c, SIFT_ERR_INVALID_ARGUMENT, "no input set");
     CTX_TRY(c, cudaSetDevice(c->device));
+    c->wantHostOut = false;   // staged path: results stay in HBM until sift_batch_download
     const int r = runDetect(c, true);
     if (r != SIFT_OK) return r;
     return finish(c, true);
@@ -756,10 +794,10 @@ int sift_batch_download(SiftContext* c, SiftBatchResult* out) {
         const int64_t nk = std::min(c->L[k].hCounters->nKeypoints, c->capKp);
         const int64_t nd = c->described ? std::min(c->L[k].hCounters->nDescriptors, c->capDesc) : 0;
         if (nKp + nk > c->capKp || nDesc + nd > c->capDesc) return fail(c, SIFT_ERR_CAPACITY, "result arrays too small");
-        if (nk > 0)
+        if (nk > 0 && !c->kpsOnHost)
             CTX_TRY(c, cudaMemcpyAsync(c->hKps + nKp, c->L[k].dKps, (size_t)nk * sizeof(SiftKeypoint),
                                        cudaMemcpyDeviceToHost, c->stream));
-        if (nd > 0)
+        if (nd > 0 && !c->descOnHost)
             CTX_TRY(c, cudaMemcpyAsync(c->hDesc + nDesc, c->L[k].dDesc, (size_t)nd * sizeof(SiftDescriptor),
                                        cudaMemcpyDeviceToHost, c->stream));
         nKp += nk;
@@ -779,9 +817,17 @@ int sift_batch_download(SiftContext* c, SiftBatchResult* out) {
 
 int sift_detect_and_describe_batch(SiftContext* c, const void* const* images, int32_t n,
                                    int32_t pitchBytes, SiftBatchResult* out) {
+    if (!out) return SIFT_ERR_INVALID_ARGUMENT;
     int r = sift_batch_upload(c, images, n, pitchBytes);
     if (r != SIFT_OK) return r;
-    const int re = sift_batch_execute(c);
+    static const bool hostOut = !(getenv("SIFTCUDA_HOST_OUT") && atoi(getenv("SIFTCUDA_HOST_OUT")) == 0);
+    c->wantHostOut = hostOut;
+    r = runDetect(c, true);
+    c->wantHostOut = false;
+    if (r != SIFT_OK) return r;
+    r = earlyKeypointCopy(c);
+    if (r != SIFT_OK) return r;
+    const int re = finish(c, true);
     if (re != SIFT_OK && re != SIFT_ERR_CAPACITY) return re;
     r = sift_batch_download(c, out);
     return r != SIFT_OK ? r : re;
@@ -793,6 +839,7 @@ int sift_detect(SiftContext* c, const void* bgra8, int32_t pitchBytes,
     const void* imgs[1] = {bgra8};
     int r = sift_batch_upload(c, imgs, 1, pitchBytes);
     if (r != SIFT_OK) return r;
+    c->wantHostOut = false;
     r = runDetect(c, false);
     if (r != SIFT_OK) return r;
     const int re = finish(c, false);
@@ -846,9 +893,13 @@ int sift_describe(SiftContext* c, const SiftKeypoint* kps, const int32_t counts[
     const int savedFrames = c->curFrames;
     c->curFrames = 1;
     c->split = false;   // caller-supplied keypoints all live in list set 0
+    c->kpsOnHost = true;   // they are the caller's (already in hKps); nothing to copy back
+    c->wantHostOut = true;
     int r = describeSet(c, 0, kOctaves, nullptr, T ? c->ev[5] : nullptr, T ? c->ev[6] : nullptr);
+    c->wantHostOut = false;
     c->described = true;
     if (r != SIFT_OK) { c->curFrames = savedFrames; return r; }
+    CTX_TRY(c, cudaEventRecord(c->evKpCopied, c->copyStream));   // finish() waits on it
     // bookkeeping without touching the detect-stage events
     const bool savedT = c->stageTiming;
     c->stageTiming = false;

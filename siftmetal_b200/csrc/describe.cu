@@ -222,14 +222,20 @@ __global__ void descSegmentStartsKernel(const int* __restrict__ segKpStart,
 constexpr int kDescCopies = 32;    // lane-private histogram copies (16 KB per warp). Sharing one copy
                                    // between lanes l and l + 16 in two half-warp rounds (8 KB, twice
                                    // the resident warps) measured equal: 472 vs 463 us at 1080p
-constexpr int kDescWarps = 2;      // 32 KB of histograms per CTA
+constexpr int kDescWarps = 7;      // 112 KB of histograms per CTA, two CTAs (14 warps) per SM
 constexpr int kDescMaxSide = 128;  // 2·radius+1; radius <= 39 for detected keypoints
 constexpr int kDescBins = 128;
-constexpr int kDescDefaultWalk = 0;
+constexpr int kDescDefaultWalk = 1;
 
 // Trilinear accumulation of one sample into the lane's histogram copy (addFeature,
 // SIFTDescriptor.metal:82-117). Two base addresses per sample (one per orientation bin); the
 // four cells are immediate offsets; loads / stores of cells outside the 4x4 grid are predicated off.
+__device__ __forceinline__ float ex2Approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 __device__ __forceinline__ void descAccumulate(char* const hl, const float2 gm, const float bx,
                                                const float by, const float r2, const bool ok,
                                                const float theta) {
@@ -239,7 +245,7 @@ __device__ __forceinline__ void descAccumulate(char* const hl, const float2 gm, 
     const float bin = turn * 8.0f;
     const int bi = (int)bin;                   // bin >= 0: truncation = floor
     const float fb = bin - (float)bi;
-    const float val = gm.y * __expf(-r2 * 0.125f);
+    const float val = gm.y * ex2Approx(r2 * (-0.125f * 1.4426950408889634f));   // exp(-r2 / 8)
     const int x0 = __float2int_rd(bx), y0 = __float2int_rd(by);   // in [-1, 3] when ok
     const float fxw = bx - (float)x0, fyw = by - (float)y0;
     // ceil = floor + 1 except on exact integers, where the reference adds a zero weight to the
@@ -256,7 +262,7 @@ __device__ __forceinline__ void descAccumulate(char* const hl, const float2 gm, 
     constexpr int DX = 8 * kDescCopies, DY = 32 * kDescCopies;      // floats to cell x+1 / y+1
     const float g0 = 1.0f - fb;
     // the eight addresses of a lane are distinct and private: load all, add, store all
-    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f, t4 = 0.f, t5 = 0.f, t6 = 0.f, t7 = 0.f;
+    float t0, t1, t2, t3, t4, t5, t6, t7;   // each read only under the predicate that loaded it
     if (c00) t0 = p0[0];
     if (c00) t1 = p1[0];
     if (c10) t2 = p0[DX];
@@ -281,7 +287,7 @@ __device__ __forceinline__ void descAccumulate(char* const hl, const float2 gm, 
 //           of 32 / C rows at a time: bounds once per row group, control flow uniform and
 //           branch-free per sample, at the price of idle lane slots at the ragged span ends.
 template <int WALK>
-__global__ void __launch_bounds__(kDescWarps * 32)
+__global__ void __launch_bounds__(256)
 descriptorKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __restrict__ kps,
                  const int* __restrict__ kpSeg, const int* __restrict__ segKpStart,
                  const Counters* __restrict__ counters, const int* __restrict__ oriOffset,
@@ -293,7 +299,8 @@ descriptorKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __r
     const int nKp = counters->nKeypoints;
     int nDesc = oriOffset[nKp];
     if (nDesc > capacity) nDesc = capacity;
-    for (int d = blockIdx.x * kDescWarps + wid; d < nDesc; d += gridDim.x * kDescWarps) {
+    const int warpsPerCta = blockDim.x >> 5;
+    for (int d = blockIdx.x * warpsPerCta + wid; d < nDesc; d += gridDim.x * warpsPerCta) {
         const int k = descKp[d];   // keypoint owning descriptor d
         const SiftKeypoint kp = kps[k];
         const int frame = kpSeg[k] / kOctaves;
@@ -385,6 +392,59 @@ descriptorKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __r
 #pragma unroll
                 for (int u = 0; u < 4; u++) descAccumulate(hl, gm[u], bxs[u], bys[u], r2s[u], ok[u], theta);
             }
+        } else if constexpr (WALK == 1) {
+            // Flattened like WALK 0, but in units of 16-byte aligned sample PAIRS (even absolute x):
+            // one LDG.128 and one row search per two samples. Rows are padded to whole pairs; the
+            // padding samples fail the exact cull (or the plane check) below.
+            int i = iMin, xs = 0, np = 0, q = lane;
+            const float2* __restrict__ grow = g;
+            auto rowBounds = [&]() {
+                const float fi = (float)i;
+                const float lo = fmaxf(fmaxf(fmaf(fi, s1, -c1), fmaf(fi, s2, -c2)), xlo);
+                const float hi = fminf(fminf(fmaf(fi, s1, c1), fmaf(fi, s2, c2)), xhi);
+                xs = (ipx + max((int)ceilf(lo - 1.0f), -ipx)) & ~1;
+                const int xe = min(ipx + (int)floorf(hi + 1.0f), o.w - 1);
+                np = max((xe - xs + 2) >> 1, 0);
+                grow = g + (size_t)(ipy + i) * o.pitch;   // dereferenced only while i <= iMax
+            };
+            auto settle = [&]() {
+                while (i <= iMax && q >= np) {
+                    q -= np;
+                    i++;
+                    rowBounds();
+                }
+            };
+            rowBounds();
+            settle();
+            constexpr int NP = 2;   // pairs per lane per iteration
+            while (__any_sync(0xffffffffu, i <= iMax)) {
+                float4 gm[NP];
+                float rxs[NP], rys[NP];
+                bool ok0[NP], ok1[NP];
+#pragma unroll
+                for (int u = 0; u < NP; u++) {
+                    const int x = xs + 2 * q;
+                    const float fj = (float)(x - ipx), fi = (float)i;
+                    const float rx = fj * a - fi * b;
+                    const float ry = fj * b + fi * a;
+                    const bool rowOk = i <= iMax;
+                    ok0[u] = rowOk && fabsf(rx) < 2.5f && fabsf(ry) < 2.5f;
+                    ok1[u] = rowOk && fabsf(rx + a) < 2.5f && fabsf(ry + b) < 2.5f && (x + 1 < o.w);
+                    gm[u] = __ldg(reinterpret_cast<const float4*>((ok0[u] || ok1[u]) ? grow + x : g));
+                    rxs[u] = rx;
+                    rys[u] = ry;
+                    q += 32;
+                    settle();
+                }
+#pragma unroll
+                for (int u = 0; u < NP; u++) {
+                    const float rx = rxs[u], ry = rys[u], rx1 = rx + a, ry1 = ry + b;
+                    descAccumulate(hl, make_float2(gm[u].x, gm[u].y), rx + 1.5f, ry + 1.5f,
+                                   rx * rx + ry * ry, ok0[u], theta);
+                    descAccumulate(hl, make_float2(gm[u].z, gm[u].w), rx1 + 1.5f, ry1 + 1.5f,
+                                   rx1 * rx1 + ry1 * ry1, ok1[u], theta);
+                }
+            }
         } else {
             constexpr int TC = WALK, TR = 32 / WALK;   // tile columns / rows
             const int lr = lane / TC, lc = lane % TC;
@@ -452,14 +512,15 @@ descriptorKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __r
         for (int q = 0; q < 4; q++)
             bytes[q * 32 + lane] = (uint8_t)(int)fminf(255.0f, __fmul_rn(f[q], 512.0f));
         __syncwarp();
-        SiftDescriptor* out = desc + d;
-        uint32_t* dst = reinterpret_cast<uint32_t*>(out->features);
-        dst[lane] = reinterpret_cast<const uint32_t*>(bytes)[lane];
-        if (lane == 0) {
+        // one contiguous 136-byte record (the result array may be pinned host memory: the stores
+        // then leave over PCIe as whole records while the kernel keeps running)
+        uint32_t* rec = reinterpret_cast<uint32_t*>(desc + d);
+        rec[2 + lane] = reinterpret_cast<const uint32_t*>(bytes)[lane];
+        if (lane < 2) {
             // index in the frame's keypoint array; kpIndexBase: keypoints of this frame that live in
             // an earlier list (octave 0 is compacted separately on single large frames)
-            out->keypoint = k - segKpStart[frame * kOctaves] + (kpIndexBase ? *kpIndexBase : 0);
-            out->theta = theta;
+            const int kIndex = k - segKpStart[frame * kOctaves] + (kpIndexBase ? *kpIndexBase : 0);
+            rec[lane] = lane == 0 ? (uint32_t)kIndex : __float_as_uint(theta);
         }
         __syncwarp();
     }
@@ -487,15 +548,19 @@ cudaError_t launchDescribe(const EngineParams& P, const SiftKeypoint* kps, const
     SIFT_CUDA_TRY(cudaGetLastError());
     if (afterOrientation) SIFT_CUDA_TRY(cudaEventRecord(afterOrientation, st));
 
-    const int smemBytes = kDescWarps * kDescBins * kDescCopies * (int)sizeof(float);
+    static const int warps = getenv("SIFTCUDA_DESC_WARPS") ? atoi(getenv("SIFTCUDA_DESC_WARPS")) : kDescWarps;
+    const int perWarp = kDescBins * kDescCopies * (int)sizeof(float);
+    const int smemBytes = warps * perWarp;
+    const int ctasPerSm = (228 * 1024) / (smemBytes + 1024);
     static const int walk = getenv("SIFTCUDA_DESC_WALK") ? atoi(getenv("SIFTCUDA_DESC_WALK")) : kDescDefaultWalk;
     auto launch = [&](auto kernel) -> cudaError_t {
         SIFT_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes));
-        kernel<<<smCount * 6, kDescWarps * 32, smemBytes, st>>>(
+        kernel<<<smCount * ctasPerSm, warps * 32, smemBytes, st>>>(
             P, kps, kpSeg, segKpStart, counters, oriOffset, oriTmp, descKp, desc, capDescriptors, kpIndexBase);
         return cudaGetLastError();
     };
     switch (walk) {
+        case 1: return launch(descriptorKernel<1>);
         case 4: return launch(descriptorKernel<4>);
         case 8: return launch(descriptorKernel<8>);
         case 16: return launch(descriptorKernel<16>);

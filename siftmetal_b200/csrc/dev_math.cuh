@@ -36,19 +36,17 @@ __device__ __forceinline__ float dm_exp2f(float x) {
     return dm_expf(__fmul_rn(x, 0.693147180559945309f));
 }
 
+// Branch-free: the two range-reduction forms share one division (selected operands), and the
+// zero case is a final select — same operations on the same values as the oracle's branches.
 __device__ __forceinline__ float dm_atan2f(float y, float x) {
-    float ax = fabsf(x), ay = fabsf(y);
-    float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-    if (mx == 0.0f) return 0.0f;
-    float a, off;
-    if (mn > __fmul_rn(mx, 0.414213562373095049f)) {
-        a = __fdiv_rn(__fsub_rn(mn, mx), __fadd_rn(mn, mx));
-        off = 0.785398163397448310f;
-    } else {
-        a = __fdiv_rn(mn, mx);
-        off = 0.0f;
-    }
-    float z = __fmul_rn(a, a);
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const bool big = mn > __fmul_rn(mx, 0.414213562373095049f);
+    const float num = big ? __fsub_rn(mn, mx) : mn;
+    const float den = big ? __fadd_rn(mn, mx) : mx;
+    const float off = big ? 0.785398163397448310f : 0.0f;
+    const float a = __fdiv_rn(num, den);
+    const float z = __fmul_rn(a, a);
     float p = 8.05374449538e-2f;
     p = __fmaf_rn(p, z, -1.38776856032e-1f);
     p = __fmaf_rn(p, z, 1.99777106478e-1f);
@@ -59,7 +57,7 @@ __device__ __forceinline__ float dm_atan2f(float y, float x) {
     if (ay > ax) r = __fsub_rn(1.57079632679489662f, r);
     if (x < 0.0f) r = __fsub_rn(3.14159265358979324f, r);
     if (y < 0.0f) r = -r;
-    return r;
+    return mx == 0.0f ? 0.0f : r;
 }
 
 __device__ __forceinline__ void dm_sincosf(float x, float* s, float* c) {
