@@ -625,26 +625,14 @@ int runDetect(SiftContext* c, bool withDescribe) {
         }
         if (o == 0) c->bandedOctave0 = banded;
         if (T && o == 0) CTX_TRY(c, cudaEventRecord(c->evBlur0[kGaussians - 1], so));
-        // (running the gradient beside blur s = 3, 4 on a side stream was measured: no gain, the
-        // stage is throughput-bound, and it blurs the per-launch timing of the blur kernel)
-        // Octave 0: the gradient field (instruction-bound) beside the extrema mask (latency-bound)
-        // on a second stream instead of ahead of it.
-        static const bool gradSide = !(getenv("SIFTCUDA_GRAD_SIDE") && atoi(getenv("SIFTCUDA_GRAD_SIDE")) == 0);
-        const bool side = gradSide && o == 0 && !(dbgSkip & 1);
-        if (side) {
-            CTX_TRY(c, cudaEventRecord(c->evBandFork, so));
-            CTX_TRY(c, cudaStreamWaitEvent(c->bandStream[1], c->evBandFork, 0));
-            CTX_TRY(c, launchGradient(q, F, c->bandStream[1]));
-            CTX_TRY(c, cudaEventRecord(c->evBandDone[1], c->bandStream[1]));
-        } else if (!(dbgSkip & 1)) {
-            CTX_TRY(c, launchGradient(q, F, so));
-        }
+        // (the gradient beside the extrema mask on a second stream, or beside blurs s = 3, 4: both
+        // measured, no gain — the stage is throughput-bound)
+        if (!(dbgSkip & 1)) CTX_TRY(c, launchGradient(q, F, so));
         c->launches++;
         if (q.w >= 3 && q.h >= 3 && !(dbgSkip & 2)) {
             CTX_TRY(c, launchExtremaMask(c->P, o, c->dMask, F, so));
             c->launches++;
         }
-        if (side) CTX_TRY(c, cudaStreamWaitEvent(so, c->evBandDone[1], 0));
         if (o > 0) CTX_TRY(c, cudaEventRecord(c->evOctDone[o], so));
         if (o == 0) {
             // Single large frame: octave 0 holds most of the keypoints and is complete long before

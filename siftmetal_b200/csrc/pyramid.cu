@@ -136,7 +136,8 @@ cudaError_t launchGrayUpsample(const uint8_t* bgra, int pitchBytes, int64_t fram
 // floats: 8 lanes on 8 consecutive rows issuing LDS.128 / STS.128 hit 8 distinct 4-bank groups,
 // so the row-per-lane X pass is conflict-free; the Y pass reads float2 columns with consecutive
 // lanes on consecutive pairs, also conflict-free.
-// (Measured alternatives — persistent CTAs with a double-buffered input, march-down strips,
+// (Measured alternatives — persistent CTAs with a double-buffered input, march-down strips, a
+// strip-streaming form with register-resident Y accumulators (profiles/experiments/),
 // 128x64 tiles — were all slower on B200; see profiles/r1/SUMMARY.md.)
 template <int NTAPS, int TX, int TY, int NT>
 struct BlurCfg {
@@ -326,253 +327,6 @@ blurKernel(const BlurArgs a, const __grid_constant__ Taps taps) {
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// Streaming form of the same blur for large planes: a CTA owns a strip of SW columns and marches
-// down a segment of rows, so the vertical halo is paid once per segment instead of once per tile
-// (L2 read amplification 1.25 instead of 2.1 at 27 taps) and no X-pass row is computed twice.
-//
-//   * input rows arrive by cp.async in chunks of C rows into a 4-deep ring (chunks k-1, k: centre
-//     pixels of the DoG; k+1: X pass; k+2: in flight);
-//   * X pass of chunk k+1 (one row, 8 consecutive outputs per task) into a double-buffered
-//     X-row buffer, in the same barrier interval as
-//   * Y pass of chunk k: a thread owns a column pair and every 4th output row (phase J, warp
-//     uniform). Each X-pass value pair is read from shared memory once and fed to the A = P/4
-//     outputs in flight in that phase — accumulators live in registers for their whole life, tap
-//     order ascending as the spec requires (X row t feeds output m with tap i = t - m). The row
-//     loop is unrolled over one period P = 4A >= NTAPS = two chunks, so every tap index is an
-//     immediate;
-//   * one __syncthreads per chunk.
-constexpr int kBlurStreamDefault = 0;
-
-template <int NTAPS>
-struct StreamCfg {
-    static constexpr int SW = 128;                 // strip width (outputs)
-    static constexpr int NT = 256;
-    static constexpr int R = NTAPS / 2;
-    static constexpr int RP = (R + 3) / 4 * 4;
-    static constexpr int A = (NTAPS + 3) / 4;      // outputs in flight per phase
-    static constexpr int P = 4 * A;                // period of the Y loop
-    static constexpr int C = P / 2;                // rows per chunk
-    static constexpr int IN_W = SW + 2 * RP;
-    static constexpr int IP = (IN_W % 8 == 4) ? IN_W : IN_W + 4;
-    static constexpr int XP = SW + 4;              // 132 = 4 * 33
-    static constexpr int NRING = 4;
-    static constexpr int SMEM_FLOATS = NRING * C * IP + 2 * C * XP;
-    static constexpr int XSEG = 8;
-    static_assert(R <= C, "centre rows live in chunks k-1, k");
-};
-
-template <int NTAPS, int J, int PARITY, bool DOG, bool HALF>
-__device__ __forceinline__ void streamYPass(const BlurArgs& a, const Taps& taps, f32x2 (&acc)[StreamCfg<NTAPS>::A],
-                                            const float* __restrict__ sX, const float* __restrict__ ringPrev,
-                                            const float* __restrict__ ringCur, int tBase, int nOut, int ys,
-                                            int gx, int cp, float* __restrict__ out, float* __restrict__ dog,
-                                            float* __restrict__ half) {
-    using S = StreamCfg<NTAPS>;
-    constexpr int R = S::R, RP = S::RP, A = S::A, P = S::P, C = S::C, IP = S::IP, XP = S::XP;
-    const bool colOk0 = gx < a.w, colOk1 = gx + 1 < a.w;
-#pragma unroll
-    for (int r = 0; r < C; r++) {
-        constexpr int dummy = 0;
-        (void)dummy;
-        const int tt = PARITY * C + r;   // t mod P
-        const float2 v = *reinterpret_cast<const float2*>(sX + r * XP + 2 * cp);
-        const f32x2 v2 = pack2(v.x, v.y);
-#pragma unroll
-        for (int s = 0; s < A; s++) {
-            const int i = (tt - 4 * s - J + 2 * P) % P;   // tap fed by this row in slot s
-            if (i < NTAPS) {
-                const f32x2 w2 = pack2(taps.w[i], taps.w[i]);
-                acc[s] = fma2(w2, v2, i == 0 ? pack2(0.0f, 0.0f) : acc[s]);
-            }
-            if (i == NTAPS - 1) {
-                const int m = tBase + r - (NTAPS - 1);     // finished output row of the segment
-                if (m >= 0 && m < nOut) {
-                    float2 o2;
-                    unpack2(acc[s], o2.x, o2.y);
-                    const int gy = ys + m;
-                    const size_t o = (size_t)gy * a.pitch + gx;
-                    float2 d2 = make_float2(0.f, 0.f);
-                    if (DOG) {
-                        // centre pixel: input row t - R, in chunk k-1 when r < R
-                        const float* crow = (r < R) ? ringPrev + (r - R + C) * IP : ringCur + (r - R) * IP;
-                        const float2 c = *reinterpret_cast<const float2*>(crow + RP + 2 * cp);
-                        d2 = make_float2(o2.x - c.x, o2.y - c.y);
-                    }
-                    if (colOk1) {
-                        *reinterpret_cast<float2*>(out + o) = o2;
-                        if (DOG) *reinterpret_cast<float2*>(dog + o) = d2;
-                    } else if (colOk0) {
-                        out[o] = o2.x;
-                        if (DOG) dog[o] = d2.x;
-                    }
-                    if (HALF && (gy & 1) == 0 && (gy >> 1) < a.halfH && colOk0 && (gx >> 1) < a.halfW)
-                        half[(size_t)(gy >> 1) * a.halfPitch + (gx >> 1)] = o2.x;   // gx is even
-                }
-            }
-        }
-    }
-}
-
-template <int NTAPS, bool DOG, bool HALF>
-__global__ void __launch_bounds__(StreamCfg<NTAPS>::NT, 3)
-blurStreamKernel(const BlurArgs a, const __grid_constant__ Taps taps, int segRows, int segsPerStrip) {
-    using S = StreamCfg<NTAPS>;
-    constexpr int R = S::R, RP = S::RP, A = S::A, C = S::C, IN_W = S::IN_W, IP = S::IP, XP = S::XP;
-    constexpr int NT = S::NT, SW = S::SW;
-    extern __shared__ __align__(16) float smem[];
-    float* const sRing = smem;                       // [NRING][C][IP]
-    float* const sX = smem + S::NRING * C * IP;      // [2][C][XP]
-
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int w = a.w, h = a.h, pitch = a.pitch;
-    const int yB = a.yBegin, yE = a.yEnd > 0 ? a.yEnd : h;
-    const int strip = blockIdx.x / segsPerStrip, seg = blockIdx.x - strip * segsPerStrip;
-    const int f = blockIdx.y;
-    const int x0 = strip * SW;
-    const int ys = yB + seg * segRows;
-    const int nOut = min(segRows, yE - ys);
-    if (nOut <= 0) return;
-    const int nChunks = (nOut + 2 * R + C - 1) / C;
-    const float* __restrict__ in = a.in + (size_t)f * a.inFrameStride;
-    float* __restrict__ out = a.out + (size_t)f * a.outFrameStride;
-    float* __restrict__ dog = DOG ? a.dog + (size_t)f * a.dogFrameStride : nullptr;
-    float* __restrict__ half = HALF ? a.half + (size_t)f * a.halfFrameStride : nullptr;
-    const bool colsInside = (x0 - RP >= 0) && (x0 + SW + RP <= w);
-
-    // chunk c = input rows ys - R + c C + [0, C) of the plane (mirrored outside), ring slot c % 4
-    auto issueLoad = [&](int c) {
-        float* dst = sRing + (c % S::NRING) * (C * IP);
-        const int row0 = ys - R + c * C;
-        if (colsInside && row0 >= 0 && row0 + C <= h) {
-            constexpr int V = IN_W / 4;
-            const float* base = in + (size_t)row0 * pitch + (x0 - RP);
-            for (int idx = tid; idx < C * V; idx += NT) {
-                const int r = idx / V, c4 = idx - r * V;
-                const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + r * IP + 4 * c4);
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(base + (size_t)r * pitch + 4 * c4));
-            }
-        } else {
-            for (int r = wid; r < C; r += NT / 32) {
-                const int gy = symmetrized(row0 + r, h);
-                const float* __restrict__ srow = in + (size_t)gy * pitch;
-                for (int cc = lane; cc < IN_W; cc += 32) {
-                    int gxx = x0 - RP + cc;
-                    if (gxx < 0) gxx = -1 - gxx;
-                    else if (gxx >= w) gxx = 2 * w - 1 - gxx;
-                    if (gxx < 0 || gxx >= w) gxx = symmetrized(x0 - RP + cc, w);
-                    const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + r * IP + cc);
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(srow + gxx));
-                }
-            }
-        }
-    };
-    // X pass of chunk c into sX[c & 1]
-    auto xPass = [&](int c) {
-        const float* src0 = sRing + (c % S::NRING) * (C * IP);
-        float* dst0 = sX + (c & 1) * (C * XP);
-        constexpr int SEGS = SW / S::XSEG;
-        constexpr int NV = (S::XSEG + 2 * RP) / 4;
-        for (int t = tid; t < C * SEGS; t += NT) {
-            const int sg = t / C, r = t - sg * C;
-            const float4* src = reinterpret_cast<const float4*>(src0 + r * IP + sg * S::XSEG);
-            float v[NV * 4];
-#pragma unroll
-            for (int k = 0; k < NV; k++) {
-                const float4 q = src[k];
-                v[4 * k + 0] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
-            }
-            float accx[S::XSEG];
-#pragma unroll
-            for (int k = 0; k < S::XSEG; k++) accx[k] = 0.0f;
-#pragma unroll
-            for (int i = 0; i < NTAPS; i++) {
-                const float wi = taps.w[i];
-#pragma unroll
-                for (int k = 0; k < S::XSEG; k++) accx[k] = fmaf(wi, v[k + (RP - R) + i], accx[k]);
-            }
-            float4* dst = reinterpret_cast<float4*>(dst0 + r * XP + sg * S::XSEG);
-            dst[0] = make_float4(accx[0], accx[1], accx[2], accx[3]);
-            dst[1] = make_float4(accx[4], accx[5], accx[6], accx[7]);
-        }
-    };
-
-    issueLoad(0);
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
-    if (nChunks > 1) issueLoad(1);
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
-    cpAsyncWaitGroup<1>();
-    __syncthreads();
-    xPass(0);
-
-    // Y-pass ownership: phase J = wid / 2 (warp uniform), column pair cp
-    const int J = wid >> 1;
-    const int cp = (wid & 1) * 32 + lane;
-    const int gx = x0 + 2 * cp;
-    f32x2 acc[A];
-#pragma unroll
-    for (int s = 0; s < A; s++) acc[s] = pack2(0.0f, 0.0f);
-
-    for (int k = 0; k < nChunks; k++) {
-        cpAsyncWaitGroup<0>();       // chunk k + 1 (issued one interval ago) has landed
-        __syncthreads();             // ... for everyone; X rows of chunk k complete; chunk k - 2 retired
-        if (k + 2 < nChunks) issueLoad(k + 2);
-        asm volatile("cp.async.commit_group;\n" ::: "memory");
-        if (k + 1 < nChunks) xPass(k + 1);
-        const float* sXk = sX + (k & 1) * (C * XP);
-        const float* ringPrev = sRing + ((k + S::NRING - 1) % S::NRING) * (C * IP);
-        const float* ringCur = sRing + (k % S::NRING) * (C * IP);
-        const int tBase = k * C;
-#define SIFT_STREAM_Y(JJ)                                                                                    \
-    if (k & 1) streamYPass<NTAPS, JJ, 1, DOG, HALF>(a, taps, acc, sXk, ringPrev, ringCur, tBase, nOut, ys,  \
-                                                    gx, cp, out, dog, half);                                  \
-    else streamYPass<NTAPS, JJ, 0, DOG, HALF>(a, taps, acc, sXk, ringPrev, ringCur, tBase, nOut, ys, gx,    \
-                                              cp, out, dog, half);
-        switch (J) {
-            case 0: SIFT_STREAM_Y(0) break;
-            case 1: SIFT_STREAM_Y(1) break;
-            case 2: SIFT_STREAM_Y(2) break;
-            default: SIFT_STREAM_Y(3) break;
-        }
-#undef SIFT_STREAM_Y
-    }
-}
-
-template <int NTAPS, bool DOG, bool HALF>
-static cudaError_t launchBlurStreamCfg(const BlurArgs& a, const Taps& taps, cudaStream_t st) {
-    using S = StreamCfg<NTAPS>;
-    static_assert(S::IN_W % 4 == 0 && S::IP % 8 == 4 && S::XP % 8 == 4, "bank layout");
-    const int smemBytes = S::SMEM_FLOATS * (int)sizeof(float);
-    auto kernel = blurStreamKernel<NTAPS, DOG, HALF>;
-    static unsigned long long configured = 0;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!((configured >> (dev & 63)) & 1ull)) {
-        SIFT_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes));
-        configured |= 1ull << (dev & 63);
-    }
-    const char* ce = getenv("SIFTCUDA_STREAM_CTAS");
-    const int ctasPerSm = ce ? std::max(1, atoi(ce)) : 3;
-    const int rows = (a.yEnd > 0 ? a.yEnd : a.h) - a.yBegin;
-    const int strips = (a.w + S::SW - 1) / S::SW;
-    // one wave of resident CTAs: segments as long as the SM count allows (the 2R-row warm-up of
-    // a segment is the only redundant work), never shorter than 64 rows
-    int segs = std::max(1, std::min((rows + 63) / 64, (148 * ctasPerSm) / std::max(1, strips * a.frames)));
-    const int segRows = (rows + segs - 1) / segs;
-    segs = (rows + segRows - 1) / segRows;
-    dim3 grid((unsigned)(strips * segs), (unsigned)a.frames);
-    kernel<<<grid, S::NT, smemBytes, st>>>(a, taps, segRows, segs);
-    return cudaGetLastError();
-}
-
-template <int NTAPS>
-static cudaError_t launchBlurStream(const BlurArgs& a, const Taps& taps, cudaStream_t st) {
-    if (a.dog && a.half) return launchBlurStreamCfg<NTAPS, true, true>(a, taps, st);
-    if (a.dog) return launchBlurStreamCfg<NTAPS, true, false>(a, taps, st);
-    if (a.half) return cudaErrorInvalidValue;
-    return launchBlurStreamCfg<NTAPS, false, false>(a, taps, st);
-}
-
 template <int NTAPS, int TX, int TY, int NT, bool DOG, bool HALF>
 static cudaError_t launchBlurCfg(const BlurArgs& a, const Taps& taps, cudaStream_t st) {
     using C = BlurCfg<NTAPS, TX, TY, NT>;
@@ -609,13 +363,6 @@ template <int NTAPS>
 static cudaError_t launchBlurT(const BlurArgs& a, const Taps& taps, cudaStream_t st) {
     const int rows = (a.yEnd > 0 ? a.yEnd : a.h) - a.yBegin;
     const long tiles64 = (long)((a.w + 63) / 64) * ((rows + 63) / 64) * a.frames;
-    // streaming strips need long row segments to amortise their warm-up rows: planes that give
-    // every resident CTA (3 per SM) at least ~100 rows of a 128-column strip
-    const char* sm = getenv("SIFTCUDA_BLUR_STREAM");
-    const int streamMode = sm ? atoi(sm) : kBlurStreamDefault;
-    const long stripCtas = (long)((a.w + 127) / 128) * a.frames;
-    if (streamMode && a.debugMode == 0 && (long)rows * stripCtas >= 100L * 3 * 148)
-        return launchBlurStream<NTAPS>(a, taps, st);
     if (tiles64 >= 2 * 148) return launchBlurFlags<NTAPS, 64, 64, 256>(a, taps, st);
     return launchBlurFlags<NTAPS, 32, 32, 128>(a, taps, st);
 }

@@ -290,34 +290,3 @@ def test_split_list_mode_matches(monkeypatch):
     for key in ("k", "d", "kc", "dc"):
         assert np.array_equal(a[key], b[key]), key
 
-
-def test_streaming_blur_matches_tiled_blur():
-    """The strip-streaming blur (large planes) and the tiled blur evaluate the same per-pixel
-    operation sequences: every Gaussian / DoG plane of a 1080p frame, the decimated seed of
-    octave 1 and the final results are bit-identical between the two kernels."""
-    import os
-    from siftmetal_b200.synth import pink_noise_bgra
-
-    img = pink_noise_bgra(1920, 1080, 11)
-    runs = []
-    saved = os.environ.get("SIFTCUDA_BLUR_STREAM")
-    try:
-        for mode in ("0", "1"):
-            os.environ["SIFTCUDA_BLUR_STREAM"] = mode
-            eng = _engine(1920, 1080)
-            res = eng.detect_and_describe([img])
-            planes = [eng.plane(_abi.PLANE_GAUSSIAN, 0, s) for s in range(6)]
-            planes += [eng.plane(_abi.PLANE_DOG, 0, s) for s in range(5)]
-            planes += [eng.plane(_abi.PLANE_GAUSSIAN, 1, s) for s in (0, 5)]
-            runs.append((planes, res))
-            eng.close()
-    finally:
-        if saved is None:
-            os.environ.pop("SIFTCUDA_BLUR_STREAM", None)
-        else:
-            os.environ["SIFTCUDA_BLUR_STREAM"] = saved
-    (pa, ra), (pb, rb) = runs
-    for i, (x, y) in enumerate(zip(pa, pb)):
-        assert np.array_equal(x, y), (i, float(np.abs(x - y).max()))
-    assert np.array_equal(ra.keypoints, rb.keypoints)
-    assert np.array_equal(ra.descriptors, rb.descriptors)
