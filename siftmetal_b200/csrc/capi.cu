@@ -83,6 +83,7 @@ struct SiftContext {
     // 136-byte records straight into the pinned result array over PCIe while it runs, and the
     // keypoints leave on a copy stream as soon as refinement has counted them — no D2H pass after
     // the last kernel.
+    bool countersClean = false;      // both sets' device counters were zeroed after the last call
     bool wantHostOut = false;        // request for the next runDetect / describe
     bool descOnHost = false;         // last describe wrote c->hDesc directly
     bool kpsOnHost = false;          // last detect's keypoints were already copied to c->hKps
@@ -502,13 +503,12 @@ int postDetect(SiftContext* c, int k, int blockBegin, int nBlocks, int nSegs, cu
     SiftContext::ListSet& L = c->L[k];
     cudaStream_t st = c->stream;
     CTX_TRY(c, launchCandidateCompaction(c->P, c->dMask, L.dBlockSums, L.dCands, c->capCand, blockBegin,
-                                         nBlocks, L.dCounters, st));
-    CTX_TRY(c, launchCandidateSegmentStarts(L.dCands, &L.dCounters->nCandidates, L.dSegStarts, nSegs, st));
-    c->launches += 4;
+                                         nBlocks, L.dSegStarts, nSegs, L.dCounters, st));
+    c->launches += 3;
     if (afterCompaction) CTX_TRY(c, cudaEventRecord(afterCompaction, st));
     CTX_TRY(c, launchRefine(c->P, L.dCands, c->capCand, L.dKpTmp, L.dFlagWords, L.dBlockSums, L.dKps, L.dKpSeg,
-                            c->capKp, nullptr, L.dSegStarts + (c->nSegs + 1), nSegs, L.dCounters, c->smCount, st));
-    c->launches += 5;
+                            c->capKp, L.dSegStarts, L.dSegStarts + (c->nSegs + 1), nSegs, L.dCounters, st));
+    c->launches += 3;
     if (afterRefine) CTX_TRY(c, cudaEventRecord(afterRefine, st));
     return SIFT_OK;
 }
@@ -523,7 +523,7 @@ int describeSet(SiftContext* c, int k, int nSegs, const int* kpIndexBase, cudaEv
                               L.dOriOffset, L.dDescKp, L.dBlockSums, c->descOnHost ? c->hDesc : L.dDesc, c->capDesc,
                               L.dSegStarts + 2 * (c->nSegs + 1), nSegs, L.dCounters, kpIndexBase, c->smCount, st,
                               afterOrientation));
-    c->launches += 6;
+    c->launches += 5;
     if (afterDescriptor) CTX_TRY(c, cudaEventRecord(afterDescriptor, st));
     return SIFT_OK;
 }
@@ -536,8 +536,11 @@ int runDetect(SiftContext* c, bool withDescribe) {
     const bool T = c->stageTiming;
     c->launches = 0;
     c->kpsOnHost = c->descOnHost = false;
-    CTX_TRY(c, cudaMemsetAsync(c->L[0].dCounters, 0, sizeof(Counters), st));
-    CTX_TRY(c, cudaMemsetAsync(c->L[1].dCounters, 0, sizeof(Counters), st));
+    if (!c->countersClean) {   // normally zeroed behind the previous call's read-back (finish)
+        CTX_TRY(c, cudaMemsetAsync(c->L[0].dCounters, 0, sizeof(Counters), st));
+        CTX_TRY(c, cudaMemsetAsync(c->L[1].dCounters, 0, sizeof(Counters), st));
+    }
+    c->countersClean = false;
     if (T) CTX_TRY(c, cudaEventRecord(c->ev[0], st));
     // DifferenceOfGaussians.encodeSeedTexture (:357-389)
     const OctaveDev& o0 = c->P.oct[0];
@@ -716,6 +719,11 @@ int finish(SiftContext* c, bool withDescribe) {
     }
     CTX_TRY(c, cudaStreamSynchronize(st));
     if (c->kpsOnHost) CTX_TRY(c, cudaEventSynchronize(c->evKpCopied));
+    // zero the counters for the next frame now, off its critical path (overflow bits accumulate by
+    // atomicOr; the counts themselves are rewritten by every scan)
+    if (cudaMemsetAsync(c->L[0].dCounters, 0, sizeof(Counters), st) == cudaSuccess &&
+        cudaMemsetAsync(c->L[1].dCounters, 0, sizeof(Counters), st) == cudaSuccess)
+        c->countersClean = true;
     const int nSegs = c->curFrames * kOctaves;
     int overflow = 0;
     for (int s = 0; s < nSegs; s++) c->candCounts[s] = c->kpCounts[s] = c->descCounts[s] = 0;

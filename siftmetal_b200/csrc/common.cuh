@@ -101,19 +101,16 @@ cudaError_t launchGradient(const OctaveDev& o, int frames, cudaStream_t st);
 // detect.cu
 cudaError_t launchExtremaMask(const EngineParams& P, int octave, uint32_t* mask, int frames,
                               cudaStream_t st);
+// mask blocks [blockBegin, blockBegin + nBlocks) → ordered candidates; segStart[nSegs + 1] receives
+// the per-(frame, octave) list offsets
 cudaError_t launchCandidateCompaction(const EngineParams& P, const uint32_t* mask,
                                       int* blockSums, Candidate* cands, int capCandidates,
-                                      int blockBegin, int nBlocks, Counters* counters,
-                                      cudaStream_t st);
-cudaError_t launchSegmentStarts(const int* kpSeg, const int* nPtr, int* segStart, int nSegs,
-                                cudaStream_t st);
-cudaError_t launchCandidateSegmentStarts(const Candidate* cands, const int* nPtr, int* segStart,
-                                         int nSegs, cudaStream_t st);
+                                      int blockBegin, int nBlocks, int* segStart, int nSegs,
+                                      Counters* counters, cudaStream_t st);
 cudaError_t launchRefine(const EngineParams& P, const Candidate* cands, int capCandidates,
                          SiftKeypoint* kpTmp, uint32_t* flagWords, int* blockSums,
-                         SiftKeypoint* kps, int* kpSeg, int capKeypoints, int* segKpCount,
-                         int* segKpStart, int nSegs, Counters* counters, int smCount,
-                         cudaStream_t st);
+                         SiftKeypoint* kps, int* kpSeg, int capKeypoints, const int* segCandStart,
+                         int* segKpStart, int nSegs, Counters* counters, cudaStream_t st);
 
 // describe.cu
 cudaError_t launchDescribe(const EngineParams& P, const SiftKeypoint* kps, const int* kpSeg,

@@ -175,11 +175,15 @@ struct OriCount {
     __device__ int operator()(int i) const { return i < counters->nKeypoints ? nOri[i] : 0; }
 };
 
-// Phase C for orientation counts: exclusive offsets per keypoint (+ one past the end).
+// Phase C for orientation counts: exclusive offsets per keypoint (+ one past the end), the owner
+// keypoint of every descriptor, and the descriptor segment starts (the first keypoint of a
+// (frame, octave) segment — kpSeg changes there — writes its offset for every segment up to its
+// own; the slot one past the end closes the rest).
 __global__ void __launch_bounds__(kScanThreads)
 oriOffsetsKernel(const int* __restrict__ nOri, const Counters* __restrict__ counters,
                  const int* __restrict__ blockOffsets, int* __restrict__ oriOffset,
-                 int* __restrict__ descKp, int capDescriptors) {
+                 int* __restrict__ descKp, int capDescriptors, const int* __restrict__ kpSeg,
+                 int* __restrict__ segDescStart, int nSegs) {
     __shared__ int sh[9];
     const int n = counters->nKeypoints;
     const int i0 = blockIdx.x * kScanChunk + threadIdx.x * kScanItemsPerThread;
@@ -192,22 +196,20 @@ oriOffsetsKernel(const int* __restrict__ nOri, const Counters* __restrict__ coun
     }
     int total;
     int pos = blockOffsets[blockIdx.x] + blockExclusiveScan256(s, sh, &total);
+    int segPrev = (i0 == 0 || i0 > n) ? -1 : kpSeg[i0 - 1];
 #pragma unroll
     for (int k = 0; k < kScanItemsPerThread; k++) {
-        if ((i0 + k) <= n) oriOffset[i0 + k] = pos;
+        const int i = i0 + k;
+        if (i <= n) {
+            oriOffset[i] = pos;
+            const int segCur = (i == n) ? nSegs : kpSeg[i];
+            for (int t = segPrev + 1; t <= segCur; t++) segDescStart[t] = pos;
+            segPrev = segCur;
+        }
         for (int t = 0; t < v[k]; t++)   // owner of each descriptor: no search in the descriptor kernel
-            if (pos + t < capDescriptors) descKp[pos + t] = i0 + k;
+            if (pos + t < capDescriptors) descKp[pos + t] = i;
         pos += v[k];
     }
-}
-
-// descriptor segment starts from keypoint segment starts
-__global__ void descSegmentStartsKernel(const int* __restrict__ segKpStart,
-                                        const int* __restrict__ oriOffset,
-                                        int* __restrict__ segDescStart, int nSegs) {
-    const int seg = blockIdx.x * blockDim.x + threadIdx.x;
-    if (seg > nSegs) return;
-    segDescStart[seg] = oriOffset[segKpStart[seg]];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -508,10 +510,7 @@ cudaError_t launchDescribe(const EngineParams& P, const SiftKeypoint* kps, const
     SIFT_CUDA_TRY(launchScanOffsets(blockSums, nBlocks, &counters->nDescriptors, capDescriptors,
                                     &counters->overflow, 4, st));
     oriOffsetsKernel<<<nBlocks, kScanThreads, 0, st>>>(nOri, counters, blockSums, oriOffset, descKp,
-                                                       capDescriptors);
-    SIFT_CUDA_TRY(cudaGetLastError());
-    descSegmentStartsKernel<<<(nSegs + 1 + 127) / 128, 128, 0, st>>>(segKpStart, oriOffset,
-                                                                   segDescStart, nSegs);
+                                                       capDescriptors, kpSeg, segDescStart, nSegs);
     SIFT_CUDA_TRY(cudaGetLastError());
     if (afterOrientation) SIFT_CUDA_TRY(cudaEventRecord(afterOrientation, st));
 

@@ -196,7 +196,7 @@ cudaError_t launchExtremaMask(const EngineParams& P, int octave, uint32_t* mask,
 // scan phase B (declared in scan.cuh)
 __global__ void __launch_bounds__(1024)
 scanOffsetsKernel(int* blockSums, int n, int* totalOut, int capacity, int* overflow,
-                  int overflowBit) {
+                  int overflowBit, const MaskSegments segs) {
     __shared__ int warpSums[33];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int ipt = (n + 1023) / 1024;
@@ -229,19 +229,31 @@ scanOffsetsKernel(int* blockSums, int n, int* totalOut, int capacity, int* overf
         blockSums[i] = run;
         run += v;
     }
+    const int total = min(warpSums[32], capacity);
     if (tid == 0) {
-        int total = warpSums[32];
-        if (total > capacity) {
-            total = capacity;
-            atomicOr(overflow, overflowBit);
-        }
+        if (warpSums[32] > capacity) atomicOr(overflow, overflowBit);
         *totalOut = total;
+    }
+    if (segs.segStart) {
+        // list segment (frame, octave) starts where its first mask block starts
+        __syncthreads();   // scanned sums of the other threads
+        for (int seg = tid; seg <= segs.nSegs; seg += 1024) {
+            int v = total;
+            if (seg < segs.nSegs) {
+                const int frame = seg / kOctaves, oc = seg - frame * kOctaves;
+                const int lb = frame * segs.blocksPerFrame + segs.octaveBlockStart[oc] - segs.blockBegin;
+                if (lb <= 0) v = 0;
+                else if (lb < n) v = min(blockSums[lb], total);
+            }
+            segs.segStart[seg] = v;
+        }
     }
 }
 
 cudaError_t launchScanOffsets(int* blockSums, int n, int* totalOut, int capacity, int* overflow,
-                              int overflowBit, cudaStream_t st) {
-    scanOffsetsKernel<<<1, 1024, 0, st>>>(blockSums, n, totalOut, capacity, overflow, overflowBit);
+                              int overflowBit, cudaStream_t st, const MaskSegments* segs) {
+    scanOffsetsKernel<<<1, 1024, 0, st>>>(blockSums, n, totalOut, capacity, overflow, overflowBit,
+                                          segs ? *segs : MaskSegments{});
     return cudaGetLastError();
 }
 
@@ -302,14 +314,20 @@ scatterCandidatesKernel(const __grid_constant__ EngineParams P, const uint32_t* 
 
 cudaError_t launchCandidateCompaction(const EngineParams& P, const uint32_t* mask,
                                       int* blockSums, Candidate* cands, int capCandidates,
-                                      int blockBegin, int nBlocks, Counters* counters,
-                                      cudaStream_t st) {
+                                      int blockBegin, int nBlocks, int* segStart, int nSegs,
+                                      Counters* counters, cudaStream_t st) {
     if (nBlocks < 1) return cudaSuccess;
     MaskPopc v{mask + (size_t)blockBegin * kScanChunk};
     scanBlockSumsKernel<<<nBlocks, kScanThreads, 0, st>>>(v, blockSums);
     SIFT_CUDA_TRY(cudaGetLastError());
+    MaskSegments ms;
+    ms.segStart = segStart;
+    ms.nSegs = nSegs;
+    ms.blocksPerFrame = P.blocksPerFrame;
+    ms.blockBegin = blockBegin;
+    for (int o = 0; o < kOctaves; o++) ms.octaveBlockStart[o] = P.oct[o].maskBlockStart;
     SIFT_CUDA_TRY(launchScanOffsets(blockSums, nBlocks, &counters->nCandidates, capCandidates,
-                                    &counters->overflow, 1, st));
+                                    &counters->overflow, 1, st, &ms));
     scatterCandidatesKernel<<<nBlocks, kScanThreads, 0, st>>>(P, mask, blockSums, cands,
                                                               capCandidates, blockBegin);
     return cudaGetLastError();
@@ -487,9 +505,24 @@ __global__ void __launch_bounds__(kRefineThreads)
 scatterKeypointsKernel(const uint32_t* __restrict__ flags, const Counters* __restrict__ counters,
                        const int* __restrict__ blockOffsets, const Candidate* __restrict__ cands,
                        const SiftKeypoint* __restrict__ kpTmp, SiftKeypoint* __restrict__ kps,
-                       int* __restrict__ kpSeg, int capacity) {
+                       int* __restrict__ kpSeg, int capacity, const int* __restrict__ candSegStart,
+                       int* __restrict__ kpSegStart, int nSegs) {
     const int n = counters->nCandidates;
     const int i = blockIdx.x * kRefineThreads + threadIdx.x;
+    // keypoint segment starts: the scanned position of each segment's first candidate (lists are
+    // sorted by segment; no search, no atomics)
+    if (i <= nSegs) {
+        const int c0 = candSegStart[i];
+        int v = counters->nKeypoints;
+        if (c0 < n) {
+            const int blk = c0 / kRefineThreads, w0 = (c0 % kRefineThreads) >> 5, bit = c0 & 31;
+            const uint32_t* __restrict__ fw = flags + blk * (kRefineThreads / 32);
+            int pos = blockOffsets[blk] + __popc(fw[w0] & ((1u << bit) - 1u));
+            for (int k = 0; k < w0; k++) pos += __popc(fw[k]);
+            v = min(pos, v);
+        }
+        kpSegStart[i] = v;
+    }
     if (blockIdx.x * kRefineThreads >= n) return;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t* __restrict__ w = flags + blockIdx.x * (kRefineThreads / 32);
@@ -503,65 +536,19 @@ scatterKeypointsKernel(const uint32_t* __restrict__ flags, const Counters* __res
     }
 }
 
-// segStart[seg] = first index whose seg >= seg (lower bound) — lists are sorted by segment, so
-// per-(frame, octave) counts are differences; no atomics.
-__global__ void segmentStartsKernel(const int* __restrict__ kpSeg, const int* __restrict__ nPtr,
-                                    int* __restrict__ segStart, int nSegs) {
-    const int seg = blockIdx.x * blockDim.x + threadIdx.x;
-    if (seg > nSegs) return;
-    const int n = *nPtr;
-    int lo = 0, hi = n;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (kpSeg[mid] < seg) lo = mid + 1;
-        else hi = mid;
-    }
-    segStart[seg] = lo;
-}
-
-__global__ void candidateSegmentStartsKernel(const Candidate* __restrict__ cands,
-                                             const int* __restrict__ nPtr,
-                                             int* __restrict__ segStart, int nSegs) {
-    const int seg = blockIdx.x * blockDim.x + threadIdx.x;
-    if (seg > nSegs) return;
-    const int n = *nPtr;
-    int lo = 0, hi = n;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (cands[mid].seg < seg) lo = mid + 1;
-        else hi = mid;
-    }
-    segStart[seg] = lo;
-}
-
-cudaError_t launchSegmentStarts(const int* kpSeg, const int* nPtr, int* segStart, int nSegs,
-                                cudaStream_t st) {
-    segmentStartsKernel<<<(nSegs + 1 + 127) / 128, 128, 0, st>>>(kpSeg, nPtr, segStart, nSegs);
-    return cudaGetLastError();
-}
-
-cudaError_t launchCandidateSegmentStarts(const Candidate* cands, const int* nPtr, int* segStart,
-                                         int nSegs, cudaStream_t st) {
-    candidateSegmentStartsKernel<<<(nSegs + 1 + 127) / 128, 128, 0, st>>>(cands, nPtr, segStart, nSegs);
-    return cudaGetLastError();
-}
-
 cudaError_t launchRefine(const EngineParams& P, const Candidate* cands, int capCandidates,
                          SiftKeypoint* kpTmp, uint32_t* flagWords, int* blockSums,
-                         SiftKeypoint* kps, int* kpSeg, int capKeypoints, int* segKpCount,
-                         int* segKpStart, int nSegs, Counters* counters, int smCount,
-                         cudaStream_t st) {
-    (void)segKpCount;
-    (void)smCount;
+                         SiftKeypoint* kps, int* kpSeg, int capKeypoints, const int* segCandStart,
+                         int* segKpStart, int nSegs, Counters* counters, cudaStream_t st) {
     const int nBlocks = (capCandidates + kRefineThreads - 1) / kRefineThreads;
     refineKernel<<<nBlocks, kRefineThreads, 0, st>>>(P, cands, counters, kpTmp, flagWords, blockSums);
     SIFT_CUDA_TRY(cudaGetLastError());
     SIFT_CUDA_TRY(launchScanOffsets(blockSums, nBlocks, &counters->nKeypoints, capKeypoints,
                                     &counters->overflow, 2, st));
     scatterKeypointsKernel<<<nBlocks, kRefineThreads, 0, st>>>(flagWords, counters, blockSums, cands,
-                                                              kpTmp, kps, kpSeg, capKeypoints);
-    SIFT_CUDA_TRY(cudaGetLastError());
-    return launchSegmentStarts(kpSeg, &counters->nKeypoints, segKpStart, nSegs, st);
+                                                              kpTmp, kps, kpSeg, capKeypoints,
+                                                              segCandStart, segKpStart, nSegs);
+    return cudaGetLastError();
 }
 
 }  // namespace sift

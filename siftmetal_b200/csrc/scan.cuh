@@ -55,7 +55,16 @@ __global__ void __launch_bounds__(kScanThreads) scanBlockSumsKernel(Value value,
 
 // Phase B: in-place exclusive scan of n block sums by a single CTA of 1024 threads;
 // *totalOut = grand total clamped to `capacity` (overflow bit set in *overflow when clamped).
+// Optional: segment starts of the compacted list straight from the scanned sums, when the items
+// are laid out segment by segment in whole blocks (the extrema mask: [frame][octave] block ranges).
+struct MaskSegments {
+    int* segStart = nullptr;      // [nSegs + 1] out; null = none
+    int nSegs = 0;
+    int blocksPerFrame = 0;
+    int blockBegin = 0;           // the scan covers global blocks [blockBegin, blockBegin + n)
+    int octaveBlockStart[kOctaves] = {};
+};
 cudaError_t launchScanOffsets(int* blockSums, int n, int* totalOut, int capacity, int* overflow,
-                              int overflowBit, cudaStream_t st);
+                              int overflowBit, cudaStream_t st, const MaskSegments* segs = nullptr);
 
 }  // namespace sift
