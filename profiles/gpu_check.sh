@@ -1,5 +1,3 @@
-# full GPU test suite + default bench line
+# full GPU test suite + A/B bench lines from profiles/ab_variants.txt
 timeout 800 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py --steps 30 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); s=d['stage_ms_per_step']; print('fps', round(d['value'],1), 'e2e', round(d['e2e']['value'],1), 'frac', round(d['roofline']['frac'],3), 'launches', d['gpu_launches'], {k: round(v,4) for k,v in s.items()})"
+bash profiles/gpu_ab.sh

@@ -83,6 +83,11 @@ struct SiftContext {
     // 136-byte records straight into the pinned result array over PCIe while it runs, and the
     // keypoints leave on a copy stream as soon as refinement has counted them — no D2H pass after
     // the last kernel.
+    // A large single frame is uploaded in two row chunks on the copy stream; the seed stage and
+    // octave 0's first row band run on chunk A while chunk B is still crossing PCIe.
+    struct SeedSplit { int grayRows = 0, upRows = 0, seedRows = 0; } upSplit;   // rows of chunk A; 0 = whole frame
+    cudaEvent_t evUp[2]{};
+    cudaEvent_t evSeedA = nullptr;
     bool countersClean = false;      // both sets' device counters were zeroed after the last call
     bool wantHostOut = false;        // request for the next runDetect / describe
     bool descOnHost = false;         // last describe wrote c->hDesc directly
@@ -167,6 +172,38 @@ cudaError_t devAlloc(SiftContext* c, T** p, size_t count) {
     return cudaSuccess;
 }
 
+// Octave 0 of a large single frame runs as independent row-band blur chains (runDetect).
+bool bandedOctave0(const SiftContext* c, int frames) {
+    const OctaveDev& q = c->P.oct[0];
+    const long tiles = (long)((q.w + 63) / 64) * ((q.h + 63) / 64) * frames;
+    const int nb = c->nBands;
+    return frames == 1 && nb > 1 && tiles >= 8L * c->smCount && q.h >= 256 * nb;
+}
+int bandBoundary(const SiftContext* c, int band) {   // first row of `band` (multiple of the tile height)
+    const OctaveDev& q = c->P.oct[0];
+    if (band >= c->nBands) return q.h;
+    return (int)(((long)q.h * band / c->nBands + 63) / 64 * 64);
+}
+
+// Rows of the input / upsampled / seed image that band 0's chain depends on: everything the
+// first upload chunk must deliver.
+SiftContext::SeedSplit seedSplitFor(const SiftContext* c, int frames) {
+    SiftContext::SeedSplit sp;
+    static const bool enabled = !(getenv("SIFTCUDA_UPLOAD_SPLIT") && atoi(getenv("SIFTCUDA_UPLOAD_SPLIT")) == 0);
+    if (!enabled || c->nBands != 2 || !bandedOctave0(c, frames)) return sp;
+    const OctaveDev& q = c->P.oct[0];
+    int sumR = 0;
+    for (int t = 0; t < kGaussians - 1; t++) sumR += c->ntaps[t] / 2;
+    const int seedRows = bandBoundary(c, 1) + sumR;
+    const int upRows = seedRows + c->seedNtaps / 2;
+    const int grayRows = (upRows - 1) / 2 + 2;
+    if (seedRows >= q.h || upRows >= q.h || grayRows >= c->cfg.height) return sp;
+    sp.grayRows = grayRows;
+    sp.upRows = upRows;
+    sp.seedRows = seedRows;
+    return sp;
+}
+
 void destroy(SiftContext* c) {
     if (!c) return;
     cudaSetDevice(c->device);
@@ -197,6 +234,9 @@ void destroy(SiftContext* c) {
         if (c->evBandDone[b]) cudaEventDestroy(c->evBandDone[b]);
     }
     if (c->evBandFork) cudaEventDestroy(c->evBandFork);
+    for (auto& e : c->evUp)
+        if (e) cudaEventDestroy(e);
+    if (c->evSeedA) cudaEventDestroy(c->evSeedA);
     if (c->evRefined) cudaEventDestroy(c->evRefined);
     if (c->evKpCopied) cudaEventDestroy(c->evKpCopied);
     if (c->copyStream) cudaStreamDestroy(c->copyStream);
@@ -409,6 +449,8 @@ int sift_create(const SiftConfig* cfg, int device, SiftContext** out) {
     A(cudaEventCreateWithFlags(&c->evBandFork, cudaEventDisableTiming));
     A(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
     A(cudaEventCreateWithFlags(&c->evRefined, cudaEventDisableTiming));
+    for (auto& evn : c->evUp) A(cudaEventCreateWithFlags(&evn, cudaEventDisableTiming));
+    A(cudaEventCreateWithFlags(&c->evSeedA, cudaEventDisableTiming));
     A(cudaEventCreateWithFlags(&c->evKpCopied, cudaEventDisableTiming));
     for (int b = 1; b < SiftContext::kMaxBands; b++) {
         A(cudaStreamCreateWithFlags(&c->bandStream[b], cudaStreamNonBlocking));
@@ -465,10 +507,23 @@ int sift_batch_upload(SiftContext* c, const void* const* images, int32_t n, int3
     CTX_TRY(c, cudaSetDevice(c->device));
     const size_t rowBytes = (size_t)c->cfg.width * 4;
     const size_t frameBytes = rowBytes * c->cfg.height;
-    for (int f = 0; f < n; f++) {
+    for (int f = 0; f < n; f++)
         if (!images[f]) return fail(c, SIFT_ERR_INVALID_ARGUMENT, "sift_batch_upload: null image");
-        CTX_TRY(c, cudaMemcpy2DAsync(c->dInput + f * frameBytes, rowBytes, images[f], pitchBytes,
-                                     rowBytes, c->cfg.height, cudaMemcpyHostToDevice, c->stream));
+    c->upSplit = seedSplitFor(c, n);
+    if (c->upSplit.grayRows > 0) {
+        // two row chunks on the copy stream, an event behind each
+        const int g = c->upSplit.grayRows;
+        const uint8_t* src = (const uint8_t*)images[0];
+        CTX_TRY(c, cudaMemcpy2DAsync(c->dInput, rowBytes, src, pitchBytes, rowBytes, g, cudaMemcpyHostToDevice,
+                                     c->copyStream));
+        CTX_TRY(c, cudaEventRecord(c->evUp[0], c->copyStream));
+        CTX_TRY(c, cudaMemcpy2DAsync(c->dInput + (size_t)g * rowBytes, rowBytes, src + (size_t)g * pitchBytes,
+                                     pitchBytes, rowBytes, c->cfg.height - g, cudaMemcpyHostToDevice, c->copyStream));
+        CTX_TRY(c, cudaEventRecord(c->evUp[1], c->copyStream));
+    } else {
+        for (int f = 0; f < n; f++)
+            CTX_TRY(c, cudaMemcpy2DAsync(c->dInput + f * frameBytes, rowBytes, images[f], pitchBytes,
+                                         rowBytes, c->cfg.height, cudaMemcpyHostToDevice, c->stream));
     }
     c->curInput = c->dInput;
     c->curPitch = (int)rowBytes;
@@ -484,6 +539,7 @@ int sift_batch_set_device_input(SiftContext* c, const void* dev, int32_t n, int3
         (n > 1 && frameStrideBytes < (int64_t)pitchBytes * c->cfg.height) || (pitchBytes & 3) ||
         (frameStrideBytes & 3) || ((uintptr_t)dev & 3))
         return fail(c, SIFT_ERR_INVALID_ARGUMENT, "sift_batch_set_device_input: bad arguments");
+    c->upSplit = SiftContext::SeedSplit{};
     c->curInput = (const uint8_t*)dev;
     c->curPitch = pitchBytes;
     c->curFrameStride = frameStrideBytes;
@@ -544,18 +600,41 @@ int runDetect(SiftContext* c, bool withDescribe) {
     if (T) CTX_TRY(c, cudaEventRecord(c->ev[0], st));
     // DifferenceOfGaussians.encodeSeedTexture (:357-389)
     const OctaveDev& o0 = c->P.oct[0];
-    CTX_TRY(c, launchGrayUpsample(c->curInput, c->curPitch, c->curFrameStride, c->dGray,
-                                  c->cfg.width, c->cfg.height, c->dScaled, o0.w, o0.h, o0.pitch,
-                                  o0.plane, F, st));
-    {
-        BlurArgs a{};
-        a.in = c->dScaled;
-        a.out = o0.G;  // octave 0 slice 0 (the reference blits seed → slice 0, :176-188)
-        a.w = o0.w; a.h = o0.h; a.pitch = o0.pitch;
-        a.inFrameStride = o0.plane;
-        a.outFrameStride = kGaussians * o0.plane;
-        a.frames = F;
-        CTX_TRY(c, launchBlur(a, c->seedTaps, c->seedNtaps, st));
+    BlurArgs seed{};
+    seed.in = c->dScaled;
+    seed.out = o0.G;  // octave 0 slice 0 (the reference blits seed → slice 0, :176-188)
+    seed.w = o0.w; seed.h = o0.h; seed.pitch = o0.pitch;
+    seed.inFrameStride = o0.plane;
+    seed.outFrameStride = kGaussians * o0.plane;
+    seed.frames = F;
+    const SiftContext::SeedSplit sp = (F == 1 && c->curInput == c->dInput) ? c->upSplit : SiftContext::SeedSplit{};
+    if (sp.grayRows > 0) {
+        // chunk A → everything band 0 of octave 0 needs, on the main stream
+        cudaStream_t sB = c->bandStream[1];
+        CTX_TRY(c, cudaStreamWaitEvent(st, c->evUp[0], 0));
+        CTX_TRY(c, launchGrayUpsample(c->curInput, c->curPitch, c->curFrameStride, c->dGray, c->cfg.width,
+                                      c->cfg.height, c->dScaled, o0.w, o0.h, o0.pitch, o0.plane, F, st, 0,
+                                      sp.grayRows, 0, sp.upRows));
+        seed.yBegin = 0; seed.yEnd = sp.seedRows;
+        CTX_TRY(c, launchBlur(seed, c->seedTaps, c->seedNtaps, st));
+        CTX_TRY(c, cudaEventRecord(c->evSeedA, st));
+        // chunk B → the rest, on band 1's stream (which continues with band 1's blur chain)
+        CTX_TRY(c, cudaStreamWaitEvent(sB, c->evUp[1], 0));
+        CTX_TRY(c, cudaStreamWaitEvent(sB, c->evSeedA, 0));
+        CTX_TRY(c, launchGrayUpsample(c->curInput, c->curPitch, c->curFrameStride, c->dGray, c->cfg.width,
+                                      c->cfg.height, c->dScaled, o0.w, o0.h, o0.pitch, o0.plane, F, sB,
+                                      sp.grayRows, c->cfg.height, sp.upRows, o0.h));
+        seed.yBegin = sp.seedRows; seed.yEnd = o0.h;
+        CTX_TRY(c, launchBlur(seed, c->seedTaps, c->seedNtaps, sB));
+        c->launches += 3;
+    } else {
+        if (c->upSplit.grayRows > 0 && c->curInput == c->dInput) {   // chunked upload, unchunked use
+            CTX_TRY(c, cudaStreamWaitEvent(st, c->evUp[1], 0));
+        }
+        CTX_TRY(c, launchGrayUpsample(c->curInput, c->curPitch, c->curFrameStride, c->dGray,
+                                      c->cfg.width, c->cfg.height, c->dScaled, o0.w, o0.h, o0.pitch,
+                                      o0.plane, F, st));
+        CTX_TRY(c, launchBlur(seed, c->seedTaps, c->seedNtaps, st));
     }
     c->launches += 2;
     if (T) CTX_TRY(c, cudaEventRecord(c->ev[1], st));
@@ -579,9 +658,8 @@ int runDetect(SiftContext* c, bool withDescribe) {
         }
         // two row bands for a plane with many tiles (octave 0 of a large single frame); batches
         // already have enough independent work per launch
-        const long tiles = (long)((q.w + 63) / 64) * ((q.h + 63) / 64) * F;
         const int nb = c->nBands;
-        const bool banded = (o == 0) && (F == 1) && nb > 1 && tiles >= 8L * c->smCount && q.h >= 256 * nb;
+        const bool banded = (o == 0) && bandedOctave0(c, F);
         if (T && o == 0) CTX_TRY(c, cudaEventRecord(c->evBlur0[0], so));
         if (banded) {
             CTX_TRY(c, cudaEventRecord(c->evBandFork, so));
@@ -590,8 +668,8 @@ int runDetect(SiftContext* c, bool withDescribe) {
         for (int band = 0; band < (banded ? nb : 1); band++) {
             cudaStream_t sb = band == 0 ? so : c->bandStream[band];
             // band rows [r0, r1), boundaries on multiples of the tile height
-            const int r0 = banded ? (int)(((long)q.h * band / nb + 63) / 64 * 64) : 0;
-            const int r1 = banded ? (band + 1 == nb ? q.h : (int)(((long)q.h * (band + 1) / nb + 63) / 64 * 64)) : q.h;
+            const int r0 = banded ? bandBoundary(c, band) : 0;
+            const int r1 = banded ? bandBoundary(c, band + 1) : q.h;
             for (int s = 0; s < kGaussians - 1; s++) {
                 if (T && o == 0 && !banded && s > 0) CTX_TRY(c, cudaEventRecord(c->evBlur0[s], sb));
                 BlurArgs a{};

@@ -80,7 +80,8 @@ struct Counters {
 cudaError_t launchGrayUpsample(const uint8_t* bgra, int pitchBytes, int64_t frameStrideBytes,
                                float* gray, int W, int H, float* scaled, int w2, int h2,
                                int pitch2, size_t scaledFrameStride, int frames,
-                               cudaStream_t st);
+                               cudaStream_t st, int grayY0 = 0, int grayY1 = 0, int upY0 = 0,
+                               int upY1 = 0);
 // out = blur(in); optional dog = out - in; optional decimated copy of out (every other pixel)
 struct BlurArgs {
     const float* in;

@@ -45,12 +45,12 @@ __device__ __forceinline__ int symmetrized(int i, int l) {
 // quotients are tabulated once per CTA in shared memory instead of 12 IEEE divisions per thread.
 __global__ void __launch_bounds__(256)
 grayKernel(const uint8_t* __restrict__ bgra, int pitchBytes, int64_t frameStrideBytes,
-           float* __restrict__ gray, int W, int H) {
+           float* __restrict__ gray, int W, int H, int yBegin) {
     __shared__ float lut[256];
     lut[threadIdx.x] = (float)threadIdx.x / 255.0f;
     __syncthreads();
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int y = blockIdx.y, f = blockIdx.z;
+    const int y = yBegin + blockIdx.y, f = blockIdx.z;
     if (x4 >= W) return;
     const uint8_t* row = bgra + (size_t)f * frameStrideBytes + (size_t)y * pitchBytes;
     float* out = gray + ((size_t)f * H + y) * W;
@@ -70,9 +70,9 @@ grayKernel(const uint8_t* __restrict__ bgra, int pitchBytes, int64_t frameStride
 // per output pixel; 4 consecutive outputs per thread.
 __global__ void __launch_bounds__(256)
 upsampleKernel(const float* __restrict__ gray, int W, int H, float* __restrict__ scaled, int w2,
-               int h2, int pitch2, size_t scaledFrameStride) {
+               int h2, int pitch2, size_t scaledFrameStride, int yBegin) {
     const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int j = blockIdx.y, f = blockIdx.z;
+    const int j = yBegin + blockIdx.y, f = blockIdx.z;
     if (i0 >= w2) return;
     const float* __restrict__ src = gray + (size_t)f * W * H;
     const float dx = (float)W / (float)w2;
@@ -109,15 +109,23 @@ upsampleKernel(const float* __restrict__ gray, int W, int H, float* __restrict__
     }
 }
 
+// Gray rows [grayY0, grayY1) and upsampled rows [upY0, upY1) (0, 0 = all): a large single frame
+// arrives in two row chunks, each converted as soon as it has landed.
 cudaError_t launchGrayUpsample(const uint8_t* bgra, int pitchBytes, int64_t frameStrideBytes,
                                float* gray, int W, int H, float* scaled, int w2, int h2,
                                int pitch2, size_t scaledFrameStride, int frames,
-                               cudaStream_t st) {
-    dim3 g1((W + 1023) / 1024, H, frames);
-    grayKernel<<<g1, 256, 0, st>>>(bgra, pitchBytes, frameStrideBytes, gray, W, H);
-    SIFT_CUDA_TRY(cudaGetLastError());
-    dim3 g2((w2 + 1023) / 1024, h2, frames);
-    upsampleKernel<<<g2, 256, 0, st>>>(gray, W, H, scaled, w2, h2, pitch2, scaledFrameStride);
+                               cudaStream_t st, int grayY0, int grayY1, int upY0, int upY1) {
+    if (grayY1 <= 0) { grayY0 = 0; grayY1 = H; }
+    if (upY1 <= 0) { upY0 = 0; upY1 = h2; }
+    if (grayY1 > grayY0) {
+        dim3 g1((W + 1023) / 1024, grayY1 - grayY0, frames);
+        grayKernel<<<g1, 256, 0, st>>>(bgra, pitchBytes, frameStrideBytes, gray, W, H, grayY0);
+        SIFT_CUDA_TRY(cudaGetLastError());
+    }
+    if (upY1 > upY0) {
+        dim3 g2((w2 + 1023) / 1024, upY1 - upY0, frames);
+        upsampleKernel<<<g2, 256, 0, st>>>(gray, W, H, scaled, w2, h2, pitch2, scaledFrameStride, upY0);
+    }
     return cudaGetLastError();
 }
 

@@ -260,6 +260,24 @@ def test_full_size_properties_1080p():
     ora = _oracle(w, h)
     okps, ocounts = ora.detect(img)
     assert np.array_equal(a.keypoint_counts[0], ocounts)
+    # ... and the full result of the fused host-buffer call (two-chunk upload, seed stage and
+    # band 0 started on the first chunk, host-resident outputs) against the oracle at full size
+    eng = _engine(w, h)
+    res = eng.detect_and_describe([img])
+    assert np.array_equal(eng.plane(_abi.PLANE_SEED), ora.plane(_abi.PLANE_SEED))
+    for s in (1, 5):
+        assert np.array_equal(eng.plane(_abi.PLANE_GAUSSIAN, 0, s), ora.plane(_abi.PLANE_GAUSSIAN, 0, s))
+    kps, desc = res.frame(0)
+    _check_frame(eng, ora, img, kps, desc, res.keypoint_counts[0], res.descriptor_counts[0],
+                 res.candidate_counts[0], planes=False)
+    # the staged path with a device-resident input (no upload chunks) gives the same arrays
+    import torch
+    dev = torch.from_numpy(img).cuda()
+    eng.set_device_input(dev.data_ptr(), 1, w * 4, w * h * 4)
+    eng.execute()
+    res2 = eng.download()
+    assert np.array_equal(res.keypoints, res2.keypoints) and np.array_equal(res.descriptors, res2.descriptors)
+    eng.close()
     assert np.array_equal(k["scaledX"], okps["scaledX"]) and np.array_equal(k["scaledY"], okps["scaledY"])
     assert np.all(np.abs(k["absoluteX"] - okps["absoluteX"]) <= POS_TOL)
 
