@@ -286,18 +286,23 @@ def main():
     wall_s = time.perf_counter() - t_wall0
 
     # ---- e2e: host buffers through the public batch call -------------------------------------------
+    e2e_stage = np.zeros(6)
+
     def step_e2e():
         nk = nd = 0
         for (s, n), pa in zip(chunks, ptr_arrays):
             k, d = eng.detect_and_describe_ptrs(pa, n, w * 4)
             nk += k
             nd += d
+            t = eng.timings()   # read after the call returned: not in anybody's critical path
+            e2e_stage[:] += np.array([t[k2 + "_ms"] for k2 in ("seed", "pyramid", "extrema", "refine", "orientation", "descriptor")])
         return nk, nd
 
     e2e_steps = 1 if args.quick else max(3, args.steps // 2)
     for _ in range(0 if args.quick else 2):
         step_e2e()
     barrier()
+    e2e_stage[:] = 0
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         nk, nd = step_e2e()
@@ -364,7 +369,10 @@ def main():
             "e2e": {"value": e2e_value, "unit": "frames/s",
                     "h2d_bytes_per_step": n_local * frame_bytes,
                     "d2h_bytes_per_step": int(nk) * 44 + int(nd) * 136 + 16 + 3 * 4 * (7 * chunk + 1),
-                    "steps": e2e_steps, "timing": "wall clock around sift_detect_and_describe_batch, pinned host frames"},
+                    "steps": e2e_steps, "timing": "wall clock around sift_detect_and_describe_batch, pinned host frames",
+                    "ms_per_step": 1000.0 * e2e_s_max / e2e_steps,
+                    "device_stage_ms_per_step": {k2: float(v) / e2e_steps for k2, v in zip(
+                        ("seed_incl_upload_wait", "pyramid", "extrema", "refine", "orientation", "descriptor"), e2e_stage)}},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }

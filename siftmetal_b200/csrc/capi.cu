@@ -756,9 +756,14 @@ int runDetect(SiftContext* c, bool withDescribe) {
         if (T) CTX_TRY(c, cudaEventRecord(c->ev[2], st));
         int r = postDetect(c, 0, 0, c->P.blocksPerFrame * F, nSegs, T ? c->ev[3] : nullptr, T ? c->ev[4] : nullptr);
         if (r != SIFT_OK) return r;
-        if (c->wantHostOut) {   // keypoint count for the early copy (earlyKeypointCopy)
-            CTX_TRY(c, cudaMemcpyAsync(c->L[0].hCounters, c->L[0].dCounters, sizeof(Counters), cudaMemcpyDeviceToHost, st));
-            CTX_TRY(c, cudaEventRecord(c->evRefined, st));
+        if (c->wantHostOut) {
+            // keypoint count for the early copy (earlyKeypointCopy), read back on the copy stream so
+            // that the main stream goes straight on to the orientation kernel
+            CTX_TRY(c, cudaEventRecord(c->evKpCopied, st));
+            CTX_TRY(c, cudaStreamWaitEvent(c->copyStream, c->evKpCopied, 0));
+            CTX_TRY(c, cudaMemcpyAsync(c->L[0].hCounters, c->L[0].dCounters, sizeof(Counters), cudaMemcpyDeviceToHost,
+                                       c->copyStream));
+            CTX_TRY(c, cudaEventRecord(c->evRefined, c->copyStream));
             c->kpsOnHost = true;
         }
         if (withDescribe) {

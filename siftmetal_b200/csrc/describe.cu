@@ -241,20 +241,18 @@ __device__ __forceinline__ float ex2Approx(float x) {
 __device__ __forceinline__ void descAccumulate(char* const hl, const float2 gm, const float bx,
                                                const float by, const float r2, const bool ok,
                                                const float theta) {
-    // orientation relative to theta, wrapped to [0, 1) turns, then 8 bins
-    float turn = (gm.x - theta) * (1.0f / kTau);
-    turn -= floorf(turn);
-    const float bin = turn * 8.0f;
-    const int bi = (int)bin;                   // bin >= 0: truncation = floor
-    const float fb = bin - (float)bi;
+    // orientation relative to theta in bins: t in (-12, 4); floor and the 3 low bits give the bin
+    const float t = (gm.x - theta) * (8.0f / kTau);
+    const int bi = __float2int_rd(t);
+    const float fb = t - (float)bi;
     const float val = gm.y * ex2Approx(r2 * (-0.125f * 1.4426950408889634f));   // exp(-r2 / 8)
     const int x0 = __float2int_rd(bx), y0 = __float2int_rd(by);   // in [-1, 3] when ok
     const float fxw = bx - (float)x0, fyw = by - (float)y0;
     // ceil = floor + 1 except on exact integers, where the reference adds a zero weight to the
-    // floor cell — same sums either way.
-    const float vx0 = val * (1.0f - fxw), vx1 = val * fxw;
-    const float v00 = vx0 * (1.0f - fyw), v01 = vx0 * fyw;
-    const float v10 = vx1 * (1.0f - fyw), v11 = vx1 * fyw;
+    // floor cell — same sums either way. Each split is one product and one difference.
+    const float vx1 = val * fxw, vx0 = val - vx1;
+    const float v01 = vx0 * fyw, v00 = vx0 - v01;
+    const float v11 = vx1 * fyw, v10 = vx1 - v11;
     const bool okx0 = ok && (x0 >= 0), okx1 = ok && (x0 < 3);
     const bool oky0 = (y0 >= 0), oky1 = (y0 < 3);
     const bool c00 = okx0 && oky0, c10 = okx1 && oky0, c01 = okx0 && oky1, c11 = okx1 && oky1;
