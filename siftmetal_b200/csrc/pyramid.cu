@@ -198,13 +198,23 @@ blurKernel(const BlurArgs a, const __grid_constant__ Taps taps) {
     for (int g = 0; g < NG; g++) {
         const int rBeg = g * GH, rEnd = min(rBeg + GH, IN_H);
         if (interior) {
+            // LPR lanes per tile row (>= the row's 16-byte vectors), whole rows per warp: row and
+            // column of a lane are fixed, the loop only adds constants to two addresses
             constexpr int V = IN_W / 4;
-            const float* base = in + (size_t)(y0 - R + rBeg) * pitch + (x0 - RP);
-            for (int idx = tid; idx < (rEnd - rBeg) * V; idx += NT) {
-                const int r = idx / V, c4 = idx - r * V;
-                const float* gp = base + (size_t)r * pitch + 4 * c4;
-                const unsigned s = (unsigned)__cvta_generic_to_shared(sIn + (rBeg + r) * IP + 4 * c4);
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gp));
+            constexpr int LPR = V > 16 ? 32 : (V > 8 ? 16 : 8);
+            constexpr int RSTEP = (NT / 32) * (32 / LPR);      // rows per CTA iteration
+            const int lane = tid & 31, wid = tid >> 5;
+            const int c4 = lane % LPR;
+            const int r0 = rBeg + wid * (32 / LPR) + lane / LPR;
+            if (c4 < V) {
+                const float* gp = in + (size_t)(y0 - R + r0) * pitch + (x0 - RP) + 4 * c4;
+                unsigned sa = (unsigned)__cvta_generic_to_shared(sIn + r0 * IP + 4 * c4);
+                const size_t gstep = (size_t)RSTEP * pitch;
+                for (int r = r0; r < rEnd; r += RSTEP) {
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gp));
+                    gp += gstep;
+                    sa += RSTEP * IP * 4;
+                }
             }
         } else {
             // edge tile: mirror boundary. One warp per row (row index reflected once per warp),
@@ -309,28 +319,47 @@ blurKernel(const BlurArgs a, const __grid_constant__ Taps taps) {
         }
         const bool full = (x0 + TX <= w) && (y0 + TY <= yE);   // CTA-uniform
         const bool noStore = (a.debugMode & 2) != 0;
+        const int gy0 = y0 + yb * RY;
+        const float* cptr = sIn + (yb * RY + R) * IP + RP + 2 * cg;   // centre pixels of the DoG
+        if (full && !noStore) {
+            // interior tile: two running row pointers, no per-row index arithmetic or guards
+            float* po = out + (size_t)gy0 * pitch + gx;
+            float* pd = DOG ? dog + (size_t)gy0 * pitch + gx : nullptr;
 #pragma unroll
-        for (int q = 0; q < RY; q++) {
-            float2 r;
-            unpack2(acc2[q], r.x, r.y);
-            const int gy = y0 + yb * RY + q;
-            const size_t o = (size_t)gy * pitch + gx;
-            float2 d2 = make_float2(0.f, 0.f);
-            if (DOG) {
-                const float2 c = *reinterpret_cast<const float2*>(sIn + (yb * RY + q + R) * IP + RP + 2 * cg);
-                d2 = make_float2(r.x - c.x, r.y - c.y);
+            for (int q = 0; q < RY; q++) {
+                float2 r;
+                unpack2(acc2[q], r.x, r.y);
+                *reinterpret_cast<float2*>(po) = r;
+                if (DOG) {
+                    const float2 c = *reinterpret_cast<const float2*>(cptr + q * IP);
+                    *reinterpret_cast<float2*>(pd) = make_float2(r.x - c.x, r.y - c.y);
+                    pd += pitch;
+                }
+                if (HALF && ((gy0 + q) & 1) == 0 && ((gy0 + q) >> 1) < a.halfH && (gx >> 1) < a.halfW)
+                    half[(size_t)((gy0 + q) >> 1) * a.halfPitch + (gx >> 1)] = r.x;   // gx is even
+                po += pitch;
             }
-            if (noStore) {
-                if (r.x == 1.2345e30f) out[o] = d2.x;   // keeps the computation alive
-            } else if (full) {
-                *reinterpret_cast<float2*>(out + o) = r;
-                if (DOG) *reinterpret_cast<float2*>(dog + o) = d2;
-            } else if (gy < yE) {
-                if (gx < w) { out[o] = r.x; if (DOG) dog[o] = d2.x; }
-                if (gx + 1 < w) { out[o + 1] = r.y; if (DOG) dog[o + 1] = d2.y; }
+        } else {
+#pragma unroll
+            for (int q = 0; q < RY; q++) {
+                float2 r;
+                unpack2(acc2[q], r.x, r.y);
+                const int gy = gy0 + q;
+                const size_t o = (size_t)gy * pitch + gx;
+                float2 d2 = make_float2(0.f, 0.f);
+                if (DOG) {
+                    const float2 c = *reinterpret_cast<const float2*>(cptr + q * IP);
+                    d2 = make_float2(r.x - c.x, r.y - c.y);
+                }
+                if (noStore) {
+                    if (r.x == 1.2345e30f) out[o] = d2.x;   // keeps the computation alive
+                } else if (gy < yE) {
+                    if (gx < w) { out[o] = r.x; if (DOG) dog[o] = d2.x; }
+                    if (gx + 1 < w) { out[o + 1] = r.y; if (DOG) dog[o + 1] = d2.y; }
+                }
+                if (HALF && (gy & 1) == 0 && (gy >> 1) < a.halfH && gy < yE && (gx >> 1) < a.halfW && gx < w)
+                    half[(size_t)(gy >> 1) * a.halfPitch + (gx >> 1)] = r.x;   // gx is even
             }
-            if (HALF && (gy & 1) == 0 && (gy >> 1) < a.halfH && gy < yE && (gx >> 1) < a.halfW && gx < w)
-                half[(size_t)(gy >> 1) * a.halfPitch + (gx >> 1)] = r.x;   // gx is even
         }
     }
 }
