@@ -1,0 +1,2 @@
+SIFTCUDA_DESC_WALK=2 timeout 800 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+bash profiles/gpu_ab.sh 2>&1 | grep -v "e2e ms"
