@@ -13,6 +13,8 @@
 // order, so they differ from the oracle in the last bits; every quantity that drives a
 // *discontinuous* decision (bin index, window radius, sample coordinate, border filter) is
 // evaluated with the spec's exact operation sequence.
+#include <algorithm>
+
 #include "common.cuh"
 #include "dev_math.cuh"
 #include "scan.cuh"
@@ -20,6 +22,20 @@
 namespace sift {
 
 constexpr float kTau = 6.28318530717958647692f;  // 2 * M_PI_F in float
+
+// Small-integer <-> float conversions on the FMA / ALU pipes (the F2I / I2F instructions run on
+// the quarter-rate XU pipe with ~4x the latency). Exact for |v| < 2^22.
+constexpr float kMagic = 12582912.0f;          // 1.5 * 2^23: ulp 1, so a directed-rounding add is floor / ceil
+constexpr int kMagicBits = 0x4B400000;
+__device__ __forceinline__ int floorToInt(float v, float& fl) {
+    const float t = __fadd_rd(v, kMagic);
+    fl = t - kMagic;
+    return __float_as_int(t) - kMagicBits;
+}
+__device__ __forceinline__ int ceilToInt(float v) { return __float_as_int(__fadd_ru(v, kMagic)) - kMagicBits; }
+__device__ __forceinline__ int floorToInt(float v) { return __float_as_int(__fadd_rd(v, kMagic)) - kMagicBits; }
+__device__ __forceinline__ float smallIntToFloat(int v) { return __int_as_float(kMagicBits + v) - kMagic; }
+
 
 // ------------------------------------------------------------------------------------------
 constexpr int kOriWarps = 8;      // warps (keypoints in flight) per CTA
@@ -85,7 +101,7 @@ orientationKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __
                 const int idx = base + u * 32 + lane;
                 ok[u] = false;
                 if (idx < nSamples) {
-                    const int jj = (int)(((float)idx + 0.5f) * invSide);
+                    const int jj = floorToInt((smallIntToFloat(idx) + 0.5f) * invSide);
                     const int ii = idx - jj * side;
                     const int sx = x + ii - r, sy = y + jj - r;
                     if (sx >= 0 && sx < o.w && sy >= 0 && sy < o.h) {
@@ -103,10 +119,13 @@ orientationKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __
                     // sits within 1e-4 of a rounding boundary (k + 0.5) is the exact sequence
                     // (IEEE divide, multiply, round-half-away) evaluated — same result always.
                     const float est = gm[u].x * ((float)kOriBins / kTau);
-                    float rb = rintf(est);
-                    if (fabsf(fabsf(est - rb) - 0.5f) < 1e-4f)
+                    const float tr = __fadd_rn(est, kMagic);      // round to nearest even = rintf
+                    float rb = tr - kMagic;
+                    int bin = __float_as_int(tr) - kMagicBits;
+                    if (fabsf(fabsf(est - rb) - 0.5f) < 1e-4f) {
                         rb = roundf(__fmul_rn(__fdiv_rn(gm[u].x, kTau), (float)kOriBins));
-                    int bin = (int)rb;
+                        bin = (int)rb;
+                    }
                     if (bin < 0) bin += kOriBins;
                     if (bin >= kOriBins) bin -= kOriBins;
                     hist[bin * 32 + lane] += wgt[u] * gm[u].y;
@@ -243,11 +262,12 @@ __device__ __forceinline__ void descAccumulate(char* const hl, const float2 gm, 
                                                const float theta) {
     // orientation relative to theta in bins: t in (-12, 4); floor and the 3 low bits give the bin
     const float t = (gm.x - theta) * (8.0f / kTau);
-    const int bi = __float2int_rd(t);
-    const float fb = t - (float)bi;
+    float tfl, bxfl, byfl;
+    const int bi = floorToInt(t, tfl);
+    const float fb = t - tfl;
     const float val = gm.y * ex2Approx(r2 * (-0.125f * 1.4426950408889634f));   // exp(-r2 / 8)
-    const int x0 = __float2int_rd(bx), y0 = __float2int_rd(by);   // in [-1, 3] when ok
-    const float fxw = bx - (float)x0, fyw = by - (float)y0;
+    const int x0 = floorToInt(bx, bxfl), y0 = floorToInt(by, byfl);   // in [-1, 3] when ok
+    const float fxw = bx - bxfl, fyw = by - byfl;
     // ceil = floor + 1 except on exact integers, where the reference adds a zero weight to the
     // floor cell — same sums either way. Each split is one product and one difference.
     const float vx1 = val * fxw, vx0 = val - vx1;
@@ -287,7 +307,7 @@ __device__ __forceinline__ void descAccumulate(char* const hl, const float2 gm, 
 // uniform control flow, but idle lane slots at the ragged span ends pay the full accumulation
 // cost: 0.60 / 0.63 / 0.74 ms against 0.46 ms for WALK 0 at the time.)
 template <int WALK>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kDescWarps * 32, 2)
 descriptorKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __restrict__ kps,
                  const int* __restrict__ kpSeg, const int* __restrict__ segKpStart,
                  const Counters* __restrict__ counters, const int* __restrict__ oriOffset,
@@ -397,45 +417,51 @@ descriptorKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __r
             // one LDG.128 and one row search per two samples. Rows are padded to whole pairs; the
             // padding samples fail the exact cull (or the plane check) below.
             int i = iMin, xs = 0, np = 0, q = lane;
-            const float2* __restrict__ grow = g;
+            float fi = smallIntToFloat(iMin);
+            const float2* __restrict__ grow = g + (size_t)(ipy + iMin) * o.pitch;
+            const int xLast = o.w - 1;
             auto rowBounds = [&]() {
-                const float fi = (float)i;
                 const float lo = fmaxf(fmaxf(fmaf(fi, s1, -c1), fmaf(fi, s2, -c2)), xlo);
                 const float hi = fminf(fminf(fmaf(fi, s1, c1), fmaf(fi, s2, c2)), xhi);
-                xs = (ipx + max((int)ceilf(lo - 1.0f), -ipx)) & ~1;
-                const int xe = min(ipx + (int)floorf(hi + 1.0f), o.w - 1);
+                xs = (ipx + max(ceilToInt(lo - 1.0f), -ipx)) & ~1;
+                const int xe = min(ipx + floorToInt(hi + 1.0f), xLast);
                 np = max((xe - xs + 2) >> 1, 0);
-                grow = g + (size_t)(ipy + i) * o.pitch;   // dereferenced only while i <= iMax
             };
             auto settle = [&]() {
                 while (i <= iMax && q >= np) {
                     q -= np;
                     i++;
+                    fi += 1.0f;
+                    grow += o.pitch;   // dereferenced only while i <= iMax
                     rowBounds();
                 }
             };
             rowBounds();
             settle();
-            constexpr int NP = 2;   // pairs per lane per iteration
-            while (__any_sync(0xffffffffu, i <= iMax)) {
-                float4 gm[NP];
-                float rxs[NP], rys[NP];
-                bool ok0[NP], ok1[NP];
+            constexpr int NP = 2;   // pairs per lane per batch
+            // One batch = coordinates + gathers of NP pairs per lane, then their accumulation.
+            auto fetch = [&](float4 (&gm)[NP], float (&rxs)[NP], float (&rys)[NP], bool (&ok0)[NP],
+                             bool (&ok1)[NP]) -> bool {
+                const bool any = __any_sync(0xffffffffu, i <= iMax);
 #pragma unroll
                 for (int u = 0; u < NP; u++) {
                     const int x = xs + 2 * q;
-                    const float fj = (float)(x - ipx), fi = (float)i;
+                    const float fj = smallIntToFloat(x - ipx);
                     const float rx = fj * a - fi * b;
                     const float ry = fj * b + fi * a;
                     const bool rowOk = i <= iMax;
                     ok0[u] = rowOk && fabsf(rx) < 2.5f && fabsf(ry) < 2.5f;
-                    ok1[u] = rowOk && fabsf(rx + a) < 2.5f && fabsf(ry + b) < 2.5f && (x + 1 < o.w);
+                    ok1[u] = rowOk && fabsf(rx + a) < 2.5f && fabsf(ry + b) < 2.5f && (x < xLast);
                     gm[u] = __ldg(reinterpret_cast<const float4*>((ok0[u] || ok1[u]) ? grow + x : g));
                     rxs[u] = rx;
                     rys[u] = ry;
                     q += 32;
                     settle();
                 }
+                return any;
+            };
+            auto accumulate = [&](const float4 (&gm)[NP], const float (&rxs)[NP], const float (&rys)[NP],
+                                  const bool (&ok0)[NP], const bool (&ok1)[NP]) {
 #pragma unroll
                 for (int u = 0; u < NP; u++) {
                     const float rx = rxs[u], ry = rys[u], rx1 = rx + a, ry1 = ry + b;
@@ -444,7 +470,13 @@ descriptorKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __r
                     descAccumulate(hl, make_float2(gm[u].z, gm[u].w), rx1 + 1.5f, ry1 + 1.5f,
                                    rx1 * rx1 + ry1 * ry1, ok1[u], theta);
                 }
-            }
+            };
+            // (issuing the gathers of batch n + 1 ahead of the accumulation of batch n, with two
+            // register sets, was measured: no change — the gather latency is already covered)
+            float4 gm[NP];
+            float rxs[NP], rys[NP];
+            bool ok0[NP], ok1[NP];
+            while (fetch(gm, rxs, rys, ok0, ok1)) accumulate(gm, rxs, rys, ok0, ok1);
         }
         __syncwarp();
         // reduce lane-private copies: lane owns bins lane, lane+32, lane+64, lane+96
@@ -512,7 +544,9 @@ cudaError_t launchDescribe(const EngineParams& P, const SiftKeypoint* kps, const
     SIFT_CUDA_TRY(cudaGetLastError());
     if (afterOrientation) SIFT_CUDA_TRY(cudaEventRecord(afterOrientation, st));
 
-    static const int warps = getenv("SIFTCUDA_DESC_WARPS") ? atoi(getenv("SIFTCUDA_DESC_WARPS")) : kDescWarps;
+    static const int warps = getenv("SIFTCUDA_DESC_WARPS")
+                                 ? std::max(1, std::min(atoi(getenv("SIFTCUDA_DESC_WARPS")), kDescWarps))
+                                 : kDescWarps;
     const int perWarp = kDescBins * kDescCopies * (int)sizeof(float);
     const int smemBytes = warps * perWarp;
     const int ctasPerSm = (228 * 1024) / (smemBytes + 1024);

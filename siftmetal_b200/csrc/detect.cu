@@ -40,15 +40,21 @@ struct RowRaw {
     float c[kDogs], e[kDogs];
 };
 
-__device__ __forceinline__ RowRaw loadRowRaw(const float* __restrict__ D, size_t plane, size_t rowOff,
-                                             int x, int ex) {
+// pc[t] points at the lane's pixel of slice t in the row to load; dx = -1 / 0 / +1 floats to the
+// edge pixel. Afterwards the pointers move one row down unless that row is the plane's last
+// (rows past the end are never consumed, the pointers just stay inside the plane).
+__device__ __forceinline__ RowRaw loadRowAdvance(const float* (&pc)[kDogs], int dx, int& row, int hLast,
+                                                 int pitch) {
     RowRaw r;
 #pragma unroll
     for (int t = 0; t < kDogs; t++) {
-        const float* __restrict__ row = D + (size_t)t * plane + rowOff;
-        r.c[t] = __ldg(row + x);
-        r.e[t] = __ldg(row + ex);
+        r.c[t] = __ldg(pc[t]);
+        r.e[t] = __ldg(pc[t] + dx);
     }
+    const int step = row < hLast ? pitch : 0;
+    row++;
+#pragma unroll
+    for (int t = 0; t < kDogs; t++) pc[t] += step;
     return r;
 }
 
@@ -84,10 +90,19 @@ extremaMaskKernel(const OctaveDev o, float softThreshold, uint32_t* __restrict__
     const bool xInside = (x >= 1) && (x <= o.w - 2);
 
     RowPart win[kDogs][3];  // [slice][row slot]; slots rotate statically (loop unrolled by 3)
-    auto rowOffset = [&](int y) { return (size_t)min(y, o.h - 1) * o.pitch; };
+    // running addresses: five slice pointers one row ahead of the last load, three mask indices
+    const int hLast = o.h - 1;
+    const int dx = ex - x;
+    int row = min(yFirst - 1, hLast);
+    const float* pc[kDogs];
+#pragma unroll
+    for (int t = 0; t < kDogs; t++) pc[t] = D + (size_t)t * o.plane + (size_t)row * o.pitch + x;
+    uint32_t* mp[kScales];
+#pragma unroll
+    for (int sc = 0; sc < kScales; sc++) mp[sc] = m + ((size_t)sc * o.h + yFirst) * o.maskRowWords + xw;
     {
-        const RowRaw r0 = loadRowRaw(D, o.plane, rowOffset(yFirst - 1), x, ex);
-        const RowRaw r1 = loadRowRaw(D, o.plane, rowOffset(yFirst), x, ex);
+        const RowRaw r0 = loadRowAdvance(pc, dx, row, hLast, o.pitch);
+        const RowRaw r1 = loadRowAdvance(pc, dx, row, hLast, o.pitch);
 #pragma unroll
         for (int t = 0; t < kDogs; t++) {
             win[t][0] = makeRowPart(r0.c[t], r0.e[t], lane);
@@ -95,8 +110,8 @@ extremaMaskKernel(const OctaveDev o, float softThreshold, uint32_t* __restrict__
         }
     }
     // software pipeline, two rows ahead: 20 independent loads in flight per lane
-    RowRaw ahead0 = loadRowRaw(D, o.plane, rowOffset(yFirst + 1), x, ex);
-    RowRaw ahead1 = loadRowRaw(D, o.plane, rowOffset(yFirst + 2), x, ex);
+    RowRaw ahead0 = loadRowAdvance(pc, dx, row, hLast, o.pitch);
+    RowRaw ahead1 = loadRowAdvance(pc, dx, row, hLast, o.pitch);
     for (int r0 = 0; r0 < rowsPerWarp; r0 += 3) {
 #pragma unroll
         for (int k = 0; k < 3; k++) {
@@ -105,7 +120,7 @@ extremaMaskKernel(const OctaveDev o, float softThreshold, uint32_t* __restrict__
             if (y > o.h - 2) return;  // warp-uniform
             const RowRaw now = ahead0;
             ahead0 = ahead1;
-            ahead1 = loadRowRaw(D, o.plane, rowOffset(y + 3), x, ex);      // consumed two rows later
+            ahead1 = loadRowAdvance(pc, dx, row, hLast, o.pitch);      // row y + 3, consumed two rows later
 #pragma unroll
             for (int t = 0; t < kDogs; t++) win[t][next] = makeRowPart(now.c[t], now.e[t], lane);
 #pragma unroll
@@ -119,7 +134,8 @@ extremaMaskKernel(const OctaveDev o, float softThreshold, uint32_t* __restrict__
                 mx = fmaxf(mx, fmaxf(fmaxf(win[s - 1][prev].crx, win[s - 1][cur].h3x), win[s - 1][next].h3x));
                 const bool cand = xInside && !(fabsf(v) <= softThreshold) && ((v < mn) || (v > mx));
                 const uint32_t word = __ballot_sync(0xffffffffu, cand);
-                if (lane == 0) m[((size_t)(s - 1) * o.h + y) * o.maskRowWords + xw] = word;
+                if (lane == 0) *mp[s - 1] = word;
+                mp[s - 1] += o.maskRowWords;
             }
         }
     }

@@ -421,44 +421,57 @@ cudaError_t launchBlur(const BlurArgs& a, const Taps& taps, int ntaps, cudaStrea
 // loads of the three rows, two float4 stores of (orientation, magnitude) pairs. The mirror
 // boundary of symmetrizedCoordinates reduces to a clamp for offsets of one pixel.
 __global__ void __launch_bounds__(256) gradientKernel(const OctaveDev o) {
+    // 4 pixels x 2 rows per thread: rows y - 1 .. y + 2 are loaded once for both output rows
     const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int y = blockIdx.y;
+    const int y = blockIdx.y * 2;
     const int s = blockIdx.z % kScales;   // 0..2 → Gaussian slice s + 1
     const int f = blockIdx.z / kScales;
     if (x0 >= o.w) return;
     const float* __restrict__ g = o.G + ((size_t)f * kGaussians + (s + 1)) * o.plane;
-    const int py = (y + 1 < o.h) ? y + 1 : o.h - 1;   // symmetrized(h) = h - 1
-    const int my = (y - 1 >= 0) ? y - 1 : 0;          // symmetrized(-1) = 0
-    const float* __restrict__ rc = g + (size_t)y * o.pitch;
+    const int hLast = o.h - 1;
+    // symmetrized(-1) = 0, symmetrized(h) = h - 1: the mirror reduces to a clamp for one pixel
+    const int yr[4] = {max(y - 1, 0), y, min(y + 1, hLast), min(y + 2, hLast)};
     // rows are padded to a multiple of 32 floats, so the float4 reads stay inside the row
-    const float4 c4 = __ldg(reinterpret_cast<const float4*>(rc + x0));
-    const float4 p4 = __ldg(reinterpret_cast<const float4*>(g + (size_t)py * o.pitch + x0));
-    const float4 m4 = __ldg(reinterpret_cast<const float4*>(g + (size_t)my * o.pitch + x0));
-    const float c[4] = {c4.x, c4.y, c4.z, c4.w};
-    const float dn[4] = {p4.x, p4.y, p4.z, p4.w};
-    const float up[4] = {m4.x, m4.y, m4.z, m4.w};
-    const float left = __ldg(rc + (x0 > 0 ? x0 - 1 : 0));
-    const float right = __ldg(rc + (x0 + 4 < o.w ? x0 + 4 : o.w - 1));
-    float r[8];
+    float4 r4[4];
+    float lf[2], rt[2];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int x = x0 + k;
-        const float cmx = (k == 0) ? left : c[k - 1];
-        float cpx = (k == 3) ? right : c[k + 1];
-        if (x + 1 >= o.w) cpx = c[k];              // symmetrized(w) = w - 1 (this pixel)
-        const float tx = (cpx - cmx) * 0.5f;
-        const float ty = (dn[k] - up[k]) * 0.5f;
-        r[2 * k] = dm_atan2f(tx, ty);
-        r[2 * k + 1] = sqrtf((tx * tx) + (ty * ty));
+    for (int k = 0; k < 4; k++) r4[k] = __ldg(reinterpret_cast<const float4*>(g + (size_t)yr[k] * o.pitch + x0));
+    const int xl = x0 > 0 ? x0 - 1 : 0, xr = x0 + 4 < o.w ? x0 + 4 : o.w - 1;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        lf[k] = __ldg(g + (size_t)yr[1 + k] * o.pitch + xl);
+        rt[k] = __ldg(g + (size_t)yr[1 + k] * o.pitch + xr);
     }
-    float2* dst = o.grad + ((size_t)f * kScales + s) * o.plane + (size_t)y * o.pitch + x0;
-    float4* d4 = reinterpret_cast<float4*>(dst);
-    d4[0] = make_float4(r[0], r[1], r[2], r[3]);
-    d4[1] = make_float4(r[4], r[5], r[6], r[7]);
+    const float v[4][4] = {{r4[0].x, r4[0].y, r4[0].z, r4[0].w}, {r4[1].x, r4[1].y, r4[1].z, r4[1].w},
+                           {r4[2].x, r4[2].y, r4[2].z, r4[2].w}, {r4[3].x, r4[3].y, r4[3].z, r4[3].w}};
+#pragma unroll
+    for (int row = 0; row < 2; row++) {
+        if (y + row > hLast) break;
+        const float* c = v[1 + row];
+        const float* up = v[row];
+        // the row below output row y + row; at the bottom edge the clamp makes it the row itself
+        const float* dn = v[2 + row];
+        float r[8];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int x = x0 + k;
+            const float cmx = (k == 0) ? lf[row] : c[k - 1];
+            float cpx = (k == 3) ? rt[row] : c[k + 1];
+            if (x + 1 >= o.w) cpx = c[k];              // symmetrized(w) = w - 1 (this pixel)
+            const float tx = (cpx - cmx) * 0.5f;
+            const float ty = (dn[k] - up[k]) * 0.5f;
+            r[2 * k] = dm_atan2f(tx, ty);
+            r[2 * k + 1] = sqrtf((tx * tx) + (ty * ty));
+        }
+        float2* dst = o.grad + ((size_t)f * kScales + s) * o.plane + (size_t)(y + row) * o.pitch + x0;
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        d4[0] = make_float4(r[0], r[1], r[2], r[3]);
+        d4[1] = make_float4(r[4], r[5], r[6], r[7]);
+    }
 }
 
 cudaError_t launchGradient(const OctaveDev& o, int frames, cudaStream_t st) {
-    dim3 grid((o.w + 1023) / 1024, o.h, kScales * frames);
+    dim3 grid((o.w + 1023) / 1024, (o.h + 1) / 2, kScales * frames);
     gradientKernel<<<grid, 256, 0, st>>>(o);
     return cudaGetLastError();
 }
