@@ -968,9 +968,8 @@ int sift_describe(SiftContext* c, const SiftKeypoint* kps, const int32_t counts[
     }
     for (int s = kOctaves; s <= c->nSegs; s++) kpStart[s] = k;
     cudaStream_t st = c->stream;
+    memset(c->L[0].hCounters, 0, sizeof(Counters));   // incl. the kernels' work-queue counters
     c->L[0].hCounters->nKeypoints = (int)n;
-    c->L[0].hCounters->nDescriptors = 0;
-    c->L[0].hCounters->overflow = 0;
     CTX_TRY(c, cudaMemcpyAsync(c->L[0].dCounters, c->L[0].hCounters, sizeof(Counters), cudaMemcpyHostToDevice, st));
     if (n > 0) {
         CTX_TRY(c, cudaMemcpyAsync(c->L[0].dKps, c->hKps, (size_t)n * sizeof(SiftKeypoint), cudaMemcpyHostToDevice, st));

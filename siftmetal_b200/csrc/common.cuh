@@ -66,6 +66,8 @@ struct Counters {
     int nKeypoints;
     int nDescriptors;
     int overflow;  // bit 0 candidates, bit 1 keypoints, bit 2 descriptors
+    int oriNext;   // work queues of the orientation / descriptor kernels: warps take their first
+    int descNext;  // item by position and every further one from these counters (zero per call)
 };
 
 #define SIFT_CUDA_TRY(expr)                                  \

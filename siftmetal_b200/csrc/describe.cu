@@ -43,16 +43,25 @@ constexpr int kOriMaxSide = 96;   // window side 2r+1; r = ceil(4.5 sigma') <= 1
 
 __global__ void __launch_bounds__(kOriWarps * 32)
 orientationKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __restrict__ kps,
-                  const int* __restrict__ kpSeg, const Counters* __restrict__ counters,
+                  const int* __restrict__ kpSeg, Counters* __restrict__ counters,
                   int* __restrict__ nOri, float* __restrict__ oriTmp) {
-    __shared__ float sHist[kOriWarps][kOriBins * 32];  // [bin][lane] per warp
-    __shared__ float sH[kOriWarps][2][kOriBins];
+    __shared__ __align__(16) float sHist[kOriWarps][kOriBins * 32];  // [bin][lane] per warp
+    __shared__ float sH[kOriWarps][kOriBins];
     __shared__ float sW[kOriWarps][kOriMaxSide];       // separable Gaussian window weights
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int n = counters->nKeypoints;
     float* hist = sHist[wid];
     float* wt = sW[wid];
-    for (int k = blockIdx.x * kOriWarps + wid; k < n; k += gridDim.x * kOriWarps) {
+    // Keypoints differ 2-3x in window size: warps pull their next keypoint from a queue counter
+    // (requested before the current one is processed, consumed after) instead of a fixed stride,
+    // so no warp is left finishing a long tail alone. Results are indexed by k: order-free.
+    const int gridWarps = gridDim.x * kOriWarps;
+    int kNext = 0;
+    // The queue runs from the end of the list: within an octave the list ascends in scale, i.e. in
+    // window area, so the cheapest items (octave 0, scale 1) come last and the tail stays short.
+    for (int t = blockIdx.x * kOriWarps + wid; t < n; t = __shfl_sync(0xffffffffu, kNext, 0)) {
+        if (lane == 0) kNext = gridWarps + atomicAdd(&counters->oriNext, 1);
+        const int k = n - 1 - t;
         const SiftKeypoint kp = kps[k];
         const int frame = kpSeg[k] / kOctaves;
         const OctaveDev& o = P.oct[kp.octave];
@@ -133,26 +142,45 @@ orientationKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __
             }
         }
         __syncwarp();
-        // reduce the 32 lane-private copies of each bin, rotated start → conflict-free
-        float* h0 = sH[wid][0];
-        float* h1 = sH[wid][1];
-        for (int b = lane; b < kOriBins; b += 32) {
-            float s = 0.0f;
-#pragma unroll 8
-            for (int l = 0; l < 32; l++) s += hist[b * 32 + ((l + lane) & 31)];
-            h0[b] = s;
+        // reduce the 32 lane-private copies of each bin: 8 lanes per bin, each sums 4 consecutive
+        // copies from one LDS.128 (8 lanes x 16 B = one conflict-free 128-byte row), then three
+        // butterfly steps; lane group bg handles bins bg, bg + 4, ...
+        float* h0 = sH[wid];
+        {
+            const int sub = lane & 7, bg = lane >> 3;
+#pragma unroll
+            for (int j = 0; j < kOriBins / 4; j++) {
+                const int b = bg + 4 * j;
+                const float4 v = *reinterpret_cast<const float4*>(hist + b * 32 + sub * 4);
+                float sum = (v.x + v.y) + (v.z + v.w);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+                if (sub == 0) h0[b] = sum;
+            }
         }
         __syncwarp();
-        // smoothHistogram (:67-85)
-        for (int it = 0; it < P.oriSmoothIterations; it++) {
-            for (int b = lane; b < kOriBins; b += 32) {
-                const float a = h0[(b - 1 + kOriBins) % kOriBins];
-                const float c = h0[b];
-                const float d = h0[(b + 1) % kOriBins];
-                h1[b] = __fdiv_rn(__fadd_rn(__fadd_rn(a, c), d), 3.0f);
+        // smoothHistogram (:67-85): circular box filter, iterated. The 36 bins live in registers
+        // (lane l: bin l, and bin 32 + l for l < 4); neighbours come by shuffle, the four wrap
+        // positions by broadcast. Same (a + c) + d, IEEE / 3 per bin as the spec.
+        {
+            float lo = h0[lane];
+            float hi = lane < kOriBins - 32 ? h0[32 + lane] : 0.0f;
+            for (int it = 0; it < P.oriSmoothIterations; it++) {
+                float pl = __shfl_up_sync(0xffffffffu, lo, 1), nl = __shfl_down_sync(0xffffffffu, lo, 1);
+                float ph = __shfl_up_sync(0xffffffffu, hi, 1), nh = __shfl_down_sync(0xffffffffu, hi, 1);
+                const float b35 = __shfl_sync(0xffffffffu, hi, kOriBins - 33), b32 = __shfl_sync(0xffffffffu, hi, 0);
+                const float b31 = __shfl_sync(0xffffffffu, lo, 31), b0 = __shfl_sync(0xffffffffu, lo, 0);
+                if (lane == 0) { pl = b35; ph = b31; }
+                if (lane == 31) nl = b32;
+                if (lane == kOriBins - 33) nh = b0;
+                lo = __fdiv_rn(__fadd_rn(__fadd_rn(pl, lo), nl), 3.0f);
+                hi = __fdiv_rn(__fadd_rn(__fadd_rn(ph, hi), nh), 3.0f);
             }
             __syncwarp();
-            float* tswap = h0; h0 = h1; h1 = tswap;
+            h0[lane] = lo;
+            if (lane < kOriBins - 32) h0[32 + lane] = hi;
+            __syncwarp();
         }
         // getPrincipalOrientations (:31-64)
         float mx = fmaxf(h0[lane], lane < kOriBins - 32 ? h0[32 + lane] : -2147483648.0f);
@@ -310,7 +338,7 @@ template <int WALK>
 __global__ void __launch_bounds__(kDescWarps * 32, 2)
 descriptorKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __restrict__ kps,
                  const int* __restrict__ kpSeg, const int* __restrict__ segKpStart,
-                 const Counters* __restrict__ counters, const int* __restrict__ oriOffset,
+                 Counters* __restrict__ counters, const int* __restrict__ oriOffset,
                  const float* __restrict__ oriTmp, const int* __restrict__ descKp,
                  SiftDescriptor* __restrict__ desc, int capacity, const int* __restrict__ kpIndexBase) {
     extern __shared__ __align__(16) float sDesc[];  // [warp][128 bins][32 copies]
@@ -320,7 +348,12 @@ descriptorKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __r
     int nDesc = oriOffset[nKp];
     if (nDesc > capacity) nDesc = capacity;
     const int warpsPerCta = blockDim.x >> 5;
-    for (int d = blockIdx.x * warpsPerCta + wid; d < nDesc; d += gridDim.x * warpsPerCta) {
+    // dynamic work queue, as in the orientation kernel (descriptor windows differ up to 4x in area)
+    const int gridWarps = gridDim.x * warpsPerCta;
+    int dNext = 0;
+    for (int t = blockIdx.x * warpsPerCta + wid; t < nDesc; t = __shfl_sync(0xffffffffu, dNext, 0)) {
+        if (lane == 0) dNext = gridWarps + atomicAdd(&counters->descNext, 1);
+        const int d = nDesc - 1 - t;   // from the end: largest windows first (see orientationKernel)
         const int k = descKp[d];   // keypoint owning descriptor d
         const SiftKeypoint kp = kps[k];
         const int frame = kpSeg[k] / kOctaves;
