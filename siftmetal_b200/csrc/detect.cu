@@ -109,9 +109,11 @@ extremaMaskKernel(const OctaveDev o, float softThreshold, uint32_t* __restrict__
             win[t][1] = makeRowPart(r1.c[t], r1.e[t], lane);
         }
     }
-    // software pipeline, two rows ahead: 20 independent loads in flight per lane
+    // software pipeline, three rows ahead: 30 independent loads in flight per lane (the kernel is
+    // bound by memory latency at 16 resident warps per SM, not by issue slots)
     RowRaw ahead0 = loadRowAdvance(pc, dx, row, hLast, o.pitch);
     RowRaw ahead1 = loadRowAdvance(pc, dx, row, hLast, o.pitch);
+    RowRaw ahead2 = loadRowAdvance(pc, dx, row, hLast, o.pitch);
     for (int r0 = 0; r0 < rowsPerWarp; r0 += 3) {
 #pragma unroll
         for (int k = 0; k < 3; k++) {
@@ -120,7 +122,8 @@ extremaMaskKernel(const OctaveDev o, float softThreshold, uint32_t* __restrict__
             if (y > o.h - 2) return;  // warp-uniform
             const RowRaw now = ahead0;
             ahead0 = ahead1;
-            ahead1 = loadRowAdvance(pc, dx, row, hLast, o.pitch);      // row y + 3, consumed two rows later
+            ahead1 = ahead2;
+            ahead2 = loadRowAdvance(pc, dx, row, hLast, o.pitch);      // row y + 4, consumed three rows later
 #pragma unroll
             for (int t = 0; t < kDogs; t++) win[t][next] = makeRowPart(now.c[t], now.e[t], lane);
 #pragma unroll
