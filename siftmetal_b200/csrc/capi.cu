@@ -693,6 +693,9 @@ int runDetect(SiftContext* c, bool withDescribe) {
                     a.halfFrameStride = kGaussians * nx.plane;
                 }
                 a.frames = F;
+                // small planes: scale s + 1 launches under scale s (programmatic dependent launch)
+                static const int pdlMaxTiles = getenv("SIFTCUDA_PDL_TILES") ? atoi(getenv("SIFTCUDA_PDL_TILES")) : 160;
+                a.pdl = (s > 0 && !banded && (long)((q.w + 31) / 32) * ((q.h + 31) / 32) * F <= pdlMaxTiles) ? 1 : 0;
                 CTX_TRY(c, launchBlur(a, c->taps[s], c->ntaps[s], sb));
                 c->launches++;
                 if (s + 1 == kScales) CTX_TRY(c, cudaEventRecord(band == 0 ? c->evSeeded[o] : c->evBandSeeded[band], sb));

@@ -97,6 +97,8 @@ struct BlurArgs {
     int frames;
     int yBegin, yEnd;  // output rows [yBegin, yEnd) of the plane (0, 0 = all rows): row bands
     int debugMode;   // 0 normal; 1 skip the X/Y FMA loops; 2 skip the stores; 3 both (tuning only)
+    int pdl;         // 1: programmatic dependent launch behind the previous kernel of the stream
+                     //    (small planes: the launch latency of scale s + 1 overlaps scale s)
 };
 cudaError_t launchBlur(const BlurArgs& a, const Taps& taps, int ntaps, cudaStream_t st);
 cudaError_t launchGradient(const OctaveDev& o, int frames, cudaStream_t st);
