@@ -70,6 +70,33 @@ struct Counters {
     int descNext;  // item by position and every further one from these counters (zero per call)
 };
 
+// Programmatic dependent launch (PDL). A kernel launched through pdlLaunch() may become resident
+// while the previous kernel of its stream is still running; pdlPrologue() at its very top lets
+// its own successor start launching and then blocks until that previous kernel has completed
+// and flushed. Both instructions are no-ops in a kernel launched the ordinary way. Used for the
+// chains of small kernels (list compaction, small-plane blurs) whose cost is launch latency.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdlPrologue() {
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
+}
+template <class... KArgs, class... Args>
+inline cudaError_t pdlLaunch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                             bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 #define SIFT_CUDA_TRY(expr)                                  \
     do {                                                     \
         cudaError_t _e = (expr);                             \

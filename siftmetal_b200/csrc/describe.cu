@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(kOriWarps * 32)
 orientationKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __restrict__ kps,
                   const int* __restrict__ kpSeg, Counters* __restrict__ counters,
                   int* __restrict__ nOri, float* __restrict__ oriTmp) {
+    pdlPrologue();
     __shared__ __align__(16) float sHist[kOriWarps][kOriBins * 32];  // [bin][lane] per warp
     __shared__ float sH[kOriWarps][kOriBins];
     __shared__ float sW[kOriWarps][kOriMaxSide];       // separable Gaussian window weights
@@ -231,6 +232,7 @@ oriOffsetsKernel(const int* __restrict__ nOri, const Counters* __restrict__ coun
                  const int* __restrict__ blockOffsets, int* __restrict__ oriOffset,
                  int* __restrict__ descKp, int capDescriptors, const int* __restrict__ kpSeg,
                  int* __restrict__ segDescStart, int nSegs) {
+    pdlPrologue();
     __shared__ int sh[9];
     const int n = counters->nKeypoints;
     const int i0 = blockIdx.x * kScanChunk + threadIdx.x * kScanItemsPerThread;
@@ -341,6 +343,7 @@ descriptorKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __r
                  Counters* __restrict__ counters, const int* __restrict__ oriOffset,
                  const float* __restrict__ oriTmp, const int* __restrict__ descKp,
                  SiftDescriptor* __restrict__ desc, int capacity, const int* __restrict__ kpIndexBase) {
+    pdlPrologue();
     extern __shared__ __align__(16) float sDesc[];  // [warp][128 bins][32 copies]
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     float* hist = sDesc + wid * (kDescBins * kDescCopies);
@@ -564,17 +567,17 @@ cudaError_t launchDescribe(const EngineParams& P, const SiftKeypoint* kps, const
                            int capDescriptors, int* segDescStart, int nSegs, Counters* counters,
                            const int* kpIndexBase, int smCount, cudaStream_t st,
                            cudaEvent_t afterOrientation) {
-    orientationKernel<<<smCount * 4, kOriWarps * 32, 0, st>>>(P, kps, kpSeg, counters, nOri, oriTmp);
-    SIFT_CUDA_TRY(cudaGetLastError());
+    SIFT_CUDA_TRY(pdlLaunch(orientationKernel, dim3(smCount * 4), dim3(kOriWarps * 32), 0, st, true, P, kps, kpSeg,
+                            counters, nOri, oriTmp));
     const int nBlocks = (capKeypoints + 1 + kScanChunk - 1) / kScanChunk;
     OriCount v{nOri, counters};
-    scanBlockSumsKernel<<<nBlocks, kScanThreads, 0, st>>>(v, blockSums);
-    SIFT_CUDA_TRY(cudaGetLastError());
+    SIFT_CUDA_TRY(pdlLaunch(scanBlockSumsKernel<OriCount>, dim3(nBlocks), dim3(kScanThreads), 0, st, true, v,
+                            blockSums));
     SIFT_CUDA_TRY(launchScanOffsets(blockSums, nBlocks, &counters->nDescriptors, capDescriptors,
                                     &counters->overflow, 4, st));
-    oriOffsetsKernel<<<nBlocks, kScanThreads, 0, st>>>(nOri, counters, blockSums, oriOffset, descKp,
-                                                       capDescriptors, kpSeg, segDescStart, nSegs);
-    SIFT_CUDA_TRY(cudaGetLastError());
+    SIFT_CUDA_TRY(pdlLaunch(oriOffsetsKernel, dim3(nBlocks), dim3(kScanThreads), 0, st, true, (const int*)nOri,
+                            (const Counters*)counters, (const int*)blockSums, oriOffset, descKp, capDescriptors,
+                            kpSeg, segDescStart, nSegs));
     if (afterOrientation) SIFT_CUDA_TRY(cudaEventRecord(afterOrientation, st));
 
     static const int warps = getenv("SIFTCUDA_DESC_WARPS")
@@ -586,9 +589,9 @@ cudaError_t launchDescribe(const EngineParams& P, const SiftKeypoint* kps, const
     static const int walk = getenv("SIFTCUDA_DESC_WALK") ? atoi(getenv("SIFTCUDA_DESC_WALK")) : kDescDefaultWalk;
     auto launch = [&](auto kernel) -> cudaError_t {
         SIFT_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes));
-        kernel<<<smCount * ctasPerSm, warps * 32, smemBytes, st>>>(
-            P, kps, kpSeg, segKpStart, counters, oriOffset, oriTmp, descKp, desc, capDescriptors, kpIndexBase);
-        return cudaGetLastError();
+        return pdlLaunch(kernel, dim3(smCount * ctasPerSm), dim3(warps * 32), (size_t)smemBytes, st, true, P, kps,
+                         kpSeg, segKpStart, counters, (const int*)oriOffset, (const float*)oriTmp,
+                         (const int*)descKp, desc, capDescriptors, kpIndexBase);
     };
     switch (walk) {
         case 1: return launch(descriptorKernel<1>);

@@ -216,6 +216,7 @@ cudaError_t launchExtremaMask(const EngineParams& P, int octave, uint32_t* mask,
 __global__ void __launch_bounds__(1024)
 scanOffsetsKernel(int* blockSums, int n, int* totalOut, int capacity, int* overflow,
                   int overflowBit, const MaskSegments segs) {
+    pdlPrologue();
     __shared__ int warpSums[33];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int ipt = (n + 1023) / 1024;
@@ -271,9 +272,8 @@ scanOffsetsKernel(int* blockSums, int n, int* totalOut, int capacity, int* overf
 
 cudaError_t launchScanOffsets(int* blockSums, int n, int* totalOut, int capacity, int* overflow,
                               int overflowBit, cudaStream_t st, const MaskSegments* segs) {
-    scanOffsetsKernel<<<1, 1024, 0, st>>>(blockSums, n, totalOut, capacity, overflow, overflowBit,
-                                          segs ? *segs : MaskSegments{});
-    return cudaGetLastError();
+    return pdlLaunch(scanOffsetsKernel, dim3(1), dim3(1024), 0, st, true, blockSums, n, totalOut, capacity,
+                     overflow, overflowBit, segs ? *segs : MaskSegments{});
 }
 
 struct MaskPopc {
@@ -286,6 +286,7 @@ __global__ void __launch_bounds__(kScanThreads)
 scatterCandidatesKernel(const __grid_constant__ EngineParams P, const uint32_t* __restrict__ mask,
                         const int* __restrict__ blockOffsets, Candidate* __restrict__ cands,
                         int capacity, int blockBegin) {
+    pdlPrologue();
     __shared__ int sh[9];
     const int b = blockBegin + blockIdx.x;   // global mask block; blockOffsets is indexed locally
     const int frame = b / P.blocksPerFrame;
@@ -347,9 +348,8 @@ cudaError_t launchCandidateCompaction(const EngineParams& P, const uint32_t* mas
     for (int o = 0; o < kOctaves; o++) ms.octaveBlockStart[o] = P.oct[o].maskBlockStart;
     SIFT_CUDA_TRY(launchScanOffsets(blockSums, nBlocks, &counters->nCandidates, capCandidates,
                                     &counters->overflow, 1, st, &ms));
-    scatterCandidatesKernel<<<nBlocks, kScanThreads, 0, st>>>(P, mask, blockSums, cands,
-                                                              capCandidates, blockBegin);
-    return cudaGetLastError();
+    return pdlLaunch(scatterCandidatesKernel, dim3(nBlocks), dim3(kScanThreads), 0, st, true, P, mask,
+                     (const int*)blockSums, cands, capCandidates, blockBegin);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -446,6 +446,7 @@ __global__ void __launch_bounds__(kRefineThreads)
 refineKernel(const __grid_constant__ EngineParams P, const Candidate* __restrict__ cands,
              const Counters* __restrict__ counters, SiftKeypoint* __restrict__ kpTmp,
              uint32_t* __restrict__ flagWords, int* __restrict__ blockSums) {
+    pdlPrologue();
     __shared__ int warpCount[kRefineThreads / 32];
     const int n = counters->nCandidates;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -526,6 +527,7 @@ scatterKeypointsKernel(const uint32_t* __restrict__ flags, const Counters* __res
                        const SiftKeypoint* __restrict__ kpTmp, SiftKeypoint* __restrict__ kps,
                        int* __restrict__ kpSeg, int capacity, const int* __restrict__ candSegStart,
                        int* __restrict__ kpSegStart, int nSegs) {
+    pdlPrologue();
     const int n = counters->nCandidates;
     const int i = blockIdx.x * kRefineThreads + threadIdx.x;
     // keypoint segment starts: the scanned position of each segment's first candidate (lists are
@@ -560,14 +562,13 @@ cudaError_t launchRefine(const EngineParams& P, const Candidate* cands, int capC
                          SiftKeypoint* kps, int* kpSeg, int capKeypoints, const int* segCandStart,
                          int* segKpStart, int nSegs, Counters* counters, cudaStream_t st) {
     const int nBlocks = (capCandidates + kRefineThreads - 1) / kRefineThreads;
-    refineKernel<<<nBlocks, kRefineThreads, 0, st>>>(P, cands, counters, kpTmp, flagWords, blockSums);
-    SIFT_CUDA_TRY(cudaGetLastError());
+    SIFT_CUDA_TRY(pdlLaunch(refineKernel, dim3(nBlocks), dim3(kRefineThreads), 0, st, true, P, cands,
+                            (const Counters*)counters, kpTmp, flagWords, blockSums));
     SIFT_CUDA_TRY(launchScanOffsets(blockSums, nBlocks, &counters->nKeypoints, capKeypoints,
                                     &counters->overflow, 2, st));
-    scatterKeypointsKernel<<<nBlocks, kRefineThreads, 0, st>>>(flagWords, counters, blockSums, cands,
-                                                              kpTmp, kps, kpSeg, capKeypoints,
-                                                              segCandStart, segKpStart, nSegs);
-    return cudaGetLastError();
+    return pdlLaunch(scatterKeypointsKernel, dim3(nBlocks), dim3(kRefineThreads), 0, st, true,
+                     (const uint32_t*)flagWords, (const Counters*)counters, (const int*)blockSums, cands,
+                     (const SiftKeypoint*)kpTmp, kps, kpSeg, capKeypoints, segCandStart, segKpStart, nSegs);
 }
 
 }  // namespace sift

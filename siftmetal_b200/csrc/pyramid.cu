@@ -177,10 +177,7 @@ blurKernel(const BlurArgs a, const __grid_constant__ Taps taps) {
     float* const sIn = smem;
     float* const sTmp = smem + IN_H * IP;
 
-    // Programmatic dependent launch: let the next kernel of the stream start launching now, and do
-    // not touch memory before the previous one has completed (both are no-ops for normal launches).
-    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
-    asm volatile("griddepcontrol.wait;\n" ::: "memory");
+    pdlPrologue();   // small planes are launched behind their predecessor (a.pdl)
     const int tid = threadIdx.x;
     const int w = a.w, h = a.h, pitch = a.pitch;
     // output rows [yB, yE): the whole plane, or one row band of it (bands of one plane run as
@@ -385,19 +382,9 @@ static cudaError_t launchBlurCfg(const BlurArgs& a, const Taps& taps, cudaStream
     const int rows = (a.yEnd > 0 ? a.yEnd : a.h) - a.yBegin;
     const long nTiles = (long)((a.w + TX - 1) / TX) * ((rows + TY - 1) / TY) * a.frames;
     if (nTiles > 2147483647L || rows < 1) return cudaErrorInvalidValue;
-    if (a.pdl) {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)nTiles);
-        cfg.blockDim = dim3(NT);
-        cfg.dynamicSmemBytes = (size_t)smemBytes;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, blurKernel<NTAPS, TX, TY, NT, DOG, HALF>, a, taps);
-    }
+    if (a.pdl)
+        return pdlLaunch(blurKernel<NTAPS, TX, TY, NT, DOG, HALF>, dim3((unsigned)nTiles), dim3(NT), (size_t)smemBytes,
+                         st, true, a, taps);
     blurKernel<NTAPS, TX, TY, NT, DOG, HALF><<<(unsigned)nTiles, NT, smemBytes, st>>>(a, taps);
     return cudaGetLastError();
 }

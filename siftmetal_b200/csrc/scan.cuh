@@ -43,6 +43,7 @@ __device__ __forceinline__ int blockExclusiveScan256(int v, int* sh, int* total)
 // int operator()(int i) that already returns 0 beyond the live range.
 template <class Value>
 __global__ void __launch_bounds__(kScanThreads) scanBlockSumsKernel(Value value, int* blockSums) {
+    pdlPrologue();
     __shared__ int sh[9];
     const int base = blockIdx.x * kScanChunk + threadIdx.x * kScanItemsPerThread;
     int s = 0;
