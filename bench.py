@@ -11,8 +11,10 @@ Default workload = BASELINE.json configs[1]: a single 1920×1080 frame per step 
 
   value      frames/s with the input already resident in HBM (device time, CUDA events recorded by
              the library on its own stream, summed over the K steps; max over ranks)
-  e2e        frames/s through the C-ABI call with HOST (pinned) buffers: H2D of the frames and
-             D2H of keypoints + descriptors inside the timed region
+  e2e        frames/s through the C-ABI call with HOST (pinned) buffers: H2D of the frames and the
+             arrival of keypoints + descriptors in host memory inside the timed region (the library
+             uploads a large frame in two chunks, copies the keypoints out while the descriptor
+             kernel runs and lets that kernel store its records straight into pinned memory)
   roofline   the dominant kernel (octave-0 Gaussian blur + DoG, 5 scales per step):
              algorithmic bytes (12 B per octave-0 pixel per scale: read G[s], write G[s+1],
              write DoG[s]) ÷ its mean time per scale from CUDA events, against the measured HBM peak
@@ -361,14 +363,14 @@ def main():
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture
                 # in profiles/r1/SUMMARY.md (mean of the 5 octave-0 launches, 1080p, cold cache; part
                 # of the 66 MB written per launch is still in the 126 MB L2 when the kernel ends)
-                "traffic": 48.6e6 * (n_local / len(chunks)) if (w, h) == (1920, 1080) else None,
+                "traffic": 47.8e6 * (n_local / len(chunks)) if (w, h) == (1920, 1080) else None,
                 "peak_source": peak_src,
                 "bytes_per_launch": bytes_per_launch, "avg_launch_ms": blur_avg_s * 1000,
                 "per_tap_launch_ms": [float(x) / (K * len(chunks)) for x in blur_ms],
             },
             "e2e": {"value": e2e_value, "unit": "frames/s",
                     "h2d_bytes_per_step": n_local * frame_bytes,
-                    "d2h_bytes_per_step": int(nk) * 44 + int(nd) * 136 + 16 + 3 * 4 * (7 * chunk + 1),
+                    "d2h_bytes_per_step": int(nk) * 44 + int(nd) * 136 + 24 + 3 * 4 * (7 * chunk + 1),
                     "steps": e2e_steps, "timing": "wall clock around sift_detect_and_describe_batch, pinned host frames",
                     "ms_per_step": 1000.0 * e2e_s_max / e2e_steps,
                     "device_stage_ms_per_step": {k2: float(v) / e2e_steps for k2, v in zip(
