@@ -393,8 +393,11 @@ descriptorKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __r
         // px, py are multiples of 1/delta and small, so the float sums of the spec are exact
         const int ipx = (int)floorf(px), ipy = (int)floorf(py);
         const float xlo = fmaxf(-(float)radius, (float)(-ipx)), xhi = fminf((float)radius, (float)(o.w - 1 - ipx));
-        const int iMin = max(-radius, -ipy);
-        const int iMax = min(radius, o.h - 1 - ipy);
+        // window rows that can meet the rotated square: |i| <= 2.5 hw (|sin| + |cos|) (+ 1 of slack);
+        // the window itself is +-radius = 2.5 sqrt(2) hw, so up to 30 % of its rows are empty
+        const int iExt = (int)(2.5f * hw * (fabsf(sinT) + fabsf(cosT))) + 2;
+        const int iMin = max(max(-radius, -iExt), -ipy);
+        const int iMax = min(min(radius, iExt), o.h - 1 - ipy);
 
 #pragma unroll 8
         for (int bb = 0; bb < 128 * kDescCopies / 32; bb++) hist[bb * 32 + lane] = 0.0f;
