@@ -195,8 +195,8 @@ SiftContext::SeedSplit seedSplitFor(const SiftContext* c, int frames) {
     int sumR = 0;
     for (int t = 0; t < kGaussians - 1; t++) sumR += c->ntaps[t] / 2;
     const int seedRows = bandBoundary(c, 1) + sumR;
-    const int upRows = seedRows + c->seedNtaps / 2;
-    const int grayRows = (upRows - 1) / 2 + 2;
+    const int upRows = (seedRows + c->seedNtaps / 2 + 1) & ~1;   // even: whole gray rows (fused gray + upsample)
+    const int grayRows = upRows / 2 + 1;                         // input rows 0 .. upRows / 2
     if (seedRows >= q.h || upRows >= q.h || grayRows >= c->cfg.height) return sp;
     sp.grayRows = grayRows;
     sp.upRows = upRows;

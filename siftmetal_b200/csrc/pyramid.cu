@@ -109,6 +109,74 @@ upsampleKernel(const float* __restrict__ gray, int W, int H, float* __restrict__
     }
 }
 
+// Gray conversion + exact 2x upsample in one pass (w2 = 2W, h2 = 2H: the only ratio the pipeline
+// uses). A thread owns gray pixels (2n, 2n + 1) of row m: it converts the 3 x 2 BGRA patch
+// (columns 2n .. 2n + 2, rows m, m + 1, mirrored at the edges), writes its two gray pixels and
+// the 4 x 2 block of upsampled pixels (columns 4n .. 4n + 3, rows 2m, 2m + 1) that depend on
+// nothing else — the same expressions as grayKernel / upsampleKernel with fx, fy in {0, 0.5},
+// 0.75 BGRA loads per output pixel instead of a gray plane round trip and 4 gathers.
+__global__ void __launch_bounds__(256)
+grayUpsample2xKernel(const uint8_t* __restrict__ bgra, int pitchBytes, int64_t frameStrideBytes,
+                     float* __restrict__ gray, int W, int H, float* __restrict__ scaled, int pitch2,
+                     size_t scaledFrameStride, int mBegin) {
+    __shared__ float lut[256];
+    lut[threadIdx.x] = (float)threadIdx.x / 255.0f;
+    __syncthreads();
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = mBegin + blockIdx.y, f = blockIdx.z;
+    const int c0 = 2 * n;
+    if (c0 >= W) return;
+    const int w2 = 2 * W;
+    const int c1 = min(c0 + 1, W - 1);
+    int c2 = c0 + 2;
+    if (c2 >= W) c2 = 2 * W - 1 - c2;      // ip = im + 1 mirrored (upsampleKernel)
+    c2 = max(c2, 0);
+    int mp = m + 1;
+    if (mp >= H) mp = 2 * H - 1 - mp;
+    const uint8_t* img = bgra + (size_t)f * frameStrideBytes;
+    float g[2][3];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const uint8_t* row = img + (size_t)(r == 0 ? m : mp) * pitchBytes;
+        const int cols[3] = {c0, c1, c2};
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const uchar4 p = *reinterpret_cast<const uchar4*>(row + 4 * cols[k]);  // b, g, r, a
+            const float bb = lut[p.x], gg = lut[p.y], rr = lut[p.z];
+            g[r][k] = ((0.0f + (0.212639005871510f * rr)) + (0.715168678767756f * gg)) +
+                      (0.072192315360734f * bb);
+        }
+    }
+    float* grow = gray + ((size_t)f * H + m) * W;
+    grow[c0] = g[0][0];
+    if (c0 + 1 < W) grow[c0 + 1] = g[0][1];
+    // output column 4n + k: im = 2n + (k >> 1), ip = im + 1, fx = (k & 1) / 2
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const float fy = r ? 0.5f : 0.0f;
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int im = k >> 1, ip = im + 1;    // indices into g[][]: columns c0, c1, c2
+            const float fx = (k & 1) ? 0.5f : 0.0f;
+            // c0 = src[jp][ip], c1 = src[jm][ip], c2 = src[jp][im], c3 = src[jm][im]; jm = m, jp = mp
+            // when the output column pair belongs to gray column c1 = W - 1 clamped (odd W edge) the
+            // values are unused (guarded below)
+            const float a = (fy * g[1][ip]) + ((1 - fy) * g[0][ip]);
+            const float b = (fy * g[1][im]) + ((1 - fy) * g[0][im]);
+            o[k] = (fx * a) + ((1 - fx) * b);
+        }
+        float* dst = scaled + (size_t)f * scaledFrameStride + (size_t)(2 * m + r) * pitch2 + 4 * n;
+        if (4 * n + 3 < w2) {
+            *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (4 * n + k < w2) dst[k] = o[k];
+        }
+    }
+}
+
 // Gray rows [grayY0, grayY1) and upsampled rows [upY0, upY1) (0, 0 = all): a large single frame
 // arrives in two row chunks, each converted as soon as it has landed.
 cudaError_t launchGrayUpsample(const uint8_t* bgra, int pitchBytes, int64_t frameStrideBytes,
@@ -117,6 +185,16 @@ cudaError_t launchGrayUpsample(const uint8_t* bgra, int pitchBytes, int64_t fram
                                cudaStream_t st, int grayY0, int grayY1, int upY0, int upY1) {
     if (grayY1 <= 0) { grayY0 = 0; grayY1 = H; }
     if (upY1 <= 0) { upY0 = 0; upY1 = h2; }
+    if (w2 == 2 * W && h2 == 2 * H && !(upY0 & 1) && !(upY1 & 1) && W >= 2 && H >= 2) {
+        // fused: gray rows [upY0 / 2, upY1 / 2) and their upsampled rows (needs input row upY1 / 2 too)
+        const int m0 = upY0 / 2, m1 = upY1 / 2;
+        if (m1 > m0) {
+            dim3 g((unsigned)(((W + 1) / 2 + 255) / 256), (unsigned)(m1 - m0), (unsigned)frames);
+            grayUpsample2xKernel<<<g, 256, 0, st>>>(bgra, pitchBytes, frameStrideBytes, gray, W, H, scaled,
+                                                    pitch2, scaledFrameStride, m0);
+        }
+        return cudaGetLastError();
+    }
     if (grayY1 > grayY0) {
         dim3 g1((W + 1023) / 1024, grayY1 - grayY0, frames);
         grayKernel<<<g1, 256, 0, st>>>(bgra, pitchBytes, frameStrideBytes, gray, W, H, grayY0);
