@@ -14,7 +14,7 @@ P("```json\n" + json.dumps({k: bench[k] for k in ("value", "unit", "ms_per_step"
 # launch list
 rows = list(csv.DictReader([l for l in open(f"{g}/launches.csv") if not l.startswith("==")]))
 names = [(r["Kernel Name"], float(r["Metric Value"])) for r in rows]
-idx = [i for i, n in enumerate(names) if "grayKernel" in n[0]]
+idx = [i for i, n in enumerate(names) if "grayKernel" in n[0] or "grayUpsample2xKernel" in n[0]]
 step = names[idx[1]:idx[2]] if len(idx) > 2 else names[idx[-1]:]
 agg = collections.OrderedDict()
 for n, t in step:
