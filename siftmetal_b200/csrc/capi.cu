@@ -85,9 +85,12 @@ struct SiftContext {
     // the last kernel.
     // A large single frame is uploaded in two row chunks on the copy stream; the seed stage and
     // octave 0's first row band run on chunk A while chunk B is still crossing PCIe.
-    struct SeedSplit { int grayRows = 0, upRows = 0, seedRows = 0; } upSplit;   // rows of chunk A; 0 = whole frame
-    cudaEvent_t evUp[2]{};
-    cudaEvent_t evSeedA = nullptr;
+    // One upload chunk per row band: chunk k ends with the last input row band k's chain needs.
+    // grayRows / upRows / seedRows[k] = input rows uploaded / upsampled rows / seed rows complete once
+    // chunks 0..k are in (cumulative; the last chunk completes the planes). n = 0: whole frame at once.
+    struct SeedSplit { int n = 0; int grayRows[kMaxBands] = {}, upRows[kMaxBands] = {}, seedRows[kMaxBands] = {}; } upSplit;
+    cudaEvent_t evUp[kMaxBands]{};
+    cudaEvent_t evSeedDone[kMaxBands]{};
     bool countersClean = false;      // both sets' device counters were zeroed after the last call
     bool wantHostOut = false;        // request for the next runDetect / describe
     bool descOnHost = false;         // last describe wrote c->hDesc directly
@@ -190,17 +193,23 @@ int bandBoundary(const SiftContext* c, int band) {   // first row of `band` (mul
 SiftContext::SeedSplit seedSplitFor(const SiftContext* c, int frames) {
     SiftContext::SeedSplit sp;
     static const bool enabled = !(getenv("SIFTCUDA_UPLOAD_SPLIT") && atoi(getenv("SIFTCUDA_UPLOAD_SPLIT")) == 0);
-    if (!enabled || c->nBands != 2 || !bandedOctave0(c, frames)) return sp;
+    if (!enabled || !bandedOctave0(c, frames)) return sp;
     const OctaveDev& q = c->P.oct[0];
+    const int nb = c->nBands, H = c->cfg.height;
     int sumR = 0;
     for (int t = 0; t < kGaussians - 1; t++) sumR += c->ntaps[t] / 2;
-    const int seedRows = bandBoundary(c, 1) + sumR;
-    const int upRows = (seedRows + c->seedNtaps / 2 + 1) & ~1;   // even: whole gray rows (fused gray + upsample)
-    const int grayRows = upRows / 2 + 1;                         // input rows 0 .. upRows / 2
-    if (seedRows >= q.h || upRows >= q.h || grayRows >= c->cfg.height) return sp;
-    sp.grayRows = grayRows;
-    sp.upRows = upRows;
-    sp.seedRows = seedRows;
+    for (int k = 0; k < nb; k++) {
+        if (k + 1 == nb) {
+            sp.seedRows[k] = q.h; sp.upRows[k] = q.h; sp.grayRows[k] = H;
+        } else {
+            sp.seedRows[k] = bandBoundary(c, k + 1) + sumR;
+            sp.upRows[k] = (sp.seedRows[k] + c->seedNtaps / 2 + 1) & ~1;   // even: whole gray rows (fused kernel)
+            sp.grayRows[k] = sp.upRows[k] / 2 + 1;                         // input rows 0 .. upRows / 2
+            const bool grows = k == 0 || (sp.grayRows[k] > sp.grayRows[k - 1] && sp.seedRows[k] > sp.seedRows[k - 1]);
+            if (!grows || sp.seedRows[k] >= q.h || sp.upRows[k] >= q.h || sp.grayRows[k] >= H) return SiftContext::SeedSplit{};
+        }
+    }
+    sp.n = nb;
     return sp;
 }
 
@@ -236,7 +245,8 @@ void destroy(SiftContext* c) {
     if (c->evBandFork) cudaEventDestroy(c->evBandFork);
     for (auto& e : c->evUp)
         if (e) cudaEventDestroy(e);
-    if (c->evSeedA) cudaEventDestroy(c->evSeedA);
+    for (auto& e : c->evSeedDone)
+        if (e) cudaEventDestroy(e);
     if (c->evRefined) cudaEventDestroy(c->evRefined);
     if (c->evKpCopied) cudaEventDestroy(c->evKpCopied);
     if (c->copyStream) cudaStreamDestroy(c->copyStream);
@@ -450,7 +460,7 @@ int sift_create(const SiftConfig* cfg, int device, SiftContext** out) {
     A(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
     A(cudaEventCreateWithFlags(&c->evRefined, cudaEventDisableTiming));
     for (auto& evn : c->evUp) A(cudaEventCreateWithFlags(&evn, cudaEventDisableTiming));
-    A(cudaEventCreateWithFlags(&c->evSeedA, cudaEventDisableTiming));
+    for (auto& evn : c->evSeedDone) A(cudaEventCreateWithFlags(&evn, cudaEventDisableTiming));
     A(cudaEventCreateWithFlags(&c->evKpCopied, cudaEventDisableTiming));
     for (int b = 1; b < SiftContext::kMaxBands; b++) {
         A(cudaStreamCreateWithFlags(&c->bandStream[b], cudaStreamNonBlocking));
@@ -510,16 +520,17 @@ int sift_batch_upload(SiftContext* c, const void* const* images, int32_t n, int3
     for (int f = 0; f < n; f++)
         if (!images[f]) return fail(c, SIFT_ERR_INVALID_ARGUMENT, "sift_batch_upload: null image");
     c->upSplit = seedSplitFor(c, n);
-    if (c->upSplit.grayRows > 0) {
-        // two row chunks on the copy stream, an event behind each
-        const int g = c->upSplit.grayRows;
+    if (c->upSplit.n > 0) {
+        // one row chunk per band on the copy stream, an event behind each
         const uint8_t* src = (const uint8_t*)images[0];
-        CTX_TRY(c, cudaMemcpy2DAsync(c->dInput, rowBytes, src, pitchBytes, rowBytes, g, cudaMemcpyHostToDevice,
-                                     c->copyStream));
-        CTX_TRY(c, cudaEventRecord(c->evUp[0], c->copyStream));
-        CTX_TRY(c, cudaMemcpy2DAsync(c->dInput + (size_t)g * rowBytes, rowBytes, src + (size_t)g * pitchBytes,
-                                     pitchBytes, rowBytes, c->cfg.height - g, cudaMemcpyHostToDevice, c->copyStream));
-        CTX_TRY(c, cudaEventRecord(c->evUp[1], c->copyStream));
+        int g0 = 0;
+        for (int k = 0; k < c->upSplit.n; k++) {
+            const int g1 = c->upSplit.grayRows[k];
+            CTX_TRY(c, cudaMemcpy2DAsync(c->dInput + (size_t)g0 * rowBytes, rowBytes, src + (size_t)g0 * pitchBytes,
+                                         pitchBytes, rowBytes, g1 - g0, cudaMemcpyHostToDevice, c->copyStream));
+            CTX_TRY(c, cudaEventRecord(c->evUp[k], c->copyStream));
+            g0 = g1;
+        }
     } else {
         for (int f = 0; f < n; f++)
             CTX_TRY(c, cudaMemcpy2DAsync(c->dInput + f * frameBytes, rowBytes, images[f], pitchBytes,
@@ -608,29 +619,23 @@ int runDetect(SiftContext* c, bool withDescribe) {
     seed.outFrameStride = kGaussians * o0.plane;
     seed.frames = F;
     const SiftContext::SeedSplit sp = (F == 1 && c->curInput == c->dInput) ? c->upSplit : SiftContext::SeedSplit{};
-    if (sp.grayRows > 0) {
-        // chunk A → everything band 0 of octave 0 needs, on the main stream
-        cudaStream_t sB = c->bandStream[1];
-        CTX_TRY(c, cudaStreamWaitEvent(st, c->evUp[0], 0));
-        CTX_TRY(c, launchGrayUpsample(c->curInput, c->curPitch, c->curFrameStride, c->dGray, c->cfg.width,
-                                      c->cfg.height, c->dScaled, o0.w, o0.h, o0.pitch, o0.plane, F, st, 0,
-                                      sp.grayRows, 0, sp.upRows));
-        seed.yBegin = 0; seed.yEnd = sp.seedRows;
-        CTX_TRY(c, launchBlur(seed, c->seedTaps, c->seedNtaps, st));
-        CTX_TRY(c, cudaEventRecord(c->evSeedA, st));
-        // chunk B → the rest, on band 1's stream (which continues with band 1's blur chain)
-        CTX_TRY(c, cudaStreamWaitEvent(sB, c->evUp[1], 0));
-        CTX_TRY(c, cudaStreamWaitEvent(sB, c->evSeedA, 0));
-        CTX_TRY(c, launchGrayUpsample(c->curInput, c->curPitch, c->curFrameStride, c->dGray, c->cfg.width,
-                                      c->cfg.height, c->dScaled, o0.w, o0.h, o0.pitch, o0.plane, F, sB,
-                                      sp.grayRows, c->cfg.height, sp.upRows, o0.h));
-        seed.yBegin = sp.seedRows; seed.yEnd = o0.h;
-        CTX_TRY(c, launchBlur(seed, c->seedTaps, c->seedNtaps, sB));
-        c->launches += 3;
-    } else {
-        if (c->upSplit.grayRows > 0 && c->curInput == c->dInput) {   // chunked upload, unchunked use
-            CTX_TRY(c, cudaStreamWaitEvent(st, c->evUp[1], 0));
+    if (sp.n > 0) {
+        // chunk k → everything band k of octave 0 still lacks, on band k's stream (main stream for
+        // band 0), behind chunk k's arrival and chunk k - 1's seed rows
+        for (int k = 0; k < sp.n; k++) {
+            cudaStream_t sk = k == 0 ? st : c->bandStream[k];
+            CTX_TRY(c, cudaStreamWaitEvent(sk, c->evUp[k], 0));
+            if (k > 0) CTX_TRY(c, cudaStreamWaitEvent(sk, c->evSeedDone[k - 1], 0));
+            const int up0 = k ? sp.upRows[k - 1] : 0, seed0 = k ? sp.seedRows[k - 1] : 0;
+            CTX_TRY(c, launchGrayUpsample(c->curInput, c->curPitch, c->curFrameStride, c->dGray, c->cfg.width,
+                                          c->cfg.height, c->dScaled, o0.w, o0.h, o0.pitch, o0.plane, F, sk,
+                                          k ? sp.grayRows[k - 1] : 0, sp.grayRows[k], up0, sp.upRows[k]));
+            seed.yBegin = seed0; seed.yEnd = sp.seedRows[k];
+            CTX_TRY(c, launchBlur(seed, c->seedTaps, c->seedNtaps, sk));
+            CTX_TRY(c, cudaEventRecord(c->evSeedDone[k], sk));
+            if (k > 0) c->launches += 2;
         }
+    } else {
         CTX_TRY(c, launchGrayUpsample(c->curInput, c->curPitch, c->curFrameStride, c->dGray,
                                       c->cfg.width, c->cfg.height, c->dScaled, o0.w, o0.h, o0.pitch,
                                       o0.plane, F, st));
