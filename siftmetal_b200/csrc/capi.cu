@@ -89,6 +89,7 @@ struct SiftContext {
     // grayRows / upRows / seedRows[k] = input rows uploaded / upsampled rows / seed rows complete once
     // chunks 0..k are in (cumulative; the last chunk completes the planes). n = 0: whole frame at once.
     struct SeedSplit { int n = 0; int grayRows[kMaxBands] = {}, upRows[kMaxBands] = {}, seedRows[kMaxBands] = {}; } upSplit;
+    cudaEvent_t evBandBlurEnd[kMaxBands]{};   // timing: end of each band's blur chain
     cudaEvent_t evUp[kMaxBands]{};
     cudaEvent_t evSeedDone[kMaxBands]{};
     bool countersClean = false;      // both sets' device counters were zeroed after the last call
@@ -182,6 +183,14 @@ bool bandedOctave0(const SiftContext* c, int frames) {
     const int nb = c->nBands;
     return frames == 1 && nb > 1 && tiles >= 8L * c->smCount && q.h >= 256 * nb;
 }
+// Gradient field and extrema mask of octave 0 per row band, right behind that band's blur chain
+// (each band then carries one more halo row: the mask of its edge rows reads the DoG row beyond).
+bool bandTails() {
+    // measured at 1080p: 1065 vs 1058 frames/s device-resident, 864 vs 872 end to end (the e2e
+    // critical path is upload -> last band's first three blurs -> octave 1 .. 6) — opt-in
+    static const bool on = getenv("SIFTCUDA_BAND_TAILS") && atoi(getenv("SIFTCUDA_BAND_TAILS")) != 0;
+    return on;
+}
 int bandBoundary(const SiftContext* c, int band) {   // first row of `band` (multiple of the tile height)
     const OctaveDev& q = c->P.oct[0];
     if (band >= c->nBands) return q.h;
@@ -202,7 +211,7 @@ SiftContext::SeedSplit seedSplitFor(const SiftContext* c, int frames) {
         if (k + 1 == nb) {
             sp.seedRows[k] = q.h; sp.upRows[k] = q.h; sp.grayRows[k] = H;
         } else {
-            sp.seedRows[k] = bandBoundary(c, k + 1) + sumR;
+            sp.seedRows[k] = bandBoundary(c, k + 1) + sumR + (bandTails() ? 1 : 0);
             sp.upRows[k] = (sp.seedRows[k] + c->seedNtaps / 2 + 1) & ~1;   // even: whole gray rows (fused kernel)
             sp.grayRows[k] = sp.upRows[k] / 2 + 1;                         // input rows 0 .. upRows / 2
             const bool grows = k == 0 || (sp.grayRows[k] > sp.grayRows[k - 1] && sp.seedRows[k] > sp.seedRows[k - 1]);
@@ -246,6 +255,8 @@ void destroy(SiftContext* c) {
     for (auto& e : c->evUp)
         if (e) cudaEventDestroy(e);
     for (auto& e : c->evSeedDone)
+        if (e) cudaEventDestroy(e);
+    for (auto& e : c->evBandBlurEnd)
         if (e) cudaEventDestroy(e);
     if (c->evRefined) cudaEventDestroy(c->evRefined);
     if (c->evKpCopied) cudaEventDestroy(c->evKpCopied);
@@ -461,6 +472,7 @@ int sift_create(const SiftConfig* cfg, int device, SiftContext** out) {
     A(cudaEventCreateWithFlags(&c->evRefined, cudaEventDisableTiming));
     for (auto& evn : c->evUp) A(cudaEventCreateWithFlags(&evn, cudaEventDisableTiming));
     for (auto& evn : c->evSeedDone) A(cudaEventCreateWithFlags(&evn, cudaEventDisableTiming));
+    for (auto& evn : c->evBandBlurEnd) A(cudaEventCreate(&evn));
     A(cudaEventCreateWithFlags(&c->evKpCopied, cudaEventDisableTiming));
     for (int b = 1; b < SiftContext::kMaxBands; b++) {
         A(cudaStreamCreateWithFlags(&c->bandStream[b], cudaStreamNonBlocking));
@@ -686,7 +698,7 @@ int runDetect(SiftContext* c, bool withDescribe) {
                 a.dogFrameStride = kDogs * q.plane;
                 if (banded) {
                     // rows the later scales of this band still need: sum of their radii
-                    int halo = 0;
+                    int halo = bandTails() ? 1 : 0;
                     for (int t = s + 1; t < kGaussians - 1; t++) halo += c->ntaps[t] / 2;
                     a.yBegin = std::max(0, r0 - halo);
                     a.yEnd = std::min(q.h, r1 + halo);
@@ -705,8 +717,14 @@ int runDetect(SiftContext* c, bool withDescribe) {
                 c->launches++;
                 if (s + 1 == kScales) CTX_TRY(c, cudaEventRecord(band == 0 ? c->evSeeded[o] : c->evBandSeeded[band], sb));
             }
+            if (banded && bandTails()) {
+                if (T) CTX_TRY(c, cudaEventRecord(c->evBandBlurEnd[band], sb));
+                if (!(dbgSkip & 1)) CTX_TRY(c, launchGradient(q, F, sb, r0, r1));
+                if (!(dbgSkip & 2)) CTX_TRY(c, launchExtremaMask(c->P, o, c->dMask, F, sb, r0, r1));
+                c->launches += 2;
+            }
         }
-        if (banded) {   // join: gradient and extrema need every row
+        if (banded) {   // join: (without band tails) gradient and extrema need every row
             for (int b = 1; b < nb; b++) {
                 CTX_TRY(c, cudaEventRecord(c->evBandDone[b], c->bandStream[b]));
                 CTX_TRY(c, cudaStreamWaitEvent(so, c->evBandDone[b], 0));
@@ -716,11 +734,13 @@ int runDetect(SiftContext* c, bool withDescribe) {
         if (T && o == 0) CTX_TRY(c, cudaEventRecord(c->evBlur0[kGaussians - 1], so));
         // (the gradient beside the extrema mask on a second stream, or beside blurs s = 3, 4: both
         // measured, no gain — the stage is throughput-bound)
-        if (!(dbgSkip & 1)) CTX_TRY(c, launchGradient(q, F, so));
-        c->launches++;
-        if (q.w >= 3 && q.h >= 3 && !(dbgSkip & 2)) {
-            CTX_TRY(c, launchExtremaMask(c->P, o, c->dMask, F, so));
+        if (!(banded && bandTails())) {
+            if (!(dbgSkip & 1)) CTX_TRY(c, launchGradient(q, F, so));
             c->launches++;
+            if (q.w >= 3 && q.h >= 3 && !(dbgSkip & 2)) {
+                CTX_TRY(c, launchExtremaMask(c->P, o, c->dMask, F, so));
+                c->launches++;
+            }
         }
         if (o > 0) CTX_TRY(c, cudaEventRecord(c->evOctDone[o], so));
         if (o == 0) {
@@ -852,6 +872,14 @@ int finish(SiftContext* c, bool withDescribe) {
             cudaEventElapsedTime(&t.total_ms, c->ev[0], c->evB[lastB]);
         }
         cudaEventElapsedTime(&t.blur_octave0_ms, c->evBlur0[0], c->evBlur0[kGaussians - 1]);
+        if (c->bandedOctave0 && bandTails()) {   // the section ends with the last band's last blur
+            t.blur_octave0_ms = 0;
+            for (int b = 0; b < c->nBands; b++) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, c->evBlur0[0], c->evBandBlurEnd[b]);
+                t.blur_octave0_ms = std::max(t.blur_octave0_ms, ms);
+            }
+        }
         for (int s = 0; s < kGaussians - 1; s++)   // per-scale split only without row bands
             t.blur_octave0_launch_ms[s] = c->bandedOctave0 ? t.blur_octave0_ms / (kGaussians - 1) : 0.0f;
         if (!c->bandedOctave0)

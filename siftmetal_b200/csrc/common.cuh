@@ -128,11 +128,11 @@ struct BlurArgs {
                      //    (small planes: the launch latency of scale s + 1 overlaps scale s)
 };
 cudaError_t launchBlur(const BlurArgs& a, const Taps& taps, int ntaps, cudaStream_t st);
-cudaError_t launchGradient(const OctaveDev& o, int frames, cudaStream_t st);
+cudaError_t launchGradient(const OctaveDev& o, int frames, cudaStream_t st, int yBegin = 0, int yEnd = 0);
 
 // detect.cu
 cudaError_t launchExtremaMask(const EngineParams& P, int octave, uint32_t* mask, int frames,
-                              cudaStream_t st);
+                              cudaStream_t st, int yBegin = 0, int yEnd = 0);
 // mask blocks [blockBegin, blockBegin + nBlocks) → ordered candidates; segStart[nSegs + 1] receives
 // the per-(frame, octave) list offsets
 cudaError_t launchCandidateCompaction(const EngineParams& P, const uint32_t* mask,

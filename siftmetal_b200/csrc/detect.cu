@@ -7,6 +7,8 @@
 //   SIFTOctave.getKeypoints (SIFTOctave.swift:198-203)                              → scan + scatter
 //   SIFTInterpolate.metal:17-300 siftInterpolate and helpers, Common.hpp:34-47 invert,
 //   SIFTOctave.interpolateKeypoints (SIFTOctave.swift:205-288)                      → refineKernel
+#include <algorithm>
+
 #include "common.cuh"
 #include "dev_math.cuh"
 #include "scan.cuh"
@@ -76,13 +78,13 @@ __device__ __forceinline__ RowPart makeRowPart(float c, float e, int lane) {
 
 __global__ void __launch_bounds__(kExtWarps * 32)
 extremaMaskKernel(const OctaveDev o, float softThreshold, uint32_t* __restrict__ mask,
-                  int blocksPerFrame, int rowsPerWarp) {
+                  int blocksPerFrame, int rowsPerWarp, int yBegin, int yEnd) {
     const int lane = threadIdx.x & 31;
     const int xw = blockIdx.x * kExtWarps + (threadIdx.x >> 5);
     if (xw >= o.maskRowWords) return;  // whole warp
     const int x = xw * 32 + lane;      // < pitch: readable even beyond w (masked below)
     const int ex = (lane == 0) ? max(x - 1, 0) : ((lane == 31) ? min(x + 1, o.w - 1) : x);
-    const int yFirst = 1 + blockIdx.y * rowsPerWarp;       // first output row of this warp
+    const int yFirst = yBegin + blockIdx.y * rowsPerWarp;  // first output row of this warp (rows [yBegin, yEnd))
     const int f = blockIdx.z;
     const float* __restrict__ D = o.D + (size_t)f * kDogs * o.plane;
     uint32_t* __restrict__ m =
@@ -119,7 +121,7 @@ extremaMaskKernel(const OctaveDev o, float softThreshold, uint32_t* __restrict__
         for (int k = 0; k < 3; k++) {
             const int y = yFirst + r0 + k;
             const int prev = k % 3, cur = (k + 1) % 3, next = (k + 2) % 3;
-            if (y > o.h - 2) return;  // warp-uniform
+            if (y >= yEnd) return;  // warp-uniform
             const RowRaw now = ahead0;
             ahead0 = ahead1;
             ahead1 = ahead2;
@@ -192,11 +194,16 @@ extremaMaskSmallKernel(const OctaveDev o, float softThreshold, uint32_t* __restr
     }
 }
 
+// Mask rows [yBegin, yEnd) ∩ [1, h - 1) of one octave (0, 0 = all rows): a row band of octave 0
+// gets its mask as soon as that band's blur chain is done.
 cudaError_t launchExtremaMask(const EngineParams& P, int octave, uint32_t* mask, int frames,
-                              cudaStream_t st) {
+                              cudaStream_t st, int yBegin, int yEnd) {
     const OctaveDev& o = P.oct[octave];
     if (o.w < 3 || o.h < 3) return cudaSuccess;
-    if ((long)o.w * o.h * frames <= 96 * 1024) {
+    const bool all = yEnd <= 0;
+    const int yA = all ? 1 : std::max(yBegin, 1), yB = all ? o.h - 1 : std::min(yEnd, o.h - 1);
+    if (yB <= yA) return cudaSuccess;
+    if (all && (long)o.w * o.h * frames <= 96 * 1024) {
         dim3 grid((o.maskRowWords * 32 + 255) / 256, o.h, frames);
         extremaMaskSmallKernel<<<grid, 256, 0, st>>>(o, P.dogThreshold * 0.8f, mask, P.blocksPerFrame);
         return cudaGetLastError();
@@ -204,10 +211,11 @@ cudaError_t launchExtremaMask(const EngineParams& P, int octave, uint32_t* mask,
     // rows per warp (multiple of 3): long strips amortise the 2-row halo on large planes; small
     // planes get short strips so that the serial row loop does not bound the launch
     const int gx = (o.maskRowWords + kExtWarps - 1) / kExtWarps;
+    const int nRows = yB - yA;
     int rows = kExtRows;
-    while (rows > 6 && (long)gx * ((o.h - 2 + rows - 1) / rows) * frames < 592) rows -= 6;
-    dim3 grid(gx, (o.h - 2 + rows - 1) / rows, frames);
-    extremaMaskKernel<<<grid, kExtWarps * 32, 0, st>>>(o, P.dogThreshold * 0.8f, mask, P.blocksPerFrame, rows);
+    while (rows > 6 && (long)gx * ((nRows + rows - 1) / rows) * frames < 592) rows -= 6;
+    dim3 grid(gx, (nRows + rows - 1) / rows, frames);
+    extremaMaskKernel<<<grid, kExtWarps * 32, 0, st>>>(o, P.dogThreshold * 0.8f, mask, P.blocksPerFrame, rows, yA, yB);
     return cudaGetLastError();
 }
 

@@ -502,10 +502,10 @@ cudaError_t launchBlur(const BlurArgs& a, const Taps& taps, int ntaps, cudaStrea
 // refined scale is in [1, 3], SIFTInterpolate.metal:187-189). 4 pixels per thread, float4
 // loads of the three rows, two float4 stores of (orientation, magnitude) pairs. The mirror
 // boundary of symmetrizedCoordinates reduces to a clamp for offsets of one pixel.
-__global__ void __launch_bounds__(256) gradientKernel(const OctaveDev o) {
+__global__ void __launch_bounds__(256) gradientKernel(const OctaveDev o, int yBegin, int yEnd) {
     // 4 pixels x 2 rows per thread: rows y - 1 .. y + 2 are loaded once for both output rows
     const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int y = blockIdx.y * 2;
+    const int y = yBegin + blockIdx.y * 2;   // rows [yBegin, yEnd), yBegin even
     const int s = blockIdx.z % kScales;   // 0..2 → Gaussian slice s + 1
     const int f = blockIdx.z / kScales;
     if (x0 >= o.w) return;
@@ -528,7 +528,7 @@ __global__ void __launch_bounds__(256) gradientKernel(const OctaveDev o) {
                            {r4[2].x, r4[2].y, r4[2].z, r4[2].w}, {r4[3].x, r4[3].y, r4[3].z, r4[3].w}};
 #pragma unroll
     for (int row = 0; row < 2; row++) {
-        if (y + row > hLast) break;
+        if (y + row >= yEnd) break;
         const float* c = v[1 + row];
         const float* up = v[row];
         // the row below output row y + row; at the bottom edge the clamp makes it the row itself
@@ -552,9 +552,13 @@ __global__ void __launch_bounds__(256) gradientKernel(const OctaveDev o) {
     }
 }
 
-cudaError_t launchGradient(const OctaveDev& o, int frames, cudaStream_t st) {
-    dim3 grid((o.w + 1023) / 1024, (o.h + 1) / 2, kScales * frames);
-    gradientKernel<<<grid, 256, 0, st>>>(o);
+cudaError_t launchGradient(const OctaveDev& o, int frames, cudaStream_t st, int yBegin, int yEnd) {
+    if (yEnd <= 0) { yBegin = 0; yEnd = o.h; }
+    yBegin &= ~1;
+    yEnd = std::min(yEnd, o.h);
+    if (yEnd <= yBegin) return cudaSuccess;
+    dim3 grid((o.w + 1023) / 1024, (yEnd - yBegin + 1) / 2, kScales * frames);
+    gradientKernel<<<grid, 256, 0, st>>>(o, yBegin, yEnd);
     return cudaGetLastError();
 }
 

@@ -282,9 +282,12 @@ def test_full_size_properties_1080p():
     assert np.all(np.abs(k["absoluteX"] - okps["absoluteX"]) <= POS_TOL)
 
 
-def test_split_list_mode_matches(monkeypatch):
-    """SIFTCUDA_SPLIT=1 (octave 0 compacted and described ahead of the deeper octaves, from a
-    second list set) must give the same result arrays as the default single pass."""
+@pytest.mark.parametrize("switch", ["SIFTCUDA_SPLIT=1", "SIFTCUDA_BAND_TAILS=1 SIFTCUDA_BANDS=3", "SIFTCUDA_BANDS=1",
+                                    "SIFTCUDA_HOST_OUT=0 SIFTCUDA_UPLOAD_SPLIT=0"])
+def test_tuning_switches_do_not_change_results(switch):
+    """The opt-in schedules (octave 0 described ahead of the deeper octaves from a second list set;
+    per-band gradient / extrema with three row bands; no row bands; explicit copies instead of
+    chunked upload + host-resident results) must give the same result arrays as the default."""
     import os
     import subprocess
     import sys
@@ -298,8 +301,10 @@ def test_split_list_mode_matches(monkeypatch):
     )
     outs = []
     for flag in ("0", "1"):
-        path = f"/tmp/sift_split_{flag}.npz"
-        env = dict(os.environ, SIFTCUDA_SPLIT=flag)
+        path = f"/tmp/sift_switch_{flag}.npz"
+        env = dict(os.environ)
+        if flag == "1":
+            env.update(kv.split("=") for kv in switch.split())
         subprocess.run([sys.executable, "-c", code, path], check=True, env=env,
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
         outs.append(np.load(path))
