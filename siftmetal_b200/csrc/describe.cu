@@ -336,7 +336,7 @@ __device__ __forceinline__ void descAccumulate(char* const hl, const float2 gm, 
 // (Measured and dropped: the warp as a (32 / C)-row x C-column tile over row groups, C = 4, 8, 16 —
 // uniform control flow, but idle lane slots at the ragged span ends pay the full accumulation
 // cost: 0.60 / 0.63 / 0.74 ms against 0.46 ms for WALK 0 at the time.)
-template <int WALK>
+template <int WALK, int NPAIRS = 3>
 __global__ void __launch_bounds__(kDescWarps * 32, 2)
 descriptorKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __restrict__ kps,
                  const int* __restrict__ kpSeg, const int* __restrict__ segKpStart,
@@ -477,7 +477,7 @@ descriptorKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __r
             };
             rowBounds();
             settle();
-            constexpr int NP = 2;   // pairs per lane per batch
+            constexpr int NP = NPAIRS;   // pairs per lane per batch (measured: 1: 0.379, 2: 0.350, 3: 0.341, 4: 0.351 ms)
             // One batch = coordinates + gathers of NP pairs per lane, then their accumulation.
             auto fetch = [&](float4 (&gm)[NP], float (&rxs)[NP], float (&rys)[NP], bool (&ok0)[NP],
                              bool (&ok1)[NP]) -> bool {
