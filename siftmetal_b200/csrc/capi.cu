@@ -225,7 +225,13 @@ SiftContext::SeedSplit seedSplitFor(const SiftContext* c, int frames) {
 void destroy(SiftContext* c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    // drain every stream of the context (a chunked upload may still be in flight on the copy stream)
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->copyStream) cudaStreamSynchronize(c->copyStream);
+    for (int o = 1; o < kOctaves; o++)
+        if (c->octStream[o]) cudaStreamSynchronize(c->octStream[o]);
+    for (int b = 1; b < SiftContext::kMaxBands; b++)
+        if (c->bandStream[b]) cudaStreamSynchronize(c->bandStream[b]);
     for (void* p : c->allocations) cudaFree(p);
     for (int k = 0; k < 2; k++) {
         if (c->L[k].hCounters) cudaFreeHost(c->L[k].hCounters);
