@@ -1,6 +1,8 @@
 """Builds profiles/<round>/SUMMARY.md from gpurun_out/: launch list shares, ncu key metrics of
 the hot kernels (incl. DRAM traffic per launch), bench JSON."""
 import collections, csv, io, json, os, re, subprocess, sys
+if len(sys.argv) != 2 or sys.argv[1].startswith("-"):
+    sys.exit("usage: python profiles/summarize.py <output dir, e.g. profiles/r1>")
 out_dir = sys.argv[1]
 g = "gpurun_out"
 lines = []
