@@ -123,9 +123,10 @@ def test_butterfly_fixture_full_parity(butterfly_bgra):
     eng.close()
 
 
-@pytest.mark.parametrize("w,h", [(203, 157), (64, 48), (640, 480), (40, 24), (333, 77)])
+@pytest.mark.parametrize("w,h", [(203, 157), (64, 48), (640, 480), (40, 24), (333, 77), (1367, 911)])
 def test_synthetic_sizes(w, h):
-    """Ragged sizes: odd widths, octaves narrower than the 27-tap kernel, empty top octaves."""
+    """Ragged sizes: odd widths, octaves narrower than the 27-tap kernel, empty top octaves, and
+    one large odd frame (row-banded octave 0, chunked upload, partial edge tiles in both axes)."""
     from siftmetal_b200.synth import pink_noise_bgra
 
     img = pink_noise_bgra(w, h, frame_index=w + h)
