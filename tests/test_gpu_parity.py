@@ -30,7 +30,8 @@ def _oracle(w, h):
     return Oracle(w, h)
 
 
-def _check_frame(eng, ora, bgra, kps, desc, kcounts, dcounts, ccounts=None, planes=True, frame=0):
+def _check_frame(eng, ora, bgra, kps, desc, kcounts, dcounts, ccounts=None, planes=True, frame=0,
+                 max_structural=0.0):
     """Full comparison of one frame's GPU results with a fresh oracle run."""
     okps, ocounts = ora.detect(bgra)
     odesc, odcounts = ora.describe()
@@ -65,15 +66,28 @@ def _check_frame(eng, ora, bgra, kps, desc, kcounts, dcounts, ccounts=None, plan
     for f in ("subScale", "value", "normalizedX", "normalizedY"):
         assert np.allclose(kps[f], okps[f], rtol=0, atol=1e-6), f
     exact = all(np.array_equal(kps[f], okps[f]) for f in kps.dtype.names)
-    # descriptors: same (keypoint, orientation) structure, θ and features within tolerance
-    assert np.array_equal(dcounts, odcounts), (dcounts, odcounts)
+    # descriptors: same (keypoint, orientation) structure, θ and features within tolerance.
+    # Structural mismatches (a keypoint with a missing / extra orientation: the 36-bin histogram is
+    # summed in a different order on the GPU, so a peak test can flip in the last bit) must be 0 on
+    # the fixture and <= 1e-4 of the keypoints on synthetic sets; the keypoints
+    # concerned are left out of the element-wise comparison.
+    nk = len(kps)
+    gpk = np.bincount(desc["keypoint"], minlength=nk)
+    opk = np.bincount(odesc["keypoint"], minlength=nk)
+    bad = np.nonzero(gpk != opk)[0]
+    assert len(bad) <= max_structural * nk, (len(bad), nk, dcounts, odcounts)
+    if len(bad):
+        desc = desc[~np.isin(desc["keypoint"], bad)]
+        odesc = odesc[~np.isin(odesc["keypoint"], bad)]
+    else:
+        assert np.array_equal(dcounts, odcounts), (dcounts, odcounts)
     assert np.array_equal(desc["keypoint"], odesc["keypoint"])
     dth = np.abs(desc["theta"] - odesc["theta"])
     dth = np.minimum(dth, 2 * np.pi - dth)
     assert np.all(dth <= THETA_TOL), dth.max()
     df = np.abs(desc["features"].astype(np.int16) - odesc["features"].astype(np.int16))
     assert df.max(initial=0) <= FEAT_TOL, df.max()
-    return {"keypoints_bit_exact": exact, "max_dtheta": float(dth.max(initial=0)),
+    return {"keypoints_bit_exact": exact, "max_dtheta": float(dth.max(initial=0)), "structural": int(len(bad)),
             "feat_mismatch_frac": float((df > 0).mean()) if df.size else 0.0}
 
 
@@ -281,6 +295,94 @@ def test_full_size_properties_1080p():
     eng.close()
     assert np.array_equal(k["scaledX"], okps["scaledX"]) and np.array_equal(k["scaledY"], okps["scaledY"])
     assert np.all(np.abs(k["absoluteX"] - okps["absoluteX"]) <= POS_TOL)
+
+
+def _free_host_gb():
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable"):
+                    return int(line.split()[1]) / 1e6
+    except OSError:
+        pass
+    return 0.0
+
+
+def test_config3_4k_frame_against_oracle():
+    """BASELINE configs[3] frame size (3840x2160): candidates, keypoints, orientations and
+    descriptors of one full-size frame against the oracle (planes are covered at 1080p)."""
+    from siftmetal_b200.synth import pink_noise_bgra
+
+    w, h = 3840, 2160
+    img = pink_noise_bgra(w, h, 11)
+    eng, ora = _engine(w, h), _oracle(w, h)
+    res = eng.detect_and_describe([img])
+    kps, desc = res.frame(0)
+    rep = _check_frame(eng, ora, img, kps, desc, res.keypoint_counts[0], res.descriptor_counts[0],
+                       res.candidate_counts[0], planes=False, max_structural=1e-4)
+    assert rep["keypoints_bit_exact"]
+    assert len(kps) > 60000          # ~ 13.7 keypoints per 1000 input pixels (SURVEY §8d)
+    # seed plane and the last Gaussian of octave 0 (largest planes of the config) bit-exact
+    assert np.array_equal(eng.plane(_abi.PLANE_SEED), ora.plane(_abi.PLANE_SEED))
+    assert np.array_equal(eng.plane(_abi.PLANE_GAUSSIAN, 0, 5), ora.plane(_abi.PLANE_GAUSSIAN, 0, 5))
+    eng.close()
+
+
+def test_config4_8k_tile_against_oracle():
+    """BASELINE configs[4]: one 8192x8192 tile (octave 0 is 16384^2: 15-bit packed coordinates,
+    the largest mask / list capacities) against the oracle at full size."""
+    from siftmetal_b200.synth import pink_noise_bgra
+
+    if _free_host_gb() < 45:
+        pytest.skip("the oracle needs ~30 GB of host memory at 8192x8192")
+    w, h = 8192, 8192
+    img = pink_noise_bgra(w, h, 21)
+    eng, ora = _engine(w, h), _oracle(w, h)
+    res = eng.detect_and_describe([img])
+    kps, desc = res.frame(0)
+    rep = _check_frame(eng, ora, img, kps, desc, res.keypoint_counts[0], res.descriptor_counts[0],
+                       res.candidate_counts[0], planes=False, max_structural=1e-4)
+    assert rep["keypoints_bit_exact"]
+    assert len(kps) > 500000
+    assert kps["scaledX"].max() > 16000 and kps["scaledY"].max() > 16000   # the far corner is reached
+    for o in (0, 6):
+        assert np.array_equal(eng.plane(_abi.PLANE_DOG, o, 4), ora.plane(_abi.PLANE_DOG, o, 4))
+    eng.close()
+
+
+def test_config2_vga256_batch_against_oracle():
+    """BASELINE configs[2]: 256 frames of 640x480 in one resident batch. Every frame's per-octave
+    candidate / keypoint / descriptor counts against the oracle; frames 0, 127 and 255 in full."""
+    from siftmetal_b200.synth import pink_noise_bgra
+
+    w, h, n = 640, 480, 256
+    uniq = [pink_noise_bgra(w, h, 100 + i) for i in range(32)]
+    order = [(7 * i + i // 32) % 32 for i in range(n)]          # every unique frame at 8 batch positions
+    frames = [uniq[k] for k in order]
+    eng, ora = _engine(w, h, max_batch=n), _oracle(w, h)
+    res = eng.detect_and_describe(frames)
+    assert res.keypoint_counts.shape == (n, 7)
+    ref = {}
+    for k in range(32):
+        okps, oc = ora.detect(uniq[k])
+        odesc, odc = ora.describe()
+        cc = np.array([len(ora.candidates(o)) for o in range(7)])
+        ref[k] = (oc.copy(), odc.copy(), cc, okps, odesc)
+    for f in range(n):
+        oc, odc, cc, okps, odesc = ref[order[f]]
+        assert np.array_equal(res.keypoint_counts[f], oc), f
+        assert np.array_equal(res.descriptor_counts[f], odc), f
+        assert np.array_equal(res.candidate_counts[f], cc), f
+    for f in (0, 127, 255):
+        kps, desc = res.frame(f)
+        _check_frame(eng, ora, frames[f], kps, desc, res.keypoint_counts[f], res.descriptor_counts[f],
+                     res.candidate_counts[f], planes=(f == 255), frame=f)
+    # same unique frame at different batch positions: identical records
+    a, b = [i for i in range(n) if order[i] == 5][:2]
+    ka, da = res.frame(a)
+    kb, db = res.frame(b)
+    assert np.array_equal(ka, kb) and np.array_equal(da["features"], db["features"])
+    eng.close()
 
 
 @pytest.mark.parametrize("switch", ["SIFTCUDA_SPLIT=1", "SIFTCUDA_BAND_TAILS=1 SIFTCUDA_BANDS=3", "SIFTCUDA_BANDS=1",
