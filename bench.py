@@ -9,15 +9,21 @@ A step = one pass of the whole hot path (seed → pyramid/DoG → extrema → re
 orientation → descriptor) over one batch of synthetic 1/f-noise frames.
 Default workload = BASELINE.json configs[1]: a single 1920×1080 frame per step per GPU.
 
-  value      frames/s with the input already resident in HBM (device time, CUDA events recorded by
-             the library on its own stream, summed over the K steps; max over ranks)
-  e2e        frames/s through the C-ABI call with HOST (pinned) buffers: H2D of the frames and the
-             arrival of keypoints + descriptors in host memory inside the timed region (the library
-             uploads a large frame in two chunks, copies the keypoints out while the descriptor
-             kernel runs and lets that kernel store its records straight into pinned memory)
-  roofline   the dominant kernel (octave-0 Gaussian blur + DoG, 5 scales per step):
-             algorithmic bytes (12 B per octave-0 pixel per scale: read G[s], write G[s+1],
-             write DoG[s]) ÷ its mean time per scale from CUDA events, against the measured HBM peak
+  value      frames/s with the input already resident in HBM: device time between two CUDA events the
+             library records on its own stream around each call's work (one CUDA-graph launch),
+             summed over the K steps, L2 flushed between steps; max over ranks
+  e2e        frames/s through the public pipelined C-ABI calls (sift_submit / sift_wait, two calls
+             in flight) with HOST (pinned) frames: every step's H2D of its frames and the arrival of
+             its keypoint + descriptor columns in host memory are inside the wall-clock timed region
+             (the kernels store the result columns straight into pinned memory; the upload of step
+             i + 1 crosses PCIe under the kernels of step i). For a sharded workload on N > 1 GPUs
+             the host gather (every rank's result columns visible to rank 0 in frame order through
+             shared memory) is inside the region too. `sync_call` is the same through the
+             synchronous sift_detect_and_describe_batch (no overlap between calls).
+  roofline   the dominant streaming kernel (octave-0 Gaussian blur + DoG, 5 scales per step):
+             algorithmic bytes (12 B per octave-0 pixel per scale: read G[s], write G[s+1], write
+             DoG[s]) ÷ its mean time per scale from CUDA events over a second, launch-by-launch
+             region of the same steps (per-stage events cannot be recorded inside a graph replay)
   cpu_baseline   the C++ oracle (a port of the reference's kernels + host stages; the Swift/Metal
              reference cannot run on Linux) on the host cores, bounded sample
 
@@ -28,6 +34,7 @@ import argparse
 import ctypes as C
 import json
 import os
+import platform
 import subprocess
 import sys
 import threading
@@ -46,16 +53,28 @@ WORKLOADS = {
     "8k": (8192, 8192, 1, False),        # configs[4]
 }
 METRIC = "1080p SIFT frames/sec (detect+describe)"
+STAGES = ("seed", "pyramid", "extrema", "refine", "orientation", "descriptor")
+NOMINAL_HBM_GBS = 8000.0   # north_star's "about 8 TB/s"; fractions are quoted against both peaks
+
+
+def workload_string(name):
+    """config.workload — the same string in both arms (the driver compares them)."""
+    w, h, total, sharded = WORKLOADS[name]
+    if sharded:
+        return f"{name}: {total} x {w}x{h} synthetic 1/f-noise BGRA8 frames per step, sharded across the GPUs"
+    return f"{name}: one {w}x{h} synthetic 1/f-noise BGRA8 frame per step per GPU"
 
 
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=30)
+    p.add_argument("--steps", type=int, default=200)
     p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--workload", default="1080p", choices=sorted(WORKLOADS))
     p.add_argument("--chunk", type=int, default=0, help="frames resident per execute (0 = auto)")
+    p.add_argument("--input-format", default="bgra8", choices=["bgra8", "gray8"],
+                   help="ingestion format of the e2e / value paths (bgra8 = the reference's)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-flush", action="store_true", help="skip the L2 flush between steps")
     p.add_argument("--quick", action="store_true", help="profiling runs under ncu: 1 warm-up, no e2e, no CPU baseline")
@@ -69,6 +88,28 @@ def measured_peaks():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the octave-0 blur, from the ncu
+    --set full capture summarised by profiles/summarize.py (None when no capture has been summarised)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2", "traffic.json")) as f:
+            d = json.load(f)
+        return float(d["blur_octave0_dram_bytes_per_launch"]), d.get("source", "profiles/r2/traffic.json")
+    except Exception:
+        return None, None
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return platform.processor() or "unknown"
 
 
 class ClockSampler:
@@ -121,11 +162,12 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_frames(w, h, n, first_index=0):
-    from siftmetal_b200.synth import pink_noise_bgra
+def make_frames(w, h, n, first_index=0, gray=False):
+    from siftmetal_b200.synth import pink_noise_bgra, pink_noise_gray
 
+    gen = pink_noise_gray if gray else pink_noise_bgra
     uniq = min(n, 8)   # distinct frames; larger batches cycle through them (generation is FFT-bound)
-    base = [pink_noise_bgra(w, h, first_index + i) for i in range(uniq)]
+    base = [gen(w, h, first_index + i) for i in range(uniq)]
     return [base[i % uniq] for i in range(n)]
 
 
@@ -159,7 +201,7 @@ def run_reference(args, rank, world):
         return
     w, h, total, _ = WORKLOADS[args.workload]
     frames = make_frames(w, h, 1)
-    # each step = one frame of the workload (bounded sample; 1080p ≈ 1.3 s on 8 cores)
+    # each step = one frame of the workload (bounded sample; 1080p ≈ 0.3 s on 16 cores)
     ol = load_oracle()
     ora = ol.Oracle(w, h, threads=0)
     cores = ol.lib().oracle_max_threads()
@@ -175,10 +217,10 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {w}x{h} 1/f-noise BGRA8, one frame per step",
+        "config": {"workload": workload_string(args.workload),
                    "note": "CPU restatement (oracle/) of the reference's Metal kernels + Swift host stages; "
-                           "the Swift/Metal reference itself cannot run on Linux"},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                           "the Swift/Metal reference itself cannot run on Linux; each step = one frame of the workload"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "cpu": cpu_model(),
                          "sample": f"{steps} x one {w}x{h} frame, OpenMP {cores} threads"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -198,7 +240,8 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from siftmetal_b200 import Engine
+    from siftmetal_b200 import Engine, _abi
+    from siftmetal_b200.sharding import ShmGather, shard_range
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
@@ -209,8 +252,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     w, h, total, sharded = WORKLOADS[args.workload]
-    from siftmetal_b200.sharding import shard_range
-
+    gray = args.input_format == "gray8"
+    bpp = 1 if gray else 4
     if sharded:   # contiguous frame blocks per rank, no collective on the data path
         first, last = shard_range(total, rank, world)
         n_local = max(1, last - first)
@@ -222,11 +265,12 @@ def main():
     # frames resident per execute: bounded by memory (≈ 70 B per octave pixel, 5.33 octave px / px)
     per_frame_bytes = w * h * 5.34 * 76 + w * h * 8
     chunk = args.chunk or max(1, min(n_local, int(60e9 // per_frame_bytes)))
-    eng = Engine(w, h, device=local, max_batch=chunk)
-    frames = make_frames(w, h, n_local, first_index=first)
+    eng = Engine(w, h, device=local, max_batch=chunk,
+                 input_format=_abi.INPUT_GRAY8 if gray else _abi.INPUT_BGRA8)
+    frames = make_frames(w, h, n_local, first_index=first, gray=gray)
 
     # pinned host staging of this rank's frames (e2e path) — torch only as the pinned allocator
-    pinned = torch.empty((n_local, h, w, 4), dtype=torch.uint8, pin_memory=True)
+    pinned = torch.empty((n_local, h, w, 4) if not gray else (n_local, h, w), dtype=torch.uint8, pin_memory=True)
     pin_np = pinned.numpy()
     for i, f in enumerate(frames):
         pin_np[i] = f
@@ -237,7 +281,7 @@ def main():
     # device-resident copy of the inputs (value path)
     dev_in = pinned.to(f"cuda:{local}")
     torch.cuda.synchronize()
-    frame_bytes = w * h * 4
+    frame_bytes = w * h * bpp
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")
 
     def barrier():
@@ -245,22 +289,23 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_device():
-        """One step with device-resident input; returns (device ms, blur ms list, kp, desc)."""
-        ms, blur, launches, nk, nd = 0.0, np.zeros(5), 0, 0, 0
-        stage = np.zeros(6)
+    def step_device(collect=None):
+        """One step with device-resident input; returns (device ms, kernel launches)."""
+        ms, launches = 0.0, 0
         for s, n in chunks:
-            eng.set_device_input(dev_in.data_ptr() + s * frame_bytes, n, w * 4, frame_bytes)
+            eng.set_device_input(dev_in.data_ptr() + s * frame_bytes, n, w * bpp, frame_bytes)
             eng.execute()
             t = eng.timings()
             ms += t["total_ms"]
-            blur += np.array(t["blur_octave0_launch_ms"])
-            stage += np.array([t[k + "_ms"] for k in ("seed", "pyramid", "extrema", "refine", "orientation", "descriptor")])
             launches += t["kernel_launches"]
-        return ms, blur, launches, stage
+            if collect is not None:
+                collect["stage"] += np.array([t[k + "_ms"] for k in STAGES])
+                collect["blur"] += np.array(t["blur_octave0_launch_ms"])
+                collect["graph"] += int(t["graph_replay"])
+        return ms, launches
 
-    # ---- warm-up ------------------------------------------------------------------------------
-    n_warm = 1 if args.quick else max(3, args.warmup)
+    # ---- warm-up (the second call of every chunk shape records its CUDA graph) ---------------------
+    n_warm = 2 if args.quick else max(3, args.warmup)
     for _ in range(n_warm):
         step_device()
     res = eng.download()
@@ -273,50 +318,102 @@ def main():
         sampler.start()
     barrier()
     t_wall0 = time.perf_counter()
-    dev_ms, blur_ms, launches = 0.0, np.zeros(5), 0
-    stage_ms = np.zeros(6)
+    dev_ms, launches = 0.0, 0
+    graph_steps = {"stage": np.zeros(6), "blur": np.zeros(5), "graph": 0}
     for _ in range(args.steps):
         if flush is not None:
             flush.zero_()                  # evict L2 (126 MB) between steps; not in the device time
             torch.cuda.synchronize()
-        ms, blur, ln, stage = step_device()
+        ms, ln = step_device(graph_steps)
         dev_ms += ms
-        blur_ms += blur
-        stage_ms += stage
         launches += ln
     barrier()
     wall_s = time.perf_counter() - t_wall0
-
-    # ---- e2e: host buffers through the public batch call -------------------------------------------
-    e2e_stage = np.zeros(6)
-
-    def step_e2e():
-        nk = nd = 0
-        for (s, n), pa in zip(chunks, ptr_arrays):
-            k, d = eng.detect_and_describe_ptrs(pa, n, w * 4)
-            nk += k
-            nd += d
-            t = eng.timings()   # read after the call returned: not in anybody's critical path
-            e2e_stage[:] += np.array([t[k2 + "_ms"] for k2 in ("seed", "pyramid", "extrema", "refine", "orientation", "descriptor")])
-        return nk, nd
-
-    e2e_steps = 1 if args.quick else max(3, args.steps // 2)
-    for _ in range(0 if args.quick else 2):
-        step_e2e()
-    barrier()
-    e2e_stage[:] = 0
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        nk, nd = step_e2e()
-    barrier()
-    e2e_s = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- e2e: host buffers through the public pipelined calls, results gathered on rank 0 ----------
+    gather = ShmGather(rank, world, eng, n_local) if (distributed and sharded) else None
+    e2e_counts = [0, 0]
+
+    def publish(result_counts):
+        e2e_counts[0] += result_counts[0]
+        e2e_counts[1] += result_counts[1]
+
+    def step_e2e_pipelined(steps):
+        """`steps` steps with two calls in flight across chunk and step boundaries."""
+        seq = [(st, ci) for st in range(steps) for ci in range(len(chunks))]
+        inflight = []
+        for st, ci in seq:
+            if len(inflight) == 2:
+                pst, pci = inflight.pop(0)
+                r = eng.wait(copy=False)
+                if gather is not None:
+                    gather.publish(r, chunks[pci][0])
+                publish((len(r.keypoint_columns), len(r.descriptor_columns)))
+                if gather is not None and pci == len(chunks) - 1:
+                    gather.step_done()                     # barrier: the step's shards are all visible
+            s, n = chunks[ci]
+            eng.submit_ptrs(ptr_arrays[ci], n, w * bpp)
+            inflight.append((st, ci))
+        while inflight:
+            pst, pci = inflight.pop(0)
+            r = eng.wait(copy=False)
+            if gather is not None:
+                gather.publish(r, chunks[pci][0])
+            publish((len(r.keypoint_columns), len(r.descriptor_columns)))
+            if gather is not None and pci == len(chunks) - 1:
+                gather.step_done()
+
+    def step_e2e_sync():
+        nk = nd = 0
+        for (s, n), pa in zip(chunks, ptr_arrays):
+            k, d = eng.detect_and_describe_ptrs(pa, n, w * bpp)
+            nk += k
+            nd += d
+        return nk, nd
+
+    e2e_steps = 2 if args.quick else max(5, args.steps // 2)
+    sync_steps = 1 if args.quick else max(3, min(e2e_steps, 50))
+    step_e2e_pipelined(2)                                    # warm-up: slot 1 allocation, its graph
+    step_e2e_sync()
+    barrier()
+    e2e_counts[:] = [0, 0]
+    t0 = time.perf_counter()
+    step_e2e_pipelined(e2e_steps)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    nk_total, nd_total = e2e_counts
+    t0 = time.perf_counter()
+    for _ in range(sync_steps):
+        step_e2e_sync()
+    barrier()
+    sync_s = time.perf_counter() - t0
+    gathered = gather.summary() if gather is not None else None
+
+    # ---- diagnostic region: the same steps launch by launch with per-stage events --------------------
+    diag = {"stage": np.zeros(6), "blur": np.zeros(5), "graph": 0}
+    diag_steps = 2 if args.quick else max(5, min(args.steps, 30))
+    eng.set_stage_timing(True)
+    step_device()
+    diag_ms = 0.0
+    for _ in range(diag_steps):
+        if flush is not None:
+            flush.zero_()
+            torch.cuda.synchronize()
+        ms, _ = step_device(diag)
+        diag_ms += ms
+    eng.set_stage_timing(False)
+    # ... and the octave-0 blur kernels alone, back to back (20 launches each)
+    isolated = None
+    if not args.quick:
+        step_device()
+        isolated = [eng.blur_bench(s, 0, 20) for s in range(5)]
+
     # ---- reduce over ranks (max time) -----------------------------------------------------------------
-    times = torch.tensor([dev_ms, e2e_s, wall_s], dtype=torch.float64, device=f"cuda:{local}")
+    times = torch.tensor([dev_ms, e2e_s, wall_s, sync_s], dtype=torch.float64, device=f"cuda:{local}")
     if distributed:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms_max, e2e_s_max, wall_s_max = [float(x) for x in times.tolist()]
+    dev_ms_max, e2e_s_max, wall_s_max, sync_s_max = [float(x) for x in times.tolist()]
 
     if rank == 0:
         K = args.steps
@@ -326,64 +423,85 @@ def main():
         p0 = info.octave_width[0] * info.octave_height[0]
         sum_p = sum(info.octave_width[o] * info.octave_height[o] for o in range(7))
         peak, peak_src = measured_peaks()
-        # dominant kernel: octave-0 blur+DoG, algorithmic bytes per launch = 12 B x P0 x frames
-        launches_timed = 5 * K * len(chunks)
-        blur_avg_s = float(blur_ms.sum()) / 1000.0 / launches_timed
+        # dominant streaming kernel: octave-0 blur+DoG, algorithmic bytes per launch = 12 B x P0 x frames
+        launches_timed = 5 * diag_steps * len(chunks)
+        blur_avg_s = float(diag["blur"].sum()) / 1000.0 / launches_timed
         bytes_per_launch = 12.0 * p0 * (n_local / len(chunks))
         achieved = bytes_per_launch / blur_avg_s / 1e9
-        model_b_bytes = (4 + 16) * w * h + 36 * sum_p     # SURVEY §8d model B, per frame
+        model_b_bytes = (bpp + 16) * w * h + 36 * sum_p   # SURVEY §8d model B, per frame
         model_bg_bytes = model_b_bytes + 36 * sum_p       # + precomputed gradients
+        traffic, traffic_src = measured_traffic()
+        frame_gbps = model_b_bytes * frames_per_step_job / world / (dev_ms_max / K / 1000) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K,
             "warmup": n_warm, "ms_per_step": dev_ms_max / K, "higher_is_better": True,
             "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": f"{args.workload}: {frames_per_step_job} x {w}x{h} 1/f-noise BGRA8 frame(s) per step"
-                            + (" sharded across ranks" if sharded else " (one per GPU; replicas when N>1)"),
+                "workload": workload_string(args.workload),
+                "input_format": args.input_format,
                 "frames_per_gpu_per_step": n_local, "resident_chunk": chunk,
                 "l2": "explicit 256 MiB flush between steps" if flush is not None else
                       "no flush (per-step working set of ~0.75 GB per 1080p frame exceeds the 126 MB L2)",
                 "keypoints_per_step_per_gpu": kp_per_step, "descriptors_per_step_per_gpu": desc_per_step,
-                "timing": "CUDA events recorded by libsiftcuda on its own stream around each execute, summed",
+                "timing": "CUDA events recorded by libsiftcuda on its own stream around each call's work "
+                          f"(CUDA-graph replay in {graph_steps['graph']} of {K * len(chunks)} calls), summed",
             },
             "wall_ms_per_step": 1000 * wall_s_max / K,
-            "stage_ms_per_step": {k: float(v) / K for k, v in zip(
-                ("seed", "pyramid", "extrema", "refine", "orientation", "descriptor"), stage_ms)},
+            "stage_ms_per_step": {k: float(v) / diag_steps for k, v in zip(STAGES, diag["stage"])},
+            "stage_timing_note": f"launch-by-launch region with per-stage events, {diag_steps} steps, "
+                                 f"{diag_ms / diag_steps:.4f} ms per step (graph replay: {dev_ms_max / K:.4f})",
             "frame_roofline": {
-                "model_B_GBps": model_b_bytes * frames_per_step_job / world / (dev_ms_max / K / 1000) / 1e9,
-                "model_B_plus_grad_GBps": model_bg_bytes * frames_per_step_job / world / (dev_ms_max / K / 1000) / 1e9,
+                "model_B_GBps": frame_gbps,
+                "model_B_plus_grad_GBps": frame_gbps * model_bg_bytes / model_b_bytes,
                 "model_B_bytes_per_frame": model_b_bytes, "peak_GBps": peak,
+                "frac_of_measured": frame_gbps / peak, "frac_of_nominal_8TBps": frame_gbps / NOMINAL_HBM_GBS,
             },
             "roofline": {
                 "bound": "hbm",
                 "kernel": "blurKernel<NTAPS,64,64,256> octave 0: 5 scales (11,15,17,21,27 taps) per step; on a large "
-                          "single frame each scale runs as 2 concurrent row-band launches, and avg_launch_ms is the "
-                          "CUDA-event time of the whole 5-scale section / 5 (one scale of the full plane)",
+                          "single frame each scale runs as 2 concurrent row-band launches; avg_launch_ms is the "
+                          "CUDA-event time of the whole 5-scale section / 5 (one scale of the full plane) in the "
+                          "launch-by-launch region; isolated_launch_ms is each kernel alone, 20 launches back to back",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture
-                # in profiles/r1/SUMMARY.md (mean of the 5 octave-0 launches, 1080p, cold cache; part
-                # of the 66 MB written per launch is still in the 126 MB L2 when the kernel ends)
-                "traffic": 47.8e6 * (n_local / len(chunks)) if (w, h) == (1920, 1080) else None,
+                "frac_of_nominal_8TBps": achieved / NOMINAL_HBM_GBS,
+                "traffic": traffic * (n_local / len(chunks)) if (traffic and (w, h) == (1920, 1080)) else None,
+                "traffic_source": traffic_src,
                 "peak_source": peak_src,
                 "bytes_per_launch": bytes_per_launch, "avg_launch_ms": blur_avg_s * 1000,
-                "per_tap_launch_ms": [float(x) / (K * len(chunks)) for x in blur_ms],
+                "per_tap_launch_ms": [float(x) / (diag_steps * len(chunks)) for x in diag["blur"]],
+                "isolated_launch_ms": isolated,
+                "isolated_frac": [bytes_per_launch / (ms / 1000.0) / 1e9 / peak for ms in isolated] if isolated else None,
             },
             "e2e": {"value": e2e_value, "unit": "frames/s",
                     "h2d_bytes_per_step": n_local * frame_bytes,
-                    "d2h_bytes_per_step": int(nk) * 44 + int(nd) * 136 + 24 + 3 * 4 * (7 * chunk + 1),
-                    "steps": e2e_steps, "timing": "wall clock around sift_detect_and_describe_batch, pinned host frames",
+                    "d2h_bytes_per_step": int(nk_total // max(e2e_steps, 1)) * 26 + int(nd_total // max(e2e_steps, 1)) * 136
+                                          + len(chunks) * (24 + 3 * 4 * (7 * chunk + 1)),
+                    "steps": e2e_steps,
+                    "timing": "wall clock around sift_submit / sift_wait with two calls in flight, pinned host frames, "
+                              "result columns in pinned host memory" + (", shards gathered on rank 0 through shared memory"
+                                                                        if gather is not None else ""),
                     "ms_per_step": 1000.0 * e2e_s_max / e2e_steps,
-                    "device_stage_ms_per_step": {k2: float(v) / e2e_steps for k2, v in zip(
-                        ("seed_incl_upload_wait", "pyramid", "extrema", "refine", "orientation", "descriptor"), e2e_stage)}},
+                    "sync_call": {"value": frames_per_step_job * sync_steps / sync_s_max, "steps": sync_steps,
+                                  "ms_per_step": 1000.0 * sync_s_max / sync_steps,
+                                  "timing": "wall clock around sift_detect_and_describe_batch, one call at a time"},
+                    "gather": gathered},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
         if not (args.no_cpu_baseline or args.quick):
             reps = 8 if w * h <= 1920 * 1080 else 1
-            spf, cores, n = time_oracle(w, h, frames[:4], 0, reps)
+            bgra = frames if not gray else make_frames(w, h, min(n_local, 4), first_index=first)
+            spf, cores, n = time_oracle(w, h, bgra[:4], 0, reps)
             line["cpu_baseline"] = {"value": 1.0 / spf, "unit": "frames/s", "cores": cores, "kind": "port",
+                                    "cpu": cpu_model(),
                                     "sample": f"{n} x one {w}x{h} frame of the same workload, OpenMP {cores} threads"}
+            if w * h <= 1920 * 1080:
+                spf1, _, n1 = time_oracle(w, h, bgra[:2], 1, 2)
+                line["cpu_baseline"]["single_thread"] = {"value": 1.0 / spf1, "cores": 1,
+                                                         "sample": f"{n1} x one {w}x{h} frame, 1 thread"}
         print(json.dumps(line))
+    if gather is not None:
+        gather.close()
     eng.close()
     if distributed:
         dist.destroy_process_group()

@@ -865,4 +865,61 @@ void oracle_math(int op, const float* a, const float* b, float* out, int64_t n) 
     }
 }
 
+// SIFTDescriptor.match(source:target:absoluteThreshold:relativeThreshold:)
+// (SIFTDescriptor.swift:298-361): for every source descriptor a linear scan over the targets in
+// order, `if distance < best { second = best; best = distance; match = t }` (:339-343) — so
+// `second` is the best seen BEFORE the last improvement, not the second smallest distance, and it
+// starts as .greatestFiniteMagnitude (:332-333); kept iff best < absoluteThreshold and
+// best < second * relativeThreshold (:353-359). distance = sqrt(distanceSquared) (Vector.swift:
+// 237-239) of indexValue = features / 255 re-ordered cell by cell (SIFTDescriptor.swift:37-80; a
+// permutation, it does not change a distance).
+//
+// Oracle-defined where the reference is unspecified: distanceSquared is vDSP.distanceSquared
+// (Accelerate, closed source, summation order and vector width unspecified, Vector.swift:234) on
+// floats that are themselves rounded quotients f / 255. Every feature is an integer 0...255, so
+// the exact value is sum((b - a)^2) / 255^2 with an integer numerator below 2^24: the oracle
+// compares candidates by that exact integer (the order any correctly rounded evaluation gives
+// except for ties in the last bit) and evaluates the two threshold tests on
+// distance = sqrtf(float(numerator)) / 255.0f, single IEEE operations.
+// Output: kept correspondences in source order; returns their number.
+int64_t oracle_match(const uint8_t* source, int64_t nSource, const uint8_t* target, int64_t nTarget,
+                     float absoluteThreshold, float relativeThreshold, SiftMatch* out) {
+    std::vector<SiftMatch> rows((size_t)std::max<int64_t>(nSource, 1));
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < nSource; i++) {
+        const uint8_t* a = source + i * 128;
+        const int32_t none = INT32_MAX;
+        int32_t best = none, second = none;
+        int64_t match = -1;
+        for (int64_t j = 0; j < nTarget; j++) {
+            const uint8_t* b = target + j * 128;
+            int32_t d2 = 0;
+            for (int k = 0; k < 128; k++) {
+                const int32_t d = (int32_t)b[k] - (int32_t)a[k];
+                d2 += d * d;
+            }
+            if (d2 < best) {
+                second = best;
+                best = d2;
+                match = j;
+            }
+        }
+        SiftMatch r;
+        r.source = (int32_t)i;
+        r.target = -1;
+        r.distance = 0.0f;
+        if (match >= 0) {   // `guard let bestMatch`, `guard let secondBestMatchDistance` (:346-352)
+            const float dBest = std::sqrt((float)best) / 255.0f;
+            const float dSecond = second == none ? 3.402823466e+38f : std::sqrt((float)second) / 255.0f;
+            r.distance = dBest;
+            if (dBest < absoluteThreshold && dBest < (dSecond * relativeThreshold)) r.target = (int32_t)match;
+        }
+        rows[(size_t)i] = r;
+    }
+    int64_t n = 0;
+    for (int64_t i = 0; i < nSource; i++)
+        if (rows[(size_t)i].target >= 0) out[n++] = rows[(size_t)i];
+    return n;
+}
+
 }  // extern "C"

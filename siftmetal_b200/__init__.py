@@ -8,7 +8,11 @@ missing or no sm_100 device is usable — there is no CPU fallback.
 from . import _abi  # noqa: F401
 from .api import (  # noqa: F401
     BatchResult,
+    DescriptorColumns,
     Engine,
+    KeypointColumns,
+    LazyDescriptorList,
+    LazyKeypointList,
     IntegralSize,
     IntVector,
     SIFT,
@@ -21,5 +25,6 @@ from .api import (  # noqa: F401
 
 __all__ = [
     "SIFT", "SIFTKeypoint", "SIFTDescriptor", "IntVector", "IntegralSize", "Engine", "BatchResult",
+    "KeypointColumns", "DescriptorColumns", "LazyKeypointList", "LazyDescriptorList",
     "SiftError", "load_library", "device_math",
 ]

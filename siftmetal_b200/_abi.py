@@ -22,8 +22,10 @@ SIFT_ERR_CUDA = 3
 SIFT_ERR_CAPACITY = 4
 SIFT_ERR_NOT_DETECTED = 5
 SIFT_ERR_OUT_OF_MEMORY = 6
+SIFT_ERR_BUSY = 7
 
-FLAG_KEEP_PYRAMID = 1
+INPUT_BGRA8, INPUT_GRAY8, INPUT_NV12 = 0, 1, 2
+INPUT_BYTES_PER_PIXEL = {INPUT_BGRA8: 4, INPUT_GRAY8: 1, INPUT_NV12: 1}
 
 PLANE_GRAY, PLANE_SEED, PLANE_GAUSSIAN, PLANE_DOG, PLANE_GRADIENT = range(5)
 
@@ -46,7 +48,8 @@ class SiftConfig(C.Structure):
         ("max_candidates_per_frame", C.c_int32),
         ("max_keypoints_per_frame", C.c_int32),
         ("max_descriptors_per_frame", C.c_int32),
-        ("flags", C.c_int32),
+        ("input_format", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -83,21 +86,49 @@ class SiftTimings(C.Structure):
         ("blur_octave0_launches", C.c_int32),
         ("kernel_launches", C.c_int32),
         ("stage_timing_enabled", C.c_int32),
+        ("graph_replay", C.c_int32),
+    ]
+
+
+class SiftKeypointColumns(C.Structure):
+    _fields_ = [
+        ("absolute_x", C.c_void_p),
+        ("absolute_y", C.c_void_p),
+        ("sigma", C.c_void_p),
+        ("value", C.c_void_p),
+        ("sub_scale", C.c_void_p),
+        ("scaled_xy", C.c_void_p),
+        ("octave_scale", C.c_void_p),
+    ]
+
+
+class SiftDescriptorColumns(C.Structure):
+    _fields_ = [
+        ("features", C.c_void_p),
+        ("theta", C.c_void_p),
+        ("keypoint", C.c_void_p),
     ]
 
 
 class SiftBatchResult(C.Structure):
     _fields_ = [
         ("n_frames", C.c_int32),
+        ("status", C.c_int32),
         ("keypoint_counts", C.POINTER(C.c_int32)),
         ("descriptor_counts", C.POINTER(C.c_int32)),
         ("candidate_counts", C.POINTER(C.c_int32)),
-        ("keypoints", C.c_void_p),
-        ("descriptors", C.c_void_p),
         ("total_keypoints", C.c_int64),
         ("total_descriptors", C.c_int64),
+        ("keypoints", SiftKeypointColumns),
+        ("descriptors", SiftDescriptorColumns),
     ]
 
+
+class SiftMatch(C.Structure):
+    _fields_ = [("source", C.c_int32), ("target", C.c_int32), ("distance", C.c_float)]
+
+
+MATCH_DTYPE = np.dtype([("source", "<i4"), ("target", "<i4"), ("distance", "<f4")])
 
 # numpy views of the result PODs
 KEYPOINT_DTYPE = np.dtype(

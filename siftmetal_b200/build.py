@@ -24,9 +24,10 @@ SOURCES = {
     "pyramid.cu": ["-fmad=false"],
     "detect.cu": ["-fmad=false"],
     "describe.cu": (["-DSIFT_DEBUG_DESC"] if os.environ.get("SIFT_DEBUG_DESC") else []),
+    "match.cu": [],
     "capi.cu": [],
 }
-HEADERS = ["common.cuh", "dev_math.cuh", "scan.cuh", os.path.join(ROOT, "include", "siftcuda.h")]
+HEADERS = ["common.cuh", "dev_math.cuh", "scan.cuh", "capi_match.inc", os.path.join(ROOT, "include", "siftcuda.h")]
 
 
 def nvcc():
@@ -69,7 +70,7 @@ def build(force=False, verbose=False):
             if r.returncode != 0:
                 raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
     if jobs or force or _stale(LIB, objs):
-        cmd = [cc] + ARCH + ["-shared", "-o", LIB] + objs + ["-cudart", "static"]
+        cmd = [cc] + ARCH + ["-shared", "-o", LIB] + objs + ["-cudart", "static", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

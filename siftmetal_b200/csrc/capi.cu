@@ -3,8 +3,14 @@
 //   DifferenceOfGaussians.init / Octave.init   (DifferenceOfGaussians.swift:233-344, :69-147)
 //   GaussianKernel / GaussianSeriesKernel taps (GaussianKernel.swift:20-43, GaussianSeriesKernel.swift:27-51)
 //   SIFT.getKeypoints / getDescriptors         (SIFT.swift:147-238)
-// One context = one device, one stream; every call is synchronous at return. There is no CPU
-// path: without a usable sm_100 device every compute entry point fails.
+// One context = one device, one compute stream (+ forked octave / band streams) and one copy
+// stream. A call's whole device work — ~70 kernels on a fork / join DAG of streams — is recorded
+// once per (slot, batch size, input) as a CUDA graph and replayed with a single launch, the way
+// the reference encodes its 102 dispatches into one command buffer (SIFT.swift:157-172). Results
+// leave the device through the kernels' own stores into pinned host columns, so nothing but a
+// 24-byte counter block and the segment starts is copied after the last kernel. Two in-flight
+// slots (input arena + result columns each) let the upload of call i + 1 run under the kernels of
+// call i. There is no CPU path: without a usable sm_100 device every compute entry point fails.
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -15,20 +21,67 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "common.cuh"
 
 using namespace sift;
+
+namespace {
+
+// NVTX range named like the reference's measure(name:) sites (Utilities/Performance.swift:12-20;
+// SIFT.swift:155,179,192,212,226). Host-side: the range covers the enqueue of that stage.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
+struct ResultColumns {
+    KeypointColumnsDev kp{};
+    DescriptorColumnsDev desc{};
+};
+
+// One in-flight call: its input arena, its pinned result columns and bookkeeping.
+struct Slot {
+    uint8_t* dInput = nullptr;          // device input arena (max_batch frames)
+    bool allocated = false;
+    ResultColumns host{};               // pinned host memory, device-addressable (UVA)
+    Counters* hCounters = nullptr;      // pinned
+    int* hSegStarts = nullptr;          // pinned: [3][nSegs + 1] candidates, keypoints, descriptors
+    cudaEvent_t evUploaded = nullptr, evStart = nullptr, evEnd = nullptr;
+    int frames = 0;
+    bool pending = false, described = false, hostOut = false, graphReplay = false, staged = false;
+    int launches = 0;
+    std::vector<int32_t> kpCounts, descCounts, candCounts;
+    int64_t nKp = 0, nDesc = 0;
+    int status = SIFT_OK;
+};
+
+struct GraphEntry {
+    int slot = 0, frames = 0, pitch = 0;
+    const void* input = nullptr;
+    int64_t frameStride = 0;
+    bool describe = false, hostOut = false;
+    int seen = 0;                       // calls with this key so far (the first one runs eagerly)
+    cudaGraphExec_t exec = nullptr;
+    int launches = 0;
+    uint64_t lastUse = 0;
+};
+
+}  // namespace
 
 struct SiftContext {
     SiftConfig cfg{};
     int device = 0;
     int smCount = 0;
+    int bytesPerPixel = 4;
     cudaStream_t stream = nullptr;
+    cudaStream_t copyStream = nullptr;
     // octave o >= 1 runs its blur chain + gradient + extrema mask on its own stream as soon as
     // octave o-1 has produced Gaussian slice 3 (fork / join around the main stream)
     cudaStream_t octStream[kOctaves]{};
 
-    // Large octaves are split into two row bands that run as independent chains of blur launches
+    // Large octaves are split into row bands that run as independent chains of blur launches
     // (each band recomputes the few halo rows the later scales need, so there is no dependency
     // between the bands): the fixed cost of a launch — latency, first wave's exposed tile load,
     // partial last wave — of one chain hides under the other chain's work.
@@ -53,71 +106,49 @@ struct SiftContext {
     // device memory
     std::vector<void*> allocations;
     int64_t deviceBytes = 0;
-    uint8_t* dInput = nullptr;
     float* dGray = nullptr;
     float* dScaled = nullptr;
-    int pitch2 = 0;
     uint32_t* dMask = nullptr;
-    // Device lists + their bookkeeping. Two sets: on a single large frame octave 0 is compacted,
-    // refined and described from set 0 as soon as its extrema mask exists, while the deeper
-    // octaves (a long latency-bound chain of small launches) are still running; they follow from
-    // set 1. Batches and the two-step API use set 0 alone.
-    struct ListSet {
-        int* dBlockSums = nullptr;
-        Candidate* dCands = nullptr;
-        SiftKeypoint* dKpTmp = nullptr;
-        uint32_t* dFlagWords = nullptr;
-        SiftKeypoint* dKps = nullptr;
-        int* dKpSeg = nullptr;
-        int* dSegStarts = nullptr;  // [3][nSegs + 1]: candidates, keypoints, descriptors
-        int* dNOri = nullptr;
-        float* dOriTmp = nullptr;
-        int* dOriOffset = nullptr;
-        int* dDescKp = nullptr;
-        SiftDescriptor* dDesc = nullptr;
-        Counters* dCounters = nullptr;
-        Counters* hCounters = nullptr;   // pinned
-        int* hSegStarts = nullptr;       // pinned
-    } L[2];
-    // Host-resident results (the fused host-buffer entry points): the descriptor kernel stores its
-    // 136-byte records straight into the pinned result array over PCIe while it runs, and the
-    // keypoints leave on a copy stream as soon as refinement has counted them — no D2H pass after
-    // the last kernel.
-    // A large single frame is uploaded in two row chunks on the copy stream; the seed stage and
-    // octave 0's first row band run on chunk A while chunk B is still crossing PCIe.
-    // One upload chunk per row band: chunk k ends with the last input row band k's chain needs.
-    // grayRows / upRows / seedRows[k] = input rows uploaded / upsampled rows / seed rows complete once
-    // chunks 0..k are in (cumulative; the last chunk completes the planes). n = 0: whole frame at once.
-    struct SeedSplit { int n = 0; int grayRows[kMaxBands] = {}, upRows[kMaxBands] = {}, seedRows[kMaxBands] = {}; } upSplit;
-    cudaEvent_t evBandBlurEnd[kMaxBands]{};   // timing: end of each band's blur chain
-    cudaEvent_t evUp[kMaxBands]{};
-    cudaEvent_t evSeedDone[kMaxBands]{};
-    bool countersClean = false;      // both sets' device counters were zeroed after the last call
-    bool wantHostOut = false;        // request for the next runDetect / describe
-    bool descOnHost = false;         // last describe wrote c->hDesc directly
-    bool kpsOnHost = false;          // last detect's keypoints were already copied to c->hKps
-    cudaStream_t copyStream = nullptr;
-    cudaEvent_t evRefined = nullptr, evKpCopied = nullptr;
-    bool split = false;              // results of the last call live in both sets
-    bool candSplit = false;          // the last detect put octaves >= 1 in set 1 (debug taps)
-    cudaEvent_t evB[5]{};            // stage boundaries of set 1's pass
+    int* dBlockSums = nullptr;
+    Candidate* dCands = nullptr;
+    SiftKeypoint* dKpTmp = nullptr;
+    uint32_t* dFlagWords = nullptr;
+    SiftKeypoint* dKps = nullptr;
+    int* dKpSeg = nullptr;
+    int* dSegStarts = nullptr;  // [3][nSegs + 1]: candidates, keypoints, descriptors
+    int* dNOri = nullptr;
+    float* dOriTmp = nullptr;
+    int* dOriOffset = nullptr;
+    int* dDescKp = nullptr;
+    Counters* dCounters = nullptr;
+    ResultColumns dev{};        // device result columns (staged path, device-side matching)
 
-    // pinned host memory
-    SiftKeypoint* hKps = nullptr;
-    SiftDescriptor* hDesc = nullptr;
-    int* hKpSeg = nullptr;
-    std::vector<int32_t> kpCounts, descCounts, candCounts;
+    Slot slot[2];
+    int head = 0, next = 0, nPending = 0;
+    Slot* last = nullptr;       // slot holding the results of the last completed call
 
-    // current input
+    // staged path input
     const uint8_t* curInput = nullptr;
     int curPitch = 0;
     int64_t curFrameStride = 0;
     int curFrames = 0;
-    bool executed = false;   // pyramid + gradients of curFrames frames are on the device
-    bool described = false;
+    bool executed = false;      // pyramid + gradients of the last call are on the device
+
+    // CUDA graphs
+    bool graphsEnabled = true;
+    std::vector<GraphEntry> graphs;
+    uint64_t useCounter = 0;
+
+    // record-shaped views for the reference's two-step API (sift_detect / sift_describe)
+    std::vector<SiftKeypoint> kpRecords;
+    std::vector<SiftDescriptor> descRecords;
+    std::vector<int> kpSegHost;
+
+    // matching
+    void* matcher = nullptr;
 
     // timing
-    bool stageTiming = true;
+    bool stageTiming = false;
     cudaEvent_t ev[SIFT_STAGE_COUNT + 1]{};
     cudaEvent_t evBlur0[kGaussians]{};
     SiftTimings timings{};
@@ -176,20 +207,69 @@ cudaError_t devAlloc(SiftContext* c, T** p, size_t count) {
     return cudaSuccess;
 }
 
-// Octave 0 of a large single frame runs as independent row-band blur chains (runDetect).
+size_t alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Result columns carved out of one block (device or pinned host): every column 256-byte aligned.
+size_t columnsBytes(size_t capKp, size_t capDesc) {
+    size_t b = 0;
+    b += 5 * alignUp(capKp * sizeof(float), 256);
+    b += alignUp(capKp * sizeof(short2), 256);
+    b += alignUp(capKp * sizeof(uchar2), 256);
+    b += alignUp(capDesc * 128, 256);
+    b += 2 * alignUp(capDesc * 4, 256);
+    return std::max<size_t>(b, 256);
+}
+ResultColumns carveColumns(void* block, size_t capKp, size_t capDesc) {
+    ResultColumns r;
+    char* p = (char*)block;
+    auto take = [&](size_t bytes) { char* q = p; p += alignUp(bytes, 256); return q; };
+    r.kp.absX = (float*)take(capKp * 4);
+    r.kp.absY = (float*)take(capKp * 4);
+    r.kp.sigma = (float*)take(capKp * 4);
+    r.kp.value = (float*)take(capKp * 4);
+    r.kp.subScale = (float*)take(capKp * 4);
+    r.kp.scaledXY = (short2*)take(capKp * sizeof(short2));
+    r.kp.octaveScale = (uchar2*)take(capKp * sizeof(uchar2));
+    r.desc.features = (uint8_t*)take(capDesc * 128);
+    r.desc.theta = (float*)take(capDesc * 4);
+    r.desc.keypoint = (int32_t*)take(capDesc * 4);
+    return r;
+}
+
+// Slot resources: slot 0 at create, slot 1 at the first call that needs two calls in flight.
+int ensureSlot(SiftContext* c, int s) {
+    Slot& S = c->slot[s];
+    if (S.allocated) return SIFT_OK;
+    const size_t frameBytes = (size_t)c->cfg.width * c->cfg.height * c->bytesPerPixel;
+    cudaError_t e = cudaSuccess;
+    auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    A(devAlloc(c, &S.dInput, (size_t)c->B * frameBytes));
+    void* block = nullptr;
+    A(cudaMallocHost(&block, columnsBytes((size_t)c->capKp, (size_t)c->capDesc)));
+    if (e == cudaSuccess) S.host = carveColumns(block, (size_t)c->capKp, (size_t)c->capDesc);
+    A(cudaMallocHost(&S.hCounters, sizeof(Counters)));
+    A(cudaMallocHost(&S.hSegStarts, 3 * (size_t)(c->nSegs + 1) * sizeof(int)));
+    A(cudaEventCreateWithFlags(&S.evUploaded, cudaEventDisableTiming));
+    A(cudaEventCreate(&S.evStart));
+    A(cudaEventCreate(&S.evEnd));
+    if (e != cudaSuccess)
+        return fail(c, e == cudaErrorMemoryAllocation ? SIFT_ERR_OUT_OF_MEMORY : SIFT_ERR_CUDA, "slot allocation", e);
+    memset(S.hCounters, 0, sizeof(Counters));
+    memset(S.hSegStarts, 0, 3 * (size_t)(c->nSegs + 1) * sizeof(int));
+    S.kpCounts.assign(c->nSegs, 0);
+    S.descCounts.assign(c->nSegs, 0);
+    S.candCounts.assign(c->nSegs, 0);
+    S.allocated = true;
+    c->info.device_bytes = c->deviceBytes;
+    return SIFT_OK;
+}
+
+// Octave 0 of a large single frame runs as independent row-band blur chains (enqueuePipeline).
 bool bandedOctave0(const SiftContext* c, int frames) {
     const OctaveDev& q = c->P.oct[0];
     const long tiles = (long)((q.w + 63) / 64) * ((q.h + 63) / 64) * frames;
     const int nb = c->nBands;
     return frames == 1 && nb > 1 && tiles >= 8L * c->smCount && q.h >= 256 * nb;
-}
-// Gradient field and extrema mask of octave 0 per row band, right behind that band's blur chain
-// (each band then carries one more halo row: the mask of its edge rows reads the DoG row beyond).
-bool bandTails() {
-    // measured at 1080p: 1065 vs 1058 frames/s device-resident, 864 vs 872 end to end (the e2e
-    // critical path is upload -> last band's first three blurs -> octave 1 .. 6) — opt-in
-    static const bool on = getenv("SIFTCUDA_BAND_TAILS") && atoi(getenv("SIFTCUDA_BAND_TAILS")) != 0;
-    return on;
 }
 int bandBoundary(const SiftContext* c, int band) {   // first row of `band` (multiple of the tile height)
     const OctaveDev& q = c->P.oct[0];
@@ -197,51 +277,30 @@ int bandBoundary(const SiftContext* c, int band) {   // first row of `band` (mul
     return (int)(((long)q.h * band / c->nBands + 63) / 64 * 64);
 }
 
-// Rows of the input / upsampled / seed image that band 0's chain depends on: everything the
-// first upload chunk must deliver.
-SiftContext::SeedSplit seedSplitFor(const SiftContext* c, int frames) {
-    SiftContext::SeedSplit sp;
-    static const bool enabled = !(getenv("SIFTCUDA_UPLOAD_SPLIT") && atoi(getenv("SIFTCUDA_UPLOAD_SPLIT")) == 0);
-    if (!enabled || !bandedOctave0(c, frames)) return sp;
-    const OctaveDev& q = c->P.oct[0];
-    const int nb = c->nBands, H = c->cfg.height;
-    int sumR = 0;
-    for (int t = 0; t < kGaussians - 1; t++) sumR += c->ntaps[t] / 2;
-    for (int k = 0; k < nb; k++) {
-        if (k + 1 == nb) {
-            sp.seedRows[k] = q.h; sp.upRows[k] = q.h; sp.grayRows[k] = H;
-        } else {
-            sp.seedRows[k] = bandBoundary(c, k + 1) + sumR + (bandTails() ? 1 : 0);
-            sp.upRows[k] = (sp.seedRows[k] + c->seedNtaps / 2 + 1) & ~1;   // even: whole gray rows (fused kernel)
-            sp.grayRows[k] = sp.upRows[k] / 2 + 1;                         // input rows 0 .. upRows / 2
-            const bool grows = k == 0 || (sp.grayRows[k] > sp.grayRows[k - 1] && sp.seedRows[k] > sp.seedRows[k - 1]);
-            if (!grows || sp.seedRows[k] >= q.h || sp.upRows[k] >= q.h || sp.grayRows[k] >= H) return SiftContext::SeedSplit{};
-        }
-    }
-    sp.n = nb;
-    return sp;
-}
+void destroyMatcher(SiftContext* c);
 
 void destroy(SiftContext* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    // drain every stream of the context (a chunked upload may still be in flight on the copy stream)
+    // drain every stream of the context (an upload may still be in flight on the copy stream)
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copyStream) cudaStreamSynchronize(c->copyStream);
     for (int o = 1; o < kOctaves; o++)
         if (c->octStream[o]) cudaStreamSynchronize(c->octStream[o]);
     for (int b = 1; b < SiftContext::kMaxBands; b++)
         if (c->bandStream[b]) cudaStreamSynchronize(c->bandStream[b]);
+    destroyMatcher(c);
+    for (auto& g : c->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
     for (void* p : c->allocations) cudaFree(p);
-    for (int k = 0; k < 2; k++) {
-        if (c->L[k].hCounters) cudaFreeHost(c->L[k].hCounters);
-        if (c->L[k].hSegStarts) cudaFreeHost(c->L[k].hSegStarts);
+    for (auto& S : c->slot) {
+        if (S.host.kp.absX) cudaFreeHost(S.host.kp.absX);   // first column = start of the block
+        if (S.hCounters) cudaFreeHost(S.hCounters);
+        if (S.hSegStarts) cudaFreeHost(S.hSegStarts);
+        if (S.evUploaded) cudaEventDestroy(S.evUploaded);
+        if (S.evStart) cudaEventDestroy(S.evStart);
+        if (S.evEnd) cudaEventDestroy(S.evEnd);
     }
-    for (auto& e : c->evB)
-        if (e) cudaEventDestroy(e);
-    if (c->hKps) cudaFreeHost(c->hKps);
-    if (c->hDesc) cudaFreeHost(c->hDesc);
-    if (c->hKpSeg) cudaFreeHost(c->hKpSeg);
     for (auto& e : c->ev)
         if (e) cudaEventDestroy(e);
     for (auto& e : c->evBlur0)
@@ -250,7 +309,6 @@ void destroy(SiftContext* c) {
         if (c->evSeeded[o]) cudaEventDestroy(c->evSeeded[o]);
         if (c->evOctDone[o]) cudaEventDestroy(c->evOctDone[o]);
         if (o > 0 && c->octStream[o]) cudaStreamDestroy(c->octStream[o]);
-
     }
     for (int b = 1; b < SiftContext::kMaxBands; b++) {
         if (c->bandStream[b]) cudaStreamDestroy(c->bandStream[b]);
@@ -258,18 +316,12 @@ void destroy(SiftContext* c) {
         if (c->evBandDone[b]) cudaEventDestroy(c->evBandDone[b]);
     }
     if (c->evBandFork) cudaEventDestroy(c->evBandFork);
-    for (auto& e : c->evUp)
-        if (e) cudaEventDestroy(e);
-    for (auto& e : c->evSeedDone)
-        if (e) cudaEventDestroy(e);
-    for (auto& e : c->evBandBlurEnd)
-        if (e) cudaEventDestroy(e);
-    if (c->evRefined) cudaEventDestroy(c->evRefined);
-    if (c->evKpCopied) cudaEventDestroy(c->evKpCopied);
     if (c->copyStream) cudaStreamDestroy(c->copyStream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
+
+bool finiteF(float v) { return v == v && v <= 3.0e38f && v >= -3.0e38f; }
 
 }  // namespace
 
@@ -289,6 +341,7 @@ int sift_config_default(SiftConfig* cfg, int32_t width, int32_t height) {
     cfg->lambda_orientation = 1.5f;
     cfg->orientation_threshold = 0.8f;
     cfg->orientation_smoothing_iterations = 6;
+    cfg->input_format = SIFT_INPUT_BGRA8;
     return SIFT_OK;
 }
 
@@ -301,6 +354,7 @@ const char* sift_status_string(int status) {
         case SIFT_ERR_CAPACITY: return "device list capacity exceeded (results truncated)";
         case SIFT_ERR_NOT_DETECTED: return "describe called before detect";
         case SIFT_ERR_OUT_OF_MEMORY: return "out of device memory";
+        case SIFT_ERR_BUSY: return "no free in-flight slot / nothing submitted";
         default: return "unknown status";
     }
 }
@@ -313,12 +367,28 @@ int sift_create(const SiftConfig* cfg, int device, SiftContext** out) {
     if (cfg->width < 8 || cfg->height < 8 || cfg->width > 16384 || cfg->height > 16384 ||
         cfg->max_batch < 1)
         return SIFT_ERR_INVALID_ARGUMENT;
+    // the 3x3x3 stencils of refinement read x - 1 .. x + 1 around every accepted position: a
+    // border below 1 would let them leave the plane (SIFTInterpolate.metal:180-190 uses 5)
+    if (cfg->image_border < 1 || cfg->image_border > 16384) return SIFT_ERR_INVALID_ARGUMENT;
+    if (!finiteF(cfg->dog_threshold) || !finiteF(cfg->edge_threshold) || !finiteF(cfg->max_offset) ||
+        !finiteF(cfg->lambda_orientation) || !finiteF(cfg->orientation_threshold) ||
+        cfg->edge_threshold <= 0.0f || cfg->lambda_orientation <= 0.0f || cfg->max_offset < 0.0f)
+        return SIFT_ERR_INVALID_ARGUMENT;
+    if (cfg->max_interpolation_iterations < 0 || cfg->max_interpolation_iterations > 1000 ||
+        cfg->orientation_smoothing_iterations < 0 || cfg->orientation_smoothing_iterations > 1000 ||
+        cfg->max_candidates_per_frame < 0 || cfg->max_keypoints_per_frame < 0 ||
+        cfg->max_descriptors_per_frame < 0 || cfg->reserved != 0)
+        return SIFT_ERR_INVALID_ARGUMENT;
+    if (cfg->input_format != SIFT_INPUT_BGRA8 && cfg->input_format != SIFT_INPUT_GRAY8 &&
+        cfg->input_format != SIFT_INPUT_NV12)
+        return SIFT_ERR_INVALID_ARGUMENT;
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count)
         return SIFT_ERR_NO_DEVICE;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SIFT_ERR_NO_DEVICE;
-    if (prop.major != 10) return SIFT_ERR_NO_DEVICE;  // the library carries sm_100a code only
+    // the library carries arch-specific sm_100a SASS only (no PTX): other 10.x parts cannot run it
+    if (prop.major != 10 || prop.minor != 0) return SIFT_ERR_NO_DEVICE;
     if (cudaSetDevice(device) != cudaSuccess) return SIFT_ERR_NO_DEVICE;
 
     SiftContext* c = new (std::nothrow) SiftContext();
@@ -328,6 +398,7 @@ int sift_create(const SiftConfig* cfg, int device, SiftContext** out) {
     c->smCount = prop.multiProcessorCount;
     c->B = cfg->max_batch;
     c->nSegs = c->B * kOctaves;
+    c->bytesPerPixel = cfg->input_format == SIFT_INPUT_BGRA8 ? 4 : 1;
     const int W = cfg->width, H = cfg->height;
 
     // ---- schedule: DifferenceOfGaussians.init (:233-344) ------------------------------------
@@ -414,9 +485,7 @@ int sift_create(const SiftConfig* cfg, int device, SiftContext** out) {
     auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
     A(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     const size_t B = (size_t)c->B;
-    A(devAlloc(c, &c->dInput, B * (size_t)W * H * 4));
     A(devAlloc(c, &c->dGray, B * (size_t)W * H));
-    c->pitch2 = c->P.oct[0].pitch;
     A(devAlloc(c, &c->dScaled, B * c->P.oct[0].plane));
     for (int o = 0; o < kOctaves; o++) {
         OctaveDev& q = c->P.oct[o];
@@ -429,20 +498,22 @@ int sift_create(const SiftConfig* cfg, int device, SiftContext** out) {
     const size_t flagWords = (size_t)c->capCand / 32 + 64;
     const size_t nBlockSums = std::max({B * (size_t)c->P.blocksPerFrame, (size_t)c->capCand / 256 + 2,
                                         (size_t)c->capKp / kScanChunk + 2}) + 16;
-    for (int k = 0; k < 2; k++) {   // set 1 only ever holds one frame's deeper octaves
-        A(devAlloc(c, &c->L[k].dBlockSums, nBlockSums));
-        A(devAlloc(c, &c->L[k].dCands, (size_t)c->capCand));
-        A(devAlloc(c, &c->L[k].dKpTmp, (size_t)c->capCand));
-        A(devAlloc(c, &c->L[k].dFlagWords, flagWords));
-        A(devAlloc(c, &c->L[k].dKps, (size_t)c->capKp));
-        A(devAlloc(c, &c->L[k].dKpSeg, (size_t)c->capKp));
-        A(devAlloc(c, &c->L[k].dSegStarts, 3 * (size_t)(c->nSegs + 1)));
-        A(devAlloc(c, &c->L[k].dNOri, (size_t)c->capKp + kScanChunk));
-        A(devAlloc(c, &c->L[k].dOriTmp, (size_t)c->capKp * kOriBins));
-        A(devAlloc(c, &c->L[k].dOriOffset, (size_t)c->capKp + kScanChunk + 1));
-        A(devAlloc(c, &c->L[k].dDesc, (size_t)c->capDesc));
-        A(devAlloc(c, &c->L[k].dDescKp, (size_t)c->capDesc));
-        A(devAlloc(c, &c->L[k].dCounters, 1));
+    A(devAlloc(c, &c->dBlockSums, nBlockSums));
+    A(devAlloc(c, &c->dCands, (size_t)c->capCand));
+    A(devAlloc(c, &c->dKpTmp, (size_t)c->capCand));
+    A(devAlloc(c, &c->dFlagWords, flagWords));
+    A(devAlloc(c, &c->dKps, (size_t)c->capKp));
+    A(devAlloc(c, &c->dKpSeg, (size_t)c->capKp));
+    A(devAlloc(c, &c->dSegStarts, 3 * (size_t)(c->nSegs + 1)));
+    A(devAlloc(c, &c->dNOri, (size_t)c->capKp + kScanChunk));
+    A(devAlloc(c, &c->dOriTmp, (size_t)c->capKp * kOriBins));
+    A(devAlloc(c, &c->dOriOffset, (size_t)c->capKp + kScanChunk + 1));
+    A(devAlloc(c, &c->dDescKp, (size_t)c->capDesc));
+    A(devAlloc(c, &c->dCounters, 1));
+    {
+        char* block = nullptr;
+        A(devAlloc(c, &block, columnsBytes((size_t)c->capKp, (size_t)c->capDesc)));
+        if (e == cudaSuccess) c->dev = carveColumns(block, (size_t)c->capKp, (size_t)c->capDesc);
     }
     if (e == cudaSuccess) A(cudaMemset(c->dMask, 0, maskWords * sizeof(uint32_t)));
     // row padding (columns w..pitch) is read by the extrema kernel's full-warp loads and masked
@@ -454,20 +525,8 @@ int sift_create(const SiftConfig* cfg, int device, SiftContext** out) {
         A(cudaMemset(q.grad, 0, B * kScales * q.plane * sizeof(float2)));
     }
     if (e == cudaSuccess) A(cudaMemset(c->dScaled, 0, B * c->P.oct[0].plane * sizeof(float)));
-    for (int k = 0; k < 2 && e == cudaSuccess; k++)
-        A(cudaMemset(c->L[k].dSegStarts, 0, 3 * (size_t)(c->nSegs + 1) * sizeof(int)));
-    for (int k = 0; k < 2; k++) {
-        A(cudaMallocHost(&c->L[k].hCounters, sizeof(Counters)));
-        A(cudaMallocHost(&c->L[k].hSegStarts, 3 * (size_t)(c->nSegs + 1) * sizeof(int)));
-        if (e == cudaSuccess) {
-            memset(c->L[k].hCounters, 0, sizeof(Counters));
-            memset(c->L[k].hSegStarts, 0, 3 * (size_t)(c->nSegs + 1) * sizeof(int));
-        }
-    }
-    for (auto& evn : c->evB) A(cudaEventCreate(&evn));
-    A(cudaMallocHost(&c->hKps, std::max<size_t>((size_t)c->capKp * sizeof(SiftKeypoint), 64)));
-    A(cudaMallocHost(&c->hDesc, std::max<size_t>((size_t)c->capDesc * sizeof(SiftDescriptor), 64)));
-    A(cudaMallocHost(&c->hKpSeg, std::max<size_t>((size_t)c->capKp * sizeof(int), 64)));
+    if (e == cudaSuccess) A(cudaMemset(c->dSegStarts, 0, 3 * (size_t)(c->nSegs + 1) * sizeof(int)));
+    if (e == cudaSuccess) A(cudaMemset(c->dCounters, 0, sizeof(Counters)));
     for (auto& evn : c->ev) A(cudaEventCreate(&evn));
     for (auto& evn : c->evBlur0) A(cudaEventCreate(&evn));
     int prioLow = 0, prioHigh = 0;
@@ -475,17 +534,13 @@ int sift_create(const SiftConfig* cfg, int device, SiftContext** out) {
     c->octStream[0] = c->stream;
     A(cudaEventCreateWithFlags(&c->evBandFork, cudaEventDisableTiming));
     A(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
-    A(cudaEventCreateWithFlags(&c->evRefined, cudaEventDisableTiming));
-    for (auto& evn : c->evUp) A(cudaEventCreateWithFlags(&evn, cudaEventDisableTiming));
-    for (auto& evn : c->evSeedDone) A(cudaEventCreateWithFlags(&evn, cudaEventDisableTiming));
-    for (auto& evn : c->evBandBlurEnd) A(cudaEventCreate(&evn));
-    A(cudaEventCreateWithFlags(&c->evKpCopied, cudaEventDisableTiming));
     for (int b = 1; b < SiftContext::kMaxBands; b++) {
         A(cudaStreamCreateWithFlags(&c->bandStream[b], cudaStreamNonBlocking));
         A(cudaEventCreateWithFlags(&c->evBandSeeded[b], cudaEventDisableTiming));
         A(cudaEventCreateWithFlags(&c->evBandDone[b], cudaEventDisableTiming));
     }
     if (const char* nb = getenv("SIFTCUDA_BANDS")) c->nBands = std::max(1, std::min(SiftContext::kMaxBands, atoi(nb)));
+    if (const char* g = getenv("SIFTCUDA_GRAPH")) c->graphsEnabled = atoi(g) != 0;
     for (int o = 0; o < kOctaves; o++) {
         // smaller octaves form a long dependent chain of tiny launches: give their streams a higher
         // priority so that their CTAs are placed ahead of the big octave-0 kernels' when SM slots
@@ -493,7 +548,6 @@ int sift_create(const SiftConfig* cfg, int device, SiftContext** out) {
         if (o > 0) A(cudaStreamCreateWithPriority(&c->octStream[o], cudaStreamNonBlocking, std::max(prioHigh, prioLow - o)));
         A(cudaEventCreateWithFlags(&c->evSeeded[o], cudaEventDisableTiming));
         A(cudaEventCreateWithFlags(&c->evOctDone[o], cudaEventDisableTiming));
-
     }
     if (e != cudaSuccess) {
         const bool oom = (e == cudaErrorMemoryAllocation);
@@ -501,9 +555,12 @@ int sift_create(const SiftConfig* cfg, int device, SiftContext** out) {
         cudaGetLastError();
         return oom ? SIFT_ERR_OUT_OF_MEMORY : SIFT_ERR_CUDA;
     }
-    c->kpCounts.assign(c->nSegs, 0);
-    c->descCounts.assign(c->nSegs, 0);
-    c->candCounts.assign(c->nSegs, 0);
+    const int rs = ensureSlot(c, 0);
+    if (rs != SIFT_OK) {
+        destroy(c);
+        cudaGetLastError();
+        return rs;
+    }
     I.device_bytes = c->deviceBytes;
     *out = c;
     return SIFT_OK;
@@ -529,34 +586,419 @@ int sift_last_timings(const SiftContext* c, SiftTimings* out) {
     return SIFT_OK;
 }
 
-int sift_batch_upload(SiftContext* c, const void* const* images, int32_t n, int32_t pitchBytes) {
-    if (!c || !images || n < 1 || n > c->B || pitchBytes < c->cfg.width * 4)
-        return fail(c, SIFT_ERR_INVALID_ARGUMENT, "sift_batch_upload: bad arguments");
-    CTX_TRY(c, cudaSetDevice(c->device));
-    const size_t rowBytes = (size_t)c->cfg.width * 4;
+int sift_pending(const SiftContext* c) { return c ? c->nPending : 0; }
+
+}  // extern "C"
+
+namespace {
+
+struct RunArgs {
+    const uint8_t* input = nullptr;
+    int pitch = 0;
+    int64_t frameStride = 0;
+    int frames = 0;
+    bool withDescribe = true;
+    bool hostOut = false;        // keypoint / descriptor columns go to the slot's pinned arrays
+    Slot* slot = nullptr;
+};
+
+// getDescriptors (SIFT.swift:207-238) over the keypoints in c->dKps.
+int enqueueDescribe(SiftContext* c, const RunArgs& r, int nSegs, bool T) {
+    cudaStream_t st = c->stream;
+    NvtxRange range("getDescriptors(orientations) + getDescriptors(descriptors)");
+    const DescriptorColumnsDev none{};
+    CTX_TRY(c, launchDescribe(c->P, c->dKps, c->dKpSeg, c->capKp, c->dSegStarts + (c->nSegs + 1), c->dNOri, c->dOriTmp,
+                              c->dOriOffset, c->dDescKp, c->dBlockSums, c->dev.desc,
+                              r.hostOut ? r.slot->host.desc : none, c->capDesc, c->dSegStarts + 2 * (c->nSegs + 1),
+                              nSegs, c->dCounters, c->smCount, st, T ? c->ev[5] : nullptr));
+    c->launches += 5;
+    if (T) CTX_TRY(c, cudaEventRecord(c->ev[6], st));
+    return SIFT_OK;
+}
+
+// The bookkeeping blocks follow the last kernel into the slot's pinned memory.
+int enqueueReadback(SiftContext* c, const RunArgs& r) {
+    cudaStream_t st = c->stream;
+    const size_t segInts = 3 * (size_t)(c->nSegs + 1);
+    CTX_TRY(c, cudaMemcpyAsync(r.slot->hCounters, c->dCounters, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    CTX_TRY(c, cudaMemcpyAsync(r.slot->hSegStarts, c->dSegStarts, segInts * sizeof(int), cudaMemcpyDeviceToHost, st));
+    return SIFT_OK;
+}
+
+// findKeypoints + getKeypointsFromOctaves + interpolateKeypoints (SIFT.swift:154-202) and
+// getDescriptors (:207-238), all frames of the batch at once, no host synchronisation inside.
+// Everything is enqueued on c->stream and streams forked from / joined to it by events, so the
+// same code runs launch by launch or under stream capture.
+int enqueuePipeline(SiftContext* c, const RunArgs& r, bool T) {
+    const int F = r.frames;
+    cudaStream_t st = c->stream;
+    c->launches = 0;
+    CTX_TRY(c, cudaMemsetAsync(c->dCounters, 0, sizeof(Counters), st));
+    if (T) CTX_TRY(c, cudaEventRecord(c->ev[0], st));
+    {
+        NvtxRange range("findKeypoints");
+        // DifferenceOfGaussians.encodeSeedTexture (:357-389)
+        const OctaveDev& o0 = c->P.oct[0];
+        CTX_TRY(c, launchGrayUpsample(r.input, c->bytesPerPixel, r.pitch, r.frameStride, c->dGray, c->cfg.width,
+                                      c->cfg.height, c->dScaled, o0.w, o0.h, o0.pitch, o0.plane, F, st));
+        BlurArgs seed{};
+        seed.in = c->dScaled;
+        seed.out = o0.G;  // octave 0 slice 0 (the reference blits seed → slice 0, :176-188)
+        seed.w = o0.w; seed.h = o0.h; seed.pitch = o0.pitch;
+        seed.inFrameStride = o0.plane;
+        seed.outFrameStride = kGaussians * o0.plane;
+        seed.frames = F;
+        CTX_TRY(c, launchBlur(seed, c->seedTaps, c->seedNtaps, st));
+        c->launches += 2;
+        if (T) CTX_TRY(c, cudaEventRecord(c->ev[1], st));
+        // encodeOctaves (:391-406): Gaussian series + DoG; octave o+1 slice 0 = octave o slice 3
+        // decimated (fused into the blur that produces slice 3); SIFTOctave.encodeGradients (:190-196)
+        // and encodeExtrema (:183-189). Octaves form a fork/join DAG: octave o+1 starts on its own
+        // stream once octave o has written slice 3, so the small octaves (launch-latency bound) run
+        // under the large kernels of octaves 0 and 1 instead of after them.
+        bool forked[kOctaves] = {};
+        static const int dbgMaxOctave = getenv("SIFTCUDA_DEBUG_MAX_OCTAVE") ? atoi(getenv("SIFTCUDA_DEBUG_MAX_OCTAVE")) : kOctaves;
+        static const int dbgSkip = getenv("SIFTCUDA_DEBUG_SKIP") ? atoi(getenv("SIFTCUDA_DEBUG_SKIP")) : 0;  // 1 gradient, 2 extrema
+        for (int o = 0; o < kOctaves; o++) {
+            const OctaveDev& q = c->P.oct[o];
+            if (q.w < 1 || q.h < 1 || o > dbgMaxOctave) continue;
+            cudaStream_t so = c->octStream[o];
+            if (o > 0) {
+                CTX_TRY(c, cudaStreamWaitEvent(so, c->evSeeded[o - 1], 0));
+                if (o == 1 && c->bandedOctave0)
+                    for (int b = 1; b < c->nBands; b++) CTX_TRY(c, cudaStreamWaitEvent(so, c->evBandSeeded[b], 0));
+                forked[o] = true;
+            }
+            // row bands for a plane with many tiles (octave 0 of a large single frame); batches
+            // already have enough independent work per launch
+            const int nb = c->nBands;
+            const bool banded = (o == 0) && bandedOctave0(c, F);
+            if (T && o == 0) CTX_TRY(c, cudaEventRecord(c->evBlur0[0], so));
+            if (banded) {
+                CTX_TRY(c, cudaEventRecord(c->evBandFork, so));
+                for (int b = 1; b < nb; b++) CTX_TRY(c, cudaStreamWaitEvent(c->bandStream[b], c->evBandFork, 0));
+            }
+            for (int band = 0; band < (banded ? nb : 1); band++) {
+                cudaStream_t sb = band == 0 ? so : c->bandStream[band];
+                // band rows [r0, r1), boundaries on multiples of the tile height
+                const int r0 = banded ? bandBoundary(c, band) : 0;
+                const int r1 = banded ? bandBoundary(c, band + 1) : q.h;
+                for (int s = 0; s < kGaussians - 1; s++) {
+                    if (T && o == 0 && !banded && s > 0) CTX_TRY(c, cudaEventRecord(c->evBlur0[s], sb));
+                    BlurArgs a{};
+                    a.in = q.G + (size_t)s * q.plane;
+                    a.out = q.G + (size_t)(s + 1) * q.plane;
+                    a.dog = q.D + (size_t)s * q.plane;
+                    a.w = q.w; a.h = q.h; a.pitch = q.pitch;
+                    a.inFrameStride = a.outFrameStride = kGaussians * q.plane;
+                    a.dogFrameStride = kDogs * q.plane;
+                    if (banded) {
+                        // rows the later scales of this band still need: sum of their radii
+                        int halo = 0;
+                        for (int t = s + 1; t < kGaussians - 1; t++) halo += c->ntaps[t] / 2;
+                        a.yBegin = std::max(0, r0 - halo);
+                        a.yEnd = std::min(q.h, r1 + halo);
+                    }
+                    if (s + 1 == kScales && o + 1 < kOctaves && c->P.oct[o + 1].w >= 1 && c->P.oct[o + 1].h >= 1) {
+                        const OctaveDev& nx = c->P.oct[o + 1];
+                        a.half = nx.G;
+                        a.halfW = nx.w; a.halfH = nx.h; a.halfPitch = nx.pitch;
+                        a.halfFrameStride = kGaussians * nx.plane;
+                    }
+                    a.frames = F;
+                    // small planes: scale s + 1 launches under scale s (programmatic dependent launch)
+                    static const int pdlMaxTiles = getenv("SIFTCUDA_PDL_TILES") ? atoi(getenv("SIFTCUDA_PDL_TILES")) : 160;
+                    a.pdl = (s > 0 && !banded && (long)((q.w + 31) / 32) * ((q.h + 31) / 32) * F <= pdlMaxTiles) ? 1 : 0;
+                    CTX_TRY(c, launchBlur(a, c->taps[s], c->ntaps[s], sb));
+                    c->launches++;
+                    if (s + 1 == kScales) CTX_TRY(c, cudaEventRecord(band == 0 ? c->evSeeded[o] : c->evBandSeeded[band], sb));
+                }
+            }
+            if (banded) {   // join: gradient and extrema need every row
+                for (int b = 1; b < nb; b++) {
+                    CTX_TRY(c, cudaEventRecord(c->evBandDone[b], c->bandStream[b]));
+                    CTX_TRY(c, cudaStreamWaitEvent(so, c->evBandDone[b], 0));
+                }
+            }
+            if (o == 0) c->bandedOctave0 = banded;
+            if (T && o == 0) CTX_TRY(c, cudaEventRecord(c->evBlur0[kGaussians - 1], so));
+            if (!(dbgSkip & 1)) CTX_TRY(c, launchGradient(q, F, so));
+            c->launches++;
+            if (q.w >= 3 && q.h >= 3 && !(dbgSkip & 2)) {
+                CTX_TRY(c, launchExtremaMask(c->P, o, c->dMask, F, so));
+                c->launches++;
+            }
+            if (o > 0) CTX_TRY(c, cudaEventRecord(c->evOctDone[o], so));
+        }
+        for (int o = 1; o < kOctaves; o++)
+            if (forked[o]) CTX_TRY(c, cudaStreamWaitEvent(st, c->evOctDone[o], 0));
+    }
+    const int nSegs = F * kOctaves;
+    if (T) CTX_TRY(c, cudaEventRecord(c->ev[2], st));
+    {
+        // mask → ordered candidates (SIFTOctave.getKeypoints :198-203)
+        NvtxRange range("getKeypointsFromOctaves");
+        CTX_TRY(c, launchCandidateCompaction(c->P, c->dMask, c->dBlockSums, c->dCands, c->capCand, 0,
+                                             c->P.blocksPerFrame * F, c->dSegStarts, nSegs, c->dCounters, st));
+        c->launches += 3;
+        if (T) CTX_TRY(c, cudaEventRecord(c->ev[3], st));
+    }
+    {
+        // refined keypoints (interpolateKeypoints :205-288); the result columns of the keypoints are
+        // written by the scatter kernel (pinned host columns for the host-buffer calls)
+        NvtxRange range("interpolateKeypoints");
+        CTX_TRY(c, launchRefine(c->P, c->dCands, c->capCand, c->dKpTmp, c->dFlagWords, c->dBlockSums, c->dKps,
+                                c->dKpSeg, c->capKp, c->dSegStarts, c->dSegStarts + (c->nSegs + 1), nSegs,
+                                c->dCounters, r.hostOut ? r.slot->host.kp : c->dev.kp, st));
+        c->launches += 3;
+        if (T) CTX_TRY(c, cudaEventRecord(c->ev[4], st));
+    }
+    if (r.withDescribe) {
+        const int rd = enqueueDescribe(c, r, nSegs, T);
+        if (rd != SIFT_OK) return rd;
+    }
+    return enqueueReadback(c, r);
+}
+
+GraphEntry* findGraph(SiftContext* c, int slot, const RunArgs& r) {
+    for (auto& g : c->graphs)
+        if (g.slot == slot && g.frames == r.frames && g.input == (const void*)r.input && g.pitch == r.pitch &&
+            g.frameStride == r.frameStride && g.describe == r.withDescribe && g.hostOut == r.hostOut)
+            return &g;
+    if (c->graphs.size() >= 16) {   // evict the least recently used entry
+        size_t victim = 0;
+        for (size_t i = 1; i < c->graphs.size(); i++)
+            if (c->graphs[i].lastUse < c->graphs[victim].lastUse) victim = i;
+        if (c->graphs[victim].exec) cudaGraphExecDestroy(c->graphs[victim].exec);
+        c->graphs.erase(c->graphs.begin() + (long)victim);
+    }
+    GraphEntry g;
+    g.slot = slot; g.frames = r.frames; g.input = r.input; g.pitch = r.pitch; g.frameStride = r.frameStride;
+    g.describe = r.withDescribe; g.hostOut = r.hostOut;
+    c->graphs.push_back(g);
+    return &c->graphs.back();
+}
+
+// Runs the pipeline for one slot: as one CUDA graph launch when this (slot, input, batch size)
+// has been seen before, launch by launch otherwise (first call; per-stage timing requested;
+// SIFTCUDA_GRAPH=0). evStart / evEnd bracket the device work either way.
+int runSlot(SiftContext* c, int slotIndex, RunArgs r) {
+    Slot& S = c->slot[slotIndex];
+    r.slot = &S;
+    cudaStream_t st = c->stream;
+    const bool T = c->stageTiming;
+    S.frames = r.frames;
+    S.described = r.withDescribe;
+    S.hostOut = r.hostOut;
+    S.graphReplay = false;
+    CTX_TRY(c, cudaEventRecord(S.evStart, st));
+    GraphEntry* g = (c->graphsEnabled && !T) ? findGraph(c, slotIndex, r) : nullptr;
+    if (g) {
+        g->lastUse = ++c->useCounter;
+        g->seen++;
+        if (g->seen == 2 && !g->exec) {
+            // second call with this key: record the DAG once
+            cudaGraph_t graph = nullptr;
+            cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed);
+            int rp = SIFT_OK;
+            if (e == cudaSuccess) {
+                rp = enqueuePipeline(c, r, false);
+                e = cudaStreamEndCapture(st, &graph);
+            }
+            if (e == cudaSuccess && rp == SIFT_OK && graph) e = cudaGraphInstantiate(&g->exec, graph, 0);
+            if (graph) cudaGraphDestroy(graph);
+            if (e != cudaSuccess || rp != SIFT_OK || !g->exec) {
+                // capture is an optimisation: fall back to launching the same kernels one by one
+                cudaGetLastError();
+                g->exec = nullptr;
+                c->graphsEnabled = false;
+                fail(c, SIFT_ERR_CUDA, "CUDA graph capture failed; running launch by launch", e);
+            } else {
+                g->launches = c->launches;
+            }
+        }
+        if (g->exec) {
+            NvtxRange range("findKeypoints + getDescriptors (graph replay)");
+            CTX_TRY(c, cudaGraphLaunch(g->exec, st));
+            S.graphReplay = true;
+            S.launches = g->launches;
+            CTX_TRY(c, cudaEventRecord(S.evEnd, st));
+            return SIFT_OK;
+        }
+    }
+    const int rp = enqueuePipeline(c, r, T);
+    if (rp != SIFT_OK) return rp;
+    S.launches = c->launches;
+    CTX_TRY(c, cudaEventRecord(S.evEnd, st));
+    return SIFT_OK;
+}
+
+// Waits for the slot's device work; per-(frame, octave) counts, timings, overflow status.
+int finishSlot(SiftContext* c, Slot& S) {
+    CTX_TRY(c, cudaEventSynchronize(S.evEnd));
+    const int nSegs = S.frames * kOctaves;
+    const int* candStart = S.hSegStarts;
+    const int* kpStart = S.hSegStarts + (c->nSegs + 1);
+    const int* descStart = S.hSegStarts + 2 * (c->nSegs + 1);
+    const int nDesc = S.hCounters->nDescriptors;
+    for (int s = 0; s < nSegs; s++) {
+        S.candCounts[s] = candStart[s + 1] - candStart[s];
+        S.kpCounts[s] = kpStart[s + 1] - kpStart[s];
+        S.descCounts[s] = S.described ? std::min(descStart[s + 1], nDesc) - std::min(descStart[s], nDesc) : 0;
+    }
+    S.nKp = std::min(S.hCounters->nKeypoints, c->capKp);
+    S.nDesc = S.described ? std::min(S.hCounters->nDescriptors, c->capDesc) : 0;
+    SiftTimings& t = c->timings;
+    memset(&t, 0, sizeof t);
+    t.kernel_launches = S.launches;
+    t.graph_replay = S.graphReplay ? 1 : 0;
+    cudaEventElapsedTime(&t.total_ms, S.evStart, S.evEnd);
+    if (c->stageTiming && !S.graphReplay) {
+        t.stage_timing_enabled = 1;
+        const int lastStage = S.described ? SIFT_STAGE_COUNT : 4;
+        for (int i = 0; i < lastStage; i++) cudaEventElapsedTime(&t.stage_ms[i], c->ev[i], c->ev[i + 1]);
+        cudaEventElapsedTime(&t.blur_octave0_ms, c->evBlur0[0], c->evBlur0[kGaussians - 1]);
+        for (int s = 0; s < kGaussians - 1; s++)   // per-scale split only without row bands
+            t.blur_octave0_launch_ms[s] = c->bandedOctave0 ? t.blur_octave0_ms / (kGaussians - 1) : 0.0f;
+        if (!c->bandedOctave0)
+            for (int s = 0; s < kGaussians - 1; s++)
+                cudaEventElapsedTime(&t.blur_octave0_launch_ms[s], c->evBlur0[s], c->evBlur0[s + 1]);
+        t.blur_octave0_launches = kGaussians - 1;
+    }
+    cudaGetLastError();   // an unrecorded timing event must not poison the next launch check
+    S.status = SIFT_OK;
+    if (S.hCounters->overflow) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "list capacity exceeded (mask %d: 1 candidates, 2 keypoints, 4 descriptors)",
+                 S.hCounters->overflow);
+        S.status = fail(c, SIFT_ERR_CAPACITY, buf);
+    }
+    c->last = &S;
+    c->executed = true;
+    return S.status;
+}
+
+void fillResult(const SiftContext* c, const Slot& S, SiftBatchResult* out) {
+    (void)c;
+    out->n_frames = S.frames;
+    out->status = S.status;
+    out->keypoint_counts = S.kpCounts.data();
+    out->descriptor_counts = S.descCounts.data();
+    out->candidate_counts = S.candCounts.data();
+    out->total_keypoints = S.nKp;
+    out->total_descriptors = S.nDesc;
+    out->keypoints.absolute_x = S.host.kp.absX;
+    out->keypoints.absolute_y = S.host.kp.absY;
+    out->keypoints.sigma = S.host.kp.sigma;
+    out->keypoints.value = S.host.kp.value;
+    out->keypoints.sub_scale = S.host.kp.subScale;
+    out->keypoints.scaled_xy = reinterpret_cast<const int16_t*>(S.host.kp.scaledXY);
+    out->keypoints.octave_scale = reinterpret_cast<const uint8_t*>(S.host.kp.octaveScale);
+    out->descriptors.features = S.host.desc.features;
+    out->descriptors.theta = S.host.desc.theta;
+    out->descriptors.keypoint = S.host.desc.keypoint;
+}
+
+// Uploads n host frames into the slot's input arena on the copy stream; the compute stream waits
+// for the last of them.
+int enqueueUpload(SiftContext* c, Slot& S, const void* const* images, int n, int pitchBytes) {
+    const size_t rowBytes = (size_t)c->cfg.width * c->bytesPerPixel;
     const size_t frameBytes = rowBytes * c->cfg.height;
     for (int f = 0; f < n; f++)
-        if (!images[f]) return fail(c, SIFT_ERR_INVALID_ARGUMENT, "sift_batch_upload: null image");
-    c->upSplit = seedSplitFor(c, n);
-    if (c->upSplit.n > 0) {
-        // one row chunk per band on the copy stream, an event behind each
-        const uint8_t* src = (const uint8_t*)images[0];
-        int g0 = 0;
-        for (int k = 0; k < c->upSplit.n; k++) {
-            const int g1 = c->upSplit.grayRows[k];
-            CTX_TRY(c, cudaMemcpy2DAsync(c->dInput + (size_t)g0 * rowBytes, rowBytes, src + (size_t)g0 * pitchBytes,
-                                         pitchBytes, rowBytes, g1 - g0, cudaMemcpyHostToDevice, c->copyStream));
-            CTX_TRY(c, cudaEventRecord(c->evUp[k], c->copyStream));
-            g0 = g1;
-        }
-    } else {
-        for (int f = 0; f < n; f++)
-            CTX_TRY(c, cudaMemcpy2DAsync(c->dInput + f * frameBytes, rowBytes, images[f], pitchBytes,
-                                         rowBytes, c->cfg.height, cudaMemcpyHostToDevice, c->stream));
-    }
-    c->curInput = c->dInput;
-    c->curPitch = (int)rowBytes;
-    c->curFrameStride = (int64_t)frameBytes;
+        CTX_TRY(c, cudaMemcpy2DAsync(S.dInput + f * frameBytes, rowBytes, images[f], (size_t)pitchBytes, rowBytes,
+                                     c->cfg.height, cudaMemcpyHostToDevice, c->copyStream));
+    CTX_TRY(c, cudaEventRecord(S.evUploaded, c->copyStream));
+    return SIFT_OK;
+}
+
+int checkImages(SiftContext* c, const void* const* images, int n, int pitchBytes, const char* who) {
+    if (!c) return SIFT_ERR_INVALID_ARGUMENT;
+    if (!images || n < 1 || n > c->B || pitchBytes < c->cfg.width * c->bytesPerPixel)
+        return fail(c, SIFT_ERR_INVALID_ARGUMENT, who);
+    for (int f = 0; f < n; f++)
+        if (!images[f]) return fail(c, SIFT_ERR_INVALID_ARGUMENT, "null image");
+    return SIFT_OK;
+}
+
+int submitHost(SiftContext* c, const void* const* images, int n, int pitchBytes, bool withDescribe) {
+    int r = checkImages(c, images, n, pitchBytes, "submit: bad arguments");
+    if (r != SIFT_OK) return r;
+    if (c->nPending >= 2) return fail(c, SIFT_ERR_BUSY, "both in-flight slots are taken: call sift_wait first");
+    CTX_TRY(c, cudaSetDevice(c->device));
+    if (c->nPending == 0) c->head = c->next = 0;   // purely synchronous callers never touch slot 1
+    const int s = c->next;
+    r = ensureSlot(c, s);
+    if (r != SIFT_OK) return r;
+    Slot& S = c->slot[s];
+    r = enqueueUpload(c, S, images, n, pitchBytes);
+    if (r != SIFT_OK) return r;
+    CTX_TRY(c, cudaStreamWaitEvent(c->stream, S.evUploaded, 0));
+    RunArgs a;
+    a.input = S.dInput;
+    a.pitch = c->cfg.width * c->bytesPerPixel;
+    a.frameStride = (int64_t)a.pitch * c->cfg.height;
+    a.frames = n;
+    a.withDescribe = withDescribe;
+    a.hostOut = true;
+    r = runSlot(c, s, a);
+    if (r != SIFT_OK) return r;
+    S.pending = true;
+    S.staged = false;
+    c->nPending++;
+    c->next ^= 1;
+    c->curInput = nullptr;
+    return SIFT_OK;
+}
+
+int waitOldest(SiftContext* c, SiftBatchResult* out) {
+    if (c->nPending < 1) return fail(c, SIFT_ERR_BUSY, "sift_wait: nothing submitted");
+    CTX_TRY(c, cudaSetDevice(c->device));
+    Slot& S = c->slot[c->head];
+    const int r = finishSlot(c, S);
+    S.pending = false;
+    c->nPending--;
+    c->head ^= 1;
+    if (r != SIFT_OK && r != SIFT_ERR_CAPACITY) return r;
+    if (out) fillResult(c, S, out);
+    return r;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sift_submit(SiftContext* c, const void* const* images, int32_t n, int32_t pitchBytes) {
+    if (!c) return SIFT_ERR_INVALID_ARGUMENT;
+    return submitHost(c, images, n, pitchBytes, true);
+}
+
+int sift_wait(SiftContext* c, SiftBatchResult* out) {
+    if (!c || !out) return SIFT_ERR_INVALID_ARGUMENT;
+    return waitOldest(c, out);
+}
+
+int sift_detect_and_describe_batch(SiftContext* c, const void* const* images, int32_t n,
+                                   int32_t pitchBytes, SiftBatchResult* out) {
+    if (!c || !out) return SIFT_ERR_INVALID_ARGUMENT;
+    if (c->nPending) return fail(c, SIFT_ERR_BUSY, "synchronous call with submitted work in flight");
+    const int r = submitHost(c, images, n, pitchBytes, true);
+    if (r != SIFT_OK) return r;
+    return waitOldest(c, out);
+}
+
+int sift_batch_upload(SiftContext* c, const void* const* images, int32_t n, int32_t pitchBytes) {
+    int r = checkImages(c, images, n, pitchBytes, "sift_batch_upload: bad arguments");
+    if (r != SIFT_OK) return r;
+    if (c->nPending) return fail(c, SIFT_ERR_BUSY, "staged call with submitted work in flight");
+    CTX_TRY(c, cudaSetDevice(c->device));
+    Slot& S = c->slot[0];
+    r = enqueueUpload(c, S, images, n, pitchBytes);
+    if (r != SIFT_OK) return r;
+    // the host frames belong to the caller again when this returns
+    CTX_TRY(c, cudaEventSynchronize(S.evUploaded));
+    c->curInput = S.dInput;
+    c->curPitch = c->cfg.width * c->bytesPerPixel;
+    c->curFrameStride = (int64_t)c->curPitch * c->cfg.height;
     c->curFrames = n;
     c->executed = false;
     return SIFT_OK;
@@ -564,11 +1006,12 @@ int sift_batch_upload(SiftContext* c, const void* const* images, int32_t n, int3
 
 int sift_batch_set_device_input(SiftContext* c, const void* dev, int32_t n, int32_t pitchBytes,
                                 int64_t frameStrideBytes) {
-    if (!c || !dev || n < 1 || n > c->B || pitchBytes < c->cfg.width * 4 ||
-        (n > 1 && frameStrideBytes < (int64_t)pitchBytes * c->cfg.height) || (pitchBytes & 3) ||
-        (frameStrideBytes & 3) || ((uintptr_t)dev & 3))
+    if (!c) return SIFT_ERR_INVALID_ARGUMENT;
+    const int align = c->bytesPerPixel == 4 ? 3 : 0;   // BGRA pixels are read as 32-bit words
+    if (!dev || n < 1 || n > c->B || pitchBytes < c->cfg.width * c->bytesPerPixel ||
+        (n > 1 && frameStrideBytes < (int64_t)pitchBytes * c->cfg.height) || (pitchBytes & align) ||
+        (frameStrideBytes & align) || ((uintptr_t)dev & (uintptr_t)align))
         return fail(c, SIFT_ERR_INVALID_ARGUMENT, "sift_batch_set_device_input: bad arguments");
-    c->upSplit = SiftContext::SeedSplit{};
     c->curInput = (const uint8_t*)dev;
     c->curPitch = pitchBytes;
     c->curFrameStride = frameStrideBytes;
@@ -577,410 +1020,103 @@ int sift_batch_set_device_input(SiftContext* c, const void* dev, int32_t n, int3
     return SIFT_OK;
 }
 
-}  // extern "C"
-
-namespace {
-
-// Mask blocks [blockBegin, blockBegin + nBlocks) → ordered candidates → refined keypoints of
-// list set k (SIFTOctave.getKeypoints :198-203, interpolateKeypoints :205-288).
-int postDetect(SiftContext* c, int k, int blockBegin, int nBlocks, int nSegs, cudaEvent_t afterCompaction,
-               cudaEvent_t afterRefine) {
-    SiftContext::ListSet& L = c->L[k];
-    cudaStream_t st = c->stream;
-    CTX_TRY(c, launchCandidateCompaction(c->P, c->dMask, L.dBlockSums, L.dCands, c->capCand, blockBegin,
-                                         nBlocks, L.dSegStarts, nSegs, L.dCounters, st));
-    c->launches += 3;
-    if (afterCompaction) CTX_TRY(c, cudaEventRecord(afterCompaction, st));
-    CTX_TRY(c, launchRefine(c->P, L.dCands, c->capCand, L.dKpTmp, L.dFlagWords, L.dBlockSums, L.dKps, L.dKpSeg,
-                            c->capKp, L.dSegStarts, L.dSegStarts + (c->nSegs + 1), nSegs, L.dCounters, st));
-    c->launches += 3;
-    if (afterRefine) CTX_TRY(c, cudaEventRecord(afterRefine, st));
-    return SIFT_OK;
-}
-
-// getDescriptors (SIFT.swift:207-238) over the keypoints of list set k.
-int describeSet(SiftContext* c, int k, int nSegs, const int* kpIndexBase, cudaEvent_t afterOrientation,
-                cudaEvent_t afterDescriptor) {
-    SiftContext::ListSet& L = c->L[k];
-    cudaStream_t st = c->stream;
-    c->descOnHost = c->wantHostOut && !c->split;   // pinned memory is device-addressable (UVA)
-    CTX_TRY(c, launchDescribe(c->P, L.dKps, L.dKpSeg, c->capKp, L.dSegStarts + (c->nSegs + 1), L.dNOri, L.dOriTmp,
-                              L.dOriOffset, L.dDescKp, L.dBlockSums, c->descOnHost ? c->hDesc : L.dDesc, c->capDesc,
-                              L.dSegStarts + 2 * (c->nSegs + 1), nSegs, L.dCounters, kpIndexBase, c->smCount, st,
-                              afterOrientation));
-    c->launches += 5;
-    if (afterDescriptor) CTX_TRY(c, cudaEventRecord(afterDescriptor, st));
-    return SIFT_OK;
-}
-
-// findKeypoints + getKeypointsFromOctaves + interpolateKeypoints (SIFT.swift:154-202), all
-// frames of the batch at once, no host synchronisation inside.
-int runDetect(SiftContext* c, bool withDescribe) {
-    const int F = c->curFrames;
-    cudaStream_t st = c->stream;
-    const bool T = c->stageTiming;
-    c->launches = 0;
-    c->kpsOnHost = c->descOnHost = false;
-    if (!c->countersClean) {   // normally zeroed behind the previous call's read-back (finish)
-        CTX_TRY(c, cudaMemsetAsync(c->L[0].dCounters, 0, sizeof(Counters), st));
-        CTX_TRY(c, cudaMemsetAsync(c->L[1].dCounters, 0, sizeof(Counters), st));
-    }
-    c->countersClean = false;
-    if (T) CTX_TRY(c, cudaEventRecord(c->ev[0], st));
-    // DifferenceOfGaussians.encodeSeedTexture (:357-389)
-    const OctaveDev& o0 = c->P.oct[0];
-    BlurArgs seed{};
-    seed.in = c->dScaled;
-    seed.out = o0.G;  // octave 0 slice 0 (the reference blits seed → slice 0, :176-188)
-    seed.w = o0.w; seed.h = o0.h; seed.pitch = o0.pitch;
-    seed.inFrameStride = o0.plane;
-    seed.outFrameStride = kGaussians * o0.plane;
-    seed.frames = F;
-    const SiftContext::SeedSplit sp = (F == 1 && c->curInput == c->dInput) ? c->upSplit : SiftContext::SeedSplit{};
-    if (sp.n > 0) {
-        // chunk k → everything band k of octave 0 still lacks, on band k's stream (main stream for
-        // band 0), behind chunk k's arrival and chunk k - 1's seed rows
-        for (int k = 0; k < sp.n; k++) {
-            cudaStream_t sk = k == 0 ? st : c->bandStream[k];
-            CTX_TRY(c, cudaStreamWaitEvent(sk, c->evUp[k], 0));
-            if (k > 0) CTX_TRY(c, cudaStreamWaitEvent(sk, c->evSeedDone[k - 1], 0));
-            const int up0 = k ? sp.upRows[k - 1] : 0, seed0 = k ? sp.seedRows[k - 1] : 0;
-            CTX_TRY(c, launchGrayUpsample(c->curInput, c->curPitch, c->curFrameStride, c->dGray, c->cfg.width,
-                                          c->cfg.height, c->dScaled, o0.w, o0.h, o0.pitch, o0.plane, F, sk,
-                                          k ? sp.grayRows[k - 1] : 0, sp.grayRows[k], up0, sp.upRows[k]));
-            seed.yBegin = seed0; seed.yEnd = sp.seedRows[k];
-            CTX_TRY(c, launchBlur(seed, c->seedTaps, c->seedNtaps, sk));
-            CTX_TRY(c, cudaEventRecord(c->evSeedDone[k], sk));
-            if (k > 0) c->launches += 2;
-        }
-    } else {
-        CTX_TRY(c, launchGrayUpsample(c->curInput, c->curPitch, c->curFrameStride, c->dGray,
-                                      c->cfg.width, c->cfg.height, c->dScaled, o0.w, o0.h, o0.pitch,
-                                      o0.plane, F, st));
-        CTX_TRY(c, launchBlur(seed, c->seedTaps, c->seedNtaps, st));
-    }
-    c->launches += 2;
-    if (T) CTX_TRY(c, cudaEventRecord(c->ev[1], st));
-    // encodeOctaves (:391-406): Gaussian series + DoG; octave o+1 slice 0 = octave o slice 3
-    // decimated (fused into the blur that produces slice 3); SIFTOctave.encodeGradients (:190-196)
-    // and encodeExtrema (:183-189). Octaves form a fork/join DAG: octave o+1 starts on its own
-    // stream once octave o has written slice 3, so the small octaves (launch-latency bound) run
-    // under the large kernels of octaves 0 and 1 instead of after them.
-    bool forked[kOctaves] = {};
-    static const int dbgMaxOctave = getenv("SIFTCUDA_DEBUG_MAX_OCTAVE") ? atoi(getenv("SIFTCUDA_DEBUG_MAX_OCTAVE")) : kOctaves;
-    static const int dbgSkip = getenv("SIFTCUDA_DEBUG_SKIP") ? atoi(getenv("SIFTCUDA_DEBUG_SKIP")) : 0;  // 1 gradient, 2 extrema
-    for (int o = 0; o < kOctaves; o++) {
-        const OctaveDev& q = c->P.oct[o];
-        if (q.w < 1 || q.h < 1 || o > dbgMaxOctave) continue;
-        cudaStream_t so = c->octStream[o];
-        if (o > 0) {
-            CTX_TRY(c, cudaStreamWaitEvent(so, c->evSeeded[o - 1], 0));
-            if (o == 1 && c->bandedOctave0)
-                for (int b = 1; b < c->nBands; b++) CTX_TRY(c, cudaStreamWaitEvent(so, c->evBandSeeded[b], 0));
-            forked[o] = true;
-        }
-        // two row bands for a plane with many tiles (octave 0 of a large single frame); batches
-        // already have enough independent work per launch
-        const int nb = c->nBands;
-        const bool banded = (o == 0) && bandedOctave0(c, F);
-        if (T && o == 0) CTX_TRY(c, cudaEventRecord(c->evBlur0[0], so));
-        if (banded) {
-            CTX_TRY(c, cudaEventRecord(c->evBandFork, so));
-            for (int b = 1; b < nb; b++) CTX_TRY(c, cudaStreamWaitEvent(c->bandStream[b], c->evBandFork, 0));
-        }
-        for (int band = 0; band < (banded ? nb : 1); band++) {
-            cudaStream_t sb = band == 0 ? so : c->bandStream[band];
-            // band rows [r0, r1), boundaries on multiples of the tile height
-            const int r0 = banded ? bandBoundary(c, band) : 0;
-            const int r1 = banded ? bandBoundary(c, band + 1) : q.h;
-            for (int s = 0; s < kGaussians - 1; s++) {
-                if (T && o == 0 && !banded && s > 0) CTX_TRY(c, cudaEventRecord(c->evBlur0[s], sb));
-                BlurArgs a{};
-                a.in = q.G + (size_t)s * q.plane;
-                a.out = q.G + (size_t)(s + 1) * q.plane;
-                a.dog = q.D + (size_t)s * q.plane;
-                a.w = q.w; a.h = q.h; a.pitch = q.pitch;
-                a.inFrameStride = a.outFrameStride = kGaussians * q.plane;
-                a.dogFrameStride = kDogs * q.plane;
-                if (banded) {
-                    // rows the later scales of this band still need: sum of their radii
-                    int halo = bandTails() ? 1 : 0;
-                    for (int t = s + 1; t < kGaussians - 1; t++) halo += c->ntaps[t] / 2;
-                    a.yBegin = std::max(0, r0 - halo);
-                    a.yEnd = std::min(q.h, r1 + halo);
-                }
-                if (s + 1 == kScales && o + 1 < kOctaves && c->P.oct[o + 1].w >= 1 && c->P.oct[o + 1].h >= 1) {
-                    const OctaveDev& nx = c->P.oct[o + 1];
-                    a.half = nx.G;
-                    a.halfW = nx.w; a.halfH = nx.h; a.halfPitch = nx.pitch;
-                    a.halfFrameStride = kGaussians * nx.plane;
-                }
-                a.frames = F;
-                // small planes: scale s + 1 launches under scale s (programmatic dependent launch)
-                static const int pdlMaxTiles = getenv("SIFTCUDA_PDL_TILES") ? atoi(getenv("SIFTCUDA_PDL_TILES")) : 160;
-                a.pdl = (s > 0 && !banded && (long)((q.w + 31) / 32) * ((q.h + 31) / 32) * F <= pdlMaxTiles) ? 1 : 0;
-                CTX_TRY(c, launchBlur(a, c->taps[s], c->ntaps[s], sb));
-                c->launches++;
-                if (s + 1 == kScales) CTX_TRY(c, cudaEventRecord(band == 0 ? c->evSeeded[o] : c->evBandSeeded[band], sb));
-            }
-            if (banded && bandTails()) {
-                if (T) CTX_TRY(c, cudaEventRecord(c->evBandBlurEnd[band], sb));
-                if (!(dbgSkip & 1)) CTX_TRY(c, launchGradient(q, F, sb, r0, r1));
-                if (!(dbgSkip & 2)) CTX_TRY(c, launchExtremaMask(c->P, o, c->dMask, F, sb, r0, r1));
-                c->launches += 2;
-            }
-        }
-        if (banded) {   // join: (without band tails) gradient and extrema need every row
-            for (int b = 1; b < nb; b++) {
-                CTX_TRY(c, cudaEventRecord(c->evBandDone[b], c->bandStream[b]));
-                CTX_TRY(c, cudaStreamWaitEvent(so, c->evBandDone[b], 0));
-            }
-        }
-        if (o == 0) c->bandedOctave0 = banded;
-        if (T && o == 0) CTX_TRY(c, cudaEventRecord(c->evBlur0[kGaussians - 1], so));
-        // (the gradient beside the extrema mask on a second stream, or beside blurs s = 3, 4: both
-        // measured, no gain — the stage is throughput-bound)
-        if (!(banded && bandTails())) {
-            if (!(dbgSkip & 1)) CTX_TRY(c, launchGradient(q, F, so));
-            c->launches++;
-            if (q.w >= 3 && q.h >= 3 && !(dbgSkip & 2)) {
-                CTX_TRY(c, launchExtremaMask(c->P, o, c->dMask, F, so));
-                c->launches++;
-            }
-        }
-        if (o > 0) CTX_TRY(c, cudaEventRecord(c->evOctDone[o], so));
-        if (o == 0) {
-            // Single large frame: octave 0 holds most of the keypoints and is complete long before
-            // the chain of deeper octaves. Compact / refine / describe it now from list set 0; the
-            // (throughput-bound) orientation and descriptor kernels then run over the
-            // (latency-bound) tail of the small octaves, which follow from set 1 after the join.
-            // Measured at 1080p: with prioritised octave streams octave 0 is itself the critical
-            // path (0.47 ms), so the split only adds a second set of scan launches (788 vs 846
-            // frames/s). Off unless SIFTCUDA_SPLIT=1.
-            static const bool wantSplit = getenv("SIFTCUDA_SPLIT") && atoi(getenv("SIFTCUDA_SPLIT")) != 0;
-            c->split = wantSplit && c->bandedOctave0 && c->P.oct[1].maskBlockStart > 0;
-            c->candSplit = c->split;
-            if (c->split) {
-                if (T) CTX_TRY(c, cudaEventRecord(c->ev[2], st));
-                int r = postDetect(c, 0, 0, c->P.oct[1].maskBlockStart, kOctaves, T ? c->ev[3] : nullptr,
-                                   T ? c->ev[4] : nullptr);
-                if (r != SIFT_OK) return r;
-                if (withDescribe) {
-                    r = describeSet(c, 0, kOctaves, nullptr, T ? c->ev[5] : nullptr, T ? c->ev[6] : nullptr);
-                    if (r != SIFT_OK) return r;
-                }
-            }
-        }
-    }
-    for (int o = 1; o < kOctaves; o++)
-        if (forked[o]) CTX_TRY(c, cudaStreamWaitEvent(st, c->evOctDone[o], 0));
-    const int nSegs = F * kOctaves;
-    if (c->split) {
-        if (T) CTX_TRY(c, cudaEventRecord(c->evB[0], st));
-        const int b1 = c->P.oct[1].maskBlockStart;
-        int r = postDetect(c, 1, b1, c->P.blocksPerFrame - b1, kOctaves, T ? c->evB[1] : nullptr,
-                           T ? c->evB[2] : nullptr);
-        if (r != SIFT_OK) return r;
-        if (withDescribe) {
-            r = describeSet(c, 1, kOctaves, &c->L[0].dCounters->nKeypoints, T ? c->evB[3] : nullptr,
-                            T ? c->evB[4] : nullptr);
-            if (r != SIFT_OK) return r;
-        }
-    } else {
-        if (T) CTX_TRY(c, cudaEventRecord(c->ev[2], st));
-        int r = postDetect(c, 0, 0, c->P.blocksPerFrame * F, nSegs, T ? c->ev[3] : nullptr, T ? c->ev[4] : nullptr);
-        if (r != SIFT_OK) return r;
-        if (c->wantHostOut) {
-            // keypoint count for the early copy (earlyKeypointCopy), read back on the copy stream so
-            // that the main stream goes straight on to the orientation kernel
-            CTX_TRY(c, cudaEventRecord(c->evKpCopied, st));
-            CTX_TRY(c, cudaStreamWaitEvent(c->copyStream, c->evKpCopied, 0));
-            CTX_TRY(c, cudaMemcpyAsync(c->L[0].hCounters, c->L[0].dCounters, sizeof(Counters), cudaMemcpyDeviceToHost,
-                                       c->copyStream));
-            CTX_TRY(c, cudaEventRecord(c->evRefined, c->copyStream));
-            c->kpsOnHost = true;
-        }
-        if (withDescribe) {
-            r = describeSet(c, 0, nSegs, nullptr, T ? c->ev[5] : nullptr, T ? c->ev[6] : nullptr);
-            if (r != SIFT_OK) return r;
-        }
-    }
-    c->executed = true;
-    c->described = withDescribe;
-    return SIFT_OK;
-}
-
-// Host-output mode: while the orientation and descriptor kernels (already queued) run, wait for
-// the refined-keypoint count and send the keypoints home on the copy stream.
-int earlyKeypointCopy(SiftContext* c) {
-    if (!c->kpsOnHost) return SIFT_OK;
-    CTX_TRY(c, cudaEventSynchronize(c->evRefined));
-    const int64_t nk = std::min(c->L[0].hCounters->nKeypoints, c->capKp);
-    if (nk > 0) {
-        CTX_TRY(c, cudaMemcpyAsync(c->hKps, c->L[0].dKps, (size_t)nk * sizeof(SiftKeypoint), cudaMemcpyDeviceToHost,
-                                   c->copyStream));
-    }
-    CTX_TRY(c, cudaEventRecord(c->evKpCopied, c->copyStream));
-    return SIFT_OK;
-}
-
-// D2H of the small bookkeeping blocks, stream drain, timing read-out, overflow check.
-int finish(SiftContext* c, bool withDescribe) {
-    cudaStream_t st = c->stream;
-    const int nSets = c->split ? 2 : 1;
-    const size_t segInts = 3 * (size_t)(c->nSegs + 1);
-    for (int k = 0; k < nSets; k++) {
-        CTX_TRY(c, cudaMemcpyAsync(c->L[k].hCounters, c->L[k].dCounters, sizeof(Counters), cudaMemcpyDeviceToHost, st));
-        CTX_TRY(c, cudaMemcpyAsync(c->L[k].hSegStarts, c->L[k].dSegStarts, segInts * sizeof(int),
-                                   cudaMemcpyDeviceToHost, st));
-    }
-    CTX_TRY(c, cudaStreamSynchronize(st));
-    if (c->kpsOnHost) CTX_TRY(c, cudaEventSynchronize(c->evKpCopied));
-    // zero the counters for the next frame now, off its critical path (overflow bits accumulate by
-    // atomicOr; the counts themselves are rewritten by every scan)
-    if (cudaMemsetAsync(c->L[0].dCounters, 0, sizeof(Counters), st) == cudaSuccess &&
-        cudaMemsetAsync(c->L[1].dCounters, 0, sizeof(Counters), st) == cudaSuccess)
-        c->countersClean = true;
-    const int nSegs = c->curFrames * kOctaves;
-    int overflow = 0;
-    for (int s = 0; s < nSegs; s++) c->candCounts[s] = c->kpCounts[s] = c->descCounts[s] = 0;
-    for (int k = 0; k < nSets; k++) {
-        const int* candStart = c->L[k].hSegStarts;
-        const int* kpStart = c->L[k].hSegStarts + (c->nSegs + 1);
-        const int* descStart = c->L[k].hSegStarts + 2 * (c->nSegs + 1);
-        const int nDesc = c->L[k].hCounters->nDescriptors;
-        for (int s = 0; s < nSegs; s++) {
-            c->candCounts[s] += candStart[s + 1] - candStart[s];
-            c->kpCounts[s] += kpStart[s + 1] - kpStart[s];
-            if (withDescribe) c->descCounts[s] += std::min(descStart[s + 1], nDesc) - std::min(descStart[s], nDesc);
-        }
-        overflow |= c->L[k].hCounters->overflow;
-    }
-    SiftTimings& t = c->timings;
-    memset(&t, 0, sizeof t);
-    t.kernel_launches = c->launches;
-    t.stage_timing_enabled = c->stageTiming;
-    if (c->stageTiming) {
-        const int last = withDescribe ? SIFT_STAGE_COUNT : 4;
-        for (int i = 0; i < last; i++) cudaEventElapsedTime(&t.stage_ms[i], c->ev[i], c->ev[i + 1]);
-        cudaEventElapsedTime(&t.total_ms, c->ev[0], c->ev[last]);
-        if (c->split) {
-            // second pass (octaves >= 1): its stages are added to the first pass's; the wait for
-            // the deeper octaves between the passes, if any, counts as pyramid time
-            const int lastB = withDescribe ? 4 : 2;
-            float ms = 0;
-            cudaEventElapsedTime(&ms, c->ev[last], c->evB[0]);
-            t.stage_ms[SIFT_STAGE_PYRAMID] += ms;
-            for (int i = 0; i < lastB; i++) {
-                cudaEventElapsedTime(&ms, c->evB[i], c->evB[i + 1]);
-                t.stage_ms[SIFT_STAGE_EXTREMA + i] += ms;
-            }
-            cudaEventElapsedTime(&t.total_ms, c->ev[0], c->evB[lastB]);
-        }
-        cudaEventElapsedTime(&t.blur_octave0_ms, c->evBlur0[0], c->evBlur0[kGaussians - 1]);
-        if (c->bandedOctave0 && bandTails()) {   // the section ends with the last band's last blur
-            t.blur_octave0_ms = 0;
-            for (int b = 0; b < c->nBands; b++) {
-                float ms = 0;
-                cudaEventElapsedTime(&ms, c->evBlur0[0], c->evBandBlurEnd[b]);
-                t.blur_octave0_ms = std::max(t.blur_octave0_ms, ms);
-            }
-        }
-        for (int s = 0; s < kGaussians - 1; s++)   // per-scale split only without row bands
-            t.blur_octave0_launch_ms[s] = c->bandedOctave0 ? t.blur_octave0_ms / (kGaussians - 1) : 0.0f;
-        if (!c->bandedOctave0)
-            for (int s = 0; s < kGaussians - 1; s++)
-                cudaEventElapsedTime(&t.blur_octave0_launch_ms[s], c->evBlur0[s], c->evBlur0[s + 1]);
-        t.blur_octave0_launches = kGaussians - 1;
-        cudaGetLastError();   // an unrecorded timing event must not poison the next launch check
-    }
-    if (overflow) {
-        char buf[160];
-        snprintf(buf, sizeof buf, "list capacity exceeded (mask %d: 1 candidates, 2 keypoints, 4 descriptors)",
-                 overflow);
-        return fail(c, SIFT_ERR_CAPACITY, buf);
-    }
-    return SIFT_OK;
-}
-
-}  // namespace
-
-extern "C" {
-
 int sift_batch_execute(SiftContext* c) {
     if (!c) return SIFT_ERR_INVALID_ARGUMENT;
     if (!c->curInput || c->curFrames < 1) return fail(c, SIFT_ERR_INVALID_ARGUMENT, "no input set");
+    if (c->nPending) return fail(c, SIFT_ERR_BUSY, "staged call with submitted work in flight");
     CTX_TRY(c, cudaSetDevice(c->device));
-    c->wantHostOut = false;   // staged path: results stay in HBM until sift_batch_download
-    const int r = runDetect(c, true);
+    RunArgs a;
+    a.input = c->curInput;
+    a.pitch = c->curPitch;
+    a.frameStride = c->curFrameStride;
+    a.frames = c->curFrames;
+    a.withDescribe = true;
+    a.hostOut = false;   // staged path: results stay in HBM until sift_batch_download
+    const int r = runSlot(c, 0, a);
     if (r != SIFT_OK) return r;
-    return finish(c, true);
+    c->slot[0].staged = true;
+    return finishSlot(c, c->slot[0]);
 }
 
 int sift_batch_download(SiftContext* c, SiftBatchResult* out) {
     if (!c || !out) return SIFT_ERR_INVALID_ARGUMENT;
-    if (!c->executed) return fail(c, SIFT_ERR_NOT_DETECTED, "download before execute");
+    if (!c->executed || !c->last) return fail(c, SIFT_ERR_NOT_DETECTED, "download before execute");
     CTX_TRY(c, cudaSetDevice(c->device));
-    // list sets are concatenated in order: set 0, then (split mode) set 1 = the deeper octaves
-    int64_t nKp = 0, nDesc = 0;
-    for (int k = 0; k < (c->split ? 2 : 1); k++) {
-        const int64_t nk = std::min(c->L[k].hCounters->nKeypoints, c->capKp);
-        const int64_t nd = c->described ? std::min(c->L[k].hCounters->nDescriptors, c->capDesc) : 0;
-        if (nKp + nk > c->capKp || nDesc + nd > c->capDesc) return fail(c, SIFT_ERR_CAPACITY, "result arrays too small");
-        if (nk > 0 && !c->kpsOnHost)
-            CTX_TRY(c, cudaMemcpyAsync(c->hKps + nKp, c->L[k].dKps, (size_t)nk * sizeof(SiftKeypoint),
-                                       cudaMemcpyDeviceToHost, c->stream));
-        if (nd > 0 && !c->descOnHost)
-            CTX_TRY(c, cudaMemcpyAsync(c->hDesc + nDesc, c->L[k].dDesc, (size_t)nd * sizeof(SiftDescriptor),
-                                       cudaMemcpyDeviceToHost, c->stream));
-        nKp += nk;
-        nDesc += nd;
+    Slot& S = *c->last;
+    if (S.staged) {
+        // device columns → the slot's pinned columns
+        cudaStream_t st = c->stream;
+        const size_t nk = (size_t)S.nKp, nd = (size_t)S.nDesc;
+        if (nk) {
+            CTX_TRY(c, cudaMemcpyAsync(S.host.kp.absX, c->dev.kp.absX, nk * 4, cudaMemcpyDeviceToHost, st));
+            CTX_TRY(c, cudaMemcpyAsync(S.host.kp.absY, c->dev.kp.absY, nk * 4, cudaMemcpyDeviceToHost, st));
+            CTX_TRY(c, cudaMemcpyAsync(S.host.kp.sigma, c->dev.kp.sigma, nk * 4, cudaMemcpyDeviceToHost, st));
+            CTX_TRY(c, cudaMemcpyAsync(S.host.kp.value, c->dev.kp.value, nk * 4, cudaMemcpyDeviceToHost, st));
+            CTX_TRY(c, cudaMemcpyAsync(S.host.kp.subScale, c->dev.kp.subScale, nk * 4, cudaMemcpyDeviceToHost, st));
+            CTX_TRY(c, cudaMemcpyAsync(S.host.kp.scaledXY, c->dev.kp.scaledXY, nk * sizeof(short2), cudaMemcpyDeviceToHost, st));
+            CTX_TRY(c, cudaMemcpyAsync(S.host.kp.octaveScale, c->dev.kp.octaveScale, nk * sizeof(uchar2), cudaMemcpyDeviceToHost, st));
+        }
+        if (nd) {
+            CTX_TRY(c, cudaMemcpyAsync(S.host.desc.features, c->dev.desc.features, nd * 128, cudaMemcpyDeviceToHost, st));
+            CTX_TRY(c, cudaMemcpyAsync(S.host.desc.theta, c->dev.desc.theta, nd * 4, cudaMemcpyDeviceToHost, st));
+            CTX_TRY(c, cudaMemcpyAsync(S.host.desc.keypoint, c->dev.desc.keypoint, nd * 4, cudaMemcpyDeviceToHost, st));
+        }
+        CTX_TRY(c, cudaStreamSynchronize(st));
     }
-    CTX_TRY(c, cudaStreamSynchronize(c->stream));
-    out->n_frames = c->curFrames;
-    out->keypoint_counts = c->kpCounts.data();
-    out->descriptor_counts = c->descCounts.data();
-    out->candidate_counts = c->candCounts.data();
-    out->keypoints = c->hKps;
-    out->descriptors = c->hDesc;
-    out->total_keypoints = nKp;
-    out->total_descriptors = nDesc;
+    fillResult(c, S, out);
     return SIFT_OK;
 }
 
-int sift_detect_and_describe_batch(SiftContext* c, const void* const* images, int32_t n,
-                                   int32_t pitchBytes, SiftBatchResult* out) {
-    if (!out) return SIFT_ERR_INVALID_ARGUMENT;
-    int r = sift_batch_upload(c, images, n, pitchBytes);
-    if (r != SIFT_OK) return r;
-    static const bool hostOut = !(getenv("SIFTCUDA_HOST_OUT") && atoi(getenv("SIFTCUDA_HOST_OUT")) == 0);
-    c->wantHostOut = hostOut;
-    r = runDetect(c, true);
-    c->wantHostOut = false;
-    if (r != SIFT_OK) return r;
-    r = earlyKeypointCopy(c);
-    if (r != SIFT_OK) return r;
-    const int re = finish(c, true);
-    if (re != SIFT_OK && re != SIFT_ERR_CAPACITY) return re;
-    r = sift_batch_download(c, out);
-    return r != SIFT_OK ? r : re;
+int sift_materialize_keypoints(const SiftContext* c, const SiftBatchResult* r, int64_t first, int64_t count,
+                               SiftKeypoint* dst) {
+    if (!c || !r || first < 0 || count < 0 || first + count > r->total_keypoints || (count > 0 && !dst))
+        return SIFT_ERR_INVALID_ARGUMENT;
+    const SiftKeypointColumns& k = r->keypoints;
+    for (int64_t i = 0; i < count; i++) {
+        const int64_t j = first + i;
+        SiftKeypoint& d = dst[i];
+        d.octave = k.octave_scale[2 * j];
+        d.scale = k.octave_scale[2 * j + 1];
+        d.subScale = k.sub_scale[j];
+        d.scaledX = k.scaled_xy[2 * j];
+        d.scaledY = k.scaled_xy[2 * j + 1];
+        d.absoluteX = k.absolute_x[j];
+        d.absoluteY = k.absolute_y[j];
+        const OctaveDev& o = c->P.oct[d.octave < kOctaves ? d.octave : 0];
+        d.normalizedX = (float)d.scaledX / (float)o.w;   // SIFTOctave.swift:278-281
+        d.normalizedY = (float)d.scaledY / (float)o.h;
+        d.sigma = k.sigma[j];
+        d.value = k.value[j];
+    }
+    return SIFT_OK;
 }
 
-int sift_detect(SiftContext* c, const void* bgra8, int32_t pitchBytes,
+int sift_materialize_descriptors(const SiftBatchResult* r, int64_t first, int64_t count, SiftDescriptor* dst) {
+    if (!r || first < 0 || count < 0 || first + count > r->total_descriptors || (count > 0 && !dst))
+        return SIFT_ERR_INVALID_ARGUMENT;
+    for (int64_t i = 0; i < count; i++) {
+        const int64_t j = first + i;
+        dst[i].keypoint = r->descriptors.keypoint[j];
+        dst[i].theta = r->descriptors.theta[j];
+        memcpy(dst[i].features, r->descriptors.features + j * 128, 128);
+    }
+    return SIFT_OK;
+}
+
+int sift_detect(SiftContext* c, const void* pixels, int32_t pitchBytes,
                 const SiftKeypoint** outKps, int32_t counts[SIFT_NUM_OCTAVES]) {
-    if (!c || !bgra8 || !outKps || !counts) return SIFT_ERR_INVALID_ARGUMENT;
-    const void* imgs[1] = {bgra8};
-    int r = sift_batch_upload(c, imgs, 1, pitchBytes);
+    if (!c || !pixels || !outKps || !counts) return SIFT_ERR_INVALID_ARGUMENT;
+    if (c->nPending) return fail(c, SIFT_ERR_BUSY, "synchronous call with submitted work in flight");
+    const void* imgs[1] = {pixels};
+    int r = submitHost(c, imgs, 1, pitchBytes, false);
     if (r != SIFT_OK) return r;
-    c->wantHostOut = false;
-    r = runDetect(c, false);
-    if (r != SIFT_OK) return r;
-    const int re = finish(c, false);
-    if (re != SIFT_OK && re != SIFT_ERR_CAPACITY) return re;
     SiftBatchResult res;
-    r = sift_batch_download(c, &res);
+    const int re = waitOldest(c, &res);
+    if (re != SIFT_OK && re != SIFT_ERR_CAPACITY) return re;
+    c->kpRecords.resize((size_t)std::max<int64_t>(res.total_keypoints, 1));
+    r = sift_materialize_keypoints(c, &res, 0, res.total_keypoints, c->kpRecords.data());
     if (r != SIFT_OK) return r;
-    *outKps = res.keypoints;
+    *outKps = c->kpRecords.data();
     for (int o = 0; o < kOctaves; o++) counts[o] = res.keypoint_counts[o];
     return re;
 }
@@ -989,6 +1125,7 @@ int sift_describe(SiftContext* c, const SiftKeypoint* kps, const int32_t counts[
                   const SiftDescriptor** outDesc, int32_t descCounts[SIFT_NUM_OCTAVES]) {
     if (!c || !counts || !outDesc || !descCounts) return SIFT_ERR_INVALID_ARGUMENT;
     if (!c->executed) return fail(c, SIFT_ERR_NOT_DETECTED, "sift_describe before sift_detect");
+    if (c->nPending) return fail(c, SIFT_ERR_BUSY, "synchronous call with submitted work in flight");
     CTX_TRY(c, cudaSetDevice(c->device));
     int64_t n = 0;
     for (int o = 0; o < kOctaves; o++) {
@@ -997,66 +1134,82 @@ int sift_describe(SiftContext* c, const SiftKeypoint* kps, const int32_t counts[
     }
     if (n > c->capKp) return fail(c, SIFT_ERR_CAPACITY, "more keypoints than max_keypoints_per_frame");
     if (n > 0 && !kps) return SIFT_ERR_INVALID_ARGUMENT;
-    // keypoints may alias our own pinned result buffer (the usual detect → describe flow)
-    if (n > 0 && kps != c->hKps) memcpy(c->hKps, kps, (size_t)n * sizeof(SiftKeypoint));
-    int* kpStart = c->L[0].hSegStarts + (c->nSegs + 1);
+    Slot& S = c->slot[0];
+    // group check + segment table on the host; the keypoints may alias (or overlap) our own
+    // record array from sift_detect, so they are only read here, never copied over themselves
+    int* kpStart = S.hSegStarts + (c->nSegs + 1);
+    c->kpSegHost.resize((size_t)std::max<int64_t>(n, 1));
     int k = 0;
     for (int o = 0; o < kOctaves; o++) {
         kpStart[o] = k;
         for (int i = 0; i < counts[o]; i++) {
-            if (c->hKps[k].octave != o) return fail(c, SIFT_ERR_INVALID_ARGUMENT, "keypoint octave does not match its group");
-            c->hKpSeg[k++] = o;
+            if (kps[k].octave != o) return fail(c, SIFT_ERR_INVALID_ARGUMENT, "keypoint octave does not match its group");
+            c->kpSegHost[(size_t)k++] = o;
         }
     }
     for (int s = kOctaves; s <= c->nSegs; s++) kpStart[s] = k;
     cudaStream_t st = c->stream;
-    memset(c->L[0].hCounters, 0, sizeof(Counters));   // incl. the kernels' work-queue counters
-    c->L[0].hCounters->nKeypoints = (int)n;
-    CTX_TRY(c, cudaMemcpyAsync(c->L[0].dCounters, c->L[0].hCounters, sizeof(Counters), cudaMemcpyHostToDevice, st));
+    memset(S.hCounters, 0, sizeof(Counters));   // incl. the kernels' work-queue counters
+    S.hCounters->nKeypoints = (int)n;
+    CTX_TRY(c, cudaEventRecord(S.evStart, st));
+    CTX_TRY(c, cudaMemcpyAsync(c->dCounters, S.hCounters, sizeof(Counters), cudaMemcpyHostToDevice, st));
     if (n > 0) {
-        CTX_TRY(c, cudaMemcpyAsync(c->L[0].dKps, c->hKps, (size_t)n * sizeof(SiftKeypoint), cudaMemcpyHostToDevice, st));
-        CTX_TRY(c, cudaMemcpyAsync(c->L[0].dKpSeg, c->hKpSeg, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
+        CTX_TRY(c, cudaMemcpyAsync(c->dKps, kps, (size_t)n * sizeof(SiftKeypoint), cudaMemcpyHostToDevice, st));
+        CTX_TRY(c, cudaMemcpyAsync(c->dKpSeg, c->kpSegHost.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
     }
-    CTX_TRY(c, cudaMemcpyAsync(c->L[0].dSegStarts + (c->nSegs + 1), kpStart, (size_t)(c->nSegs + 1) * sizeof(int),
+    CTX_TRY(c, cudaMemcpyAsync(c->dSegStarts + (c->nSegs + 1), kpStart, (size_t)(c->nSegs + 1) * sizeof(int),
                                cudaMemcpyHostToDevice, st));
+    // the pageable sources above must have been consumed before the caller's array is touched again
+    CTX_TRY(c, cudaStreamSynchronize(st));
     const bool T = c->stageTiming;
     c->launches = 0;
+    RunArgs a;
+    a.frames = 1;
+    a.withDescribe = true;
+    a.hostOut = true;
+    a.slot = &S;
     if (T) CTX_TRY(c, cudaEventRecord(c->ev[4], st));
-    const int savedFrames = c->curFrames;
-    c->curFrames = 1;
-    c->split = false;   // caller-supplied keypoints all live in list set 0
-    c->kpsOnHost = true;   // they are the caller's (already in hKps); nothing to copy back
-    c->wantHostOut = true;
-    int r = describeSet(c, 0, kOctaves, nullptr, T ? c->ev[5] : nullptr, T ? c->ev[6] : nullptr);
-    c->wantHostOut = false;
-    c->described = true;
-    if (r != SIFT_OK) { c->curFrames = savedFrames; return r; }
-    CTX_TRY(c, cudaEventRecord(c->evKpCopied, c->copyStream));   // finish() waits on it
-    // bookkeeping without touching the detect-stage events
-    const bool savedT = c->stageTiming;
-    c->stageTiming = false;
-    const int re = finish(c, true);
-    c->stageTiming = savedT;
+    int r = enqueueDescribe(c, a, kOctaves, T);
+    if (r != SIFT_OK) return r;
+    r = enqueueReadback(c, a);
+    if (r != SIFT_OK) return r;
+    CTX_TRY(c, cudaEventRecord(S.evEnd, st));
+    CTX_TRY(c, cudaEventSynchronize(S.evEnd));
+    // bookkeeping: only the descriptor segment table changed
+    const int* descStart = S.hSegStarts + 2 * (c->nSegs + 1);
+    const int nDesc = std::min(S.hCounters->nDescriptors, c->capDesc);
+    memset(&c->timings, 0, sizeof c->timings);
+    c->timings.kernel_launches = c->launches;
+    cudaEventElapsedTime(&c->timings.total_ms, S.evStart, S.evEnd);
     if (T) {
+        c->timings.stage_timing_enabled = 1;
         cudaEventElapsedTime(&c->timings.stage_ms[4], c->ev[4], c->ev[5]);
         cudaEventElapsedTime(&c->timings.stage_ms[5], c->ev[5], c->ev[6]);
-        cudaEventElapsedTime(&c->timings.total_ms, c->ev[4], c->ev[6]);
     }
-    if (re != SIFT_OK && re != SIFT_ERR_CAPACITY) { c->curFrames = savedFrames; return re; }
+    cudaGetLastError();
+    for (int o = 0; o < kOctaves; o++) descCounts[o] = std::min(descStart[o + 1], nDesc) - std::min(descStart[o], nDesc);
+    S.frames = 1;
+    S.described = true;
+    S.hostOut = true;
+    S.staged = false;
+    S.nDesc = nDesc;
+    for (int o = 0; o < kOctaves; o++) S.descCounts[o] = descCounts[o];
+    c->descRecords.resize((size_t)std::max(nDesc, 1));
     SiftBatchResult res;
-    r = sift_batch_download(c, &res);
-    c->curFrames = savedFrames;
+    fillResult(c, S, &res);
+    res.total_descriptors = nDesc;
+    r = sift_materialize_descriptors(&res, 0, nDesc, c->descRecords.data());
     if (r != SIFT_OK) return r;
-    *outDesc = res.descriptors;
-    for (int o = 0; o < kOctaves; o++) descCounts[o] = res.descriptor_counts[o];
-    return re;
+    *outDesc = c->descRecords.data();
+    if (S.hCounters->overflow & 4) return fail(c, SIFT_ERR_CAPACITY, "descriptor capacity exceeded");
+    return SIFT_OK;
 }
 
 int sift_debug_download(SiftContext* c, int32_t what, int32_t frame, int32_t octave, int32_t slice,
                         float* dst, int64_t dstFloats) {
     if (!c || !dst) return SIFT_ERR_INVALID_ARGUMENT;
-    if (!c->executed) return fail(c, SIFT_ERR_NOT_DETECTED, "debug download before execute");
-    if (frame < 0 || frame >= c->curFrames) return fail(c, SIFT_ERR_INVALID_ARGUMENT, "bad frame");
+    if (!c->executed || !c->last) return fail(c, SIFT_ERR_NOT_DETECTED, "debug download before execute");
+    if (frame < 0 || frame >= c->last->frames) return fail(c, SIFT_ERR_INVALID_ARGUMENT, "bad frame");
     CTX_TRY(c, cudaSetDevice(c->device));
     CTX_TRY(c, cudaStreamSynchronize(c->stream));
     const float* src = nullptr;
@@ -1088,17 +1241,17 @@ int sift_debug_download(SiftContext* c, int32_t what, int32_t frame, int32_t oct
 
 int64_t sift_debug_candidates(SiftContext* c, int32_t frame, int32_t octave, int32_t* dst,
                               int64_t capTriples) {
-    if (!c || !c->executed || frame < 0 || frame >= c->curFrames || octave < 0 || octave >= kOctaves)
+    if (!c || !c->executed || !c->last || frame < 0 || frame >= c->last->frames || octave < 0 || octave >= kOctaves)
         return -(int64_t)SIFT_ERR_INVALID_ARGUMENT;
     if (cudaSetDevice(c->device) != cudaSuccess) return -(int64_t)SIFT_ERR_CUDA;
+    const Slot& S = *c->last;
     const int seg = frame * kOctaves + octave;
-    const SiftContext::ListSet& L = c->L[(c->candSplit && octave >= 1) ? 1 : 0];
-    const int nAll = std::min(L.hCounters->nCandidates, c->capCand);
-    const int a = std::min(L.hSegStarts[seg], nAll), b = std::min(L.hSegStarts[seg + 1], nAll);
+    const int nAll = std::min(S.hCounters->nCandidates, c->capCand);
+    const int a = std::min(S.hSegStarts[seg], nAll), b = std::min(S.hSegStarts[seg + 1], nAll);
     const int n = b - a;
     if (!dst || n <= 0) return n;
     std::vector<Candidate> tmp((size_t)n);
-    if (cudaMemcpy(tmp.data(), L.dCands + a, (size_t)n * sizeof(Candidate), cudaMemcpyDeviceToHost) != cudaSuccess)
+    if (cudaMemcpy(tmp.data(), c->dCands + a, (size_t)n * sizeof(Candidate), cudaMemcpyDeviceToHost) != cudaSuccess)
         return -(int64_t)SIFT_ERR_CUDA;
     for (int i = 0; i < n && i < capTriples; i++) {
         dst[3 * i + 0] = (int32_t)(tmp[i].xys & 0x7fff);
@@ -1110,7 +1263,7 @@ int64_t sift_debug_candidates(SiftContext* c, int32_t frame, int32_t octave, int
 
 int sift_debug_blur_bench(SiftContext* c, int32_t scale, int32_t mode, int32_t iters, float* outMs) {
     if (!c || !outMs || scale < 0 || scale >= kGaussians - 1 || iters < 1) return SIFT_ERR_INVALID_ARGUMENT;
-    if (!c->executed) return fail(c, SIFT_ERR_NOT_DETECTED, "blur bench before execute");
+    if (!c->executed || !c->last) return fail(c, SIFT_ERR_NOT_DETECTED, "blur bench before execute");
     CTX_TRY(c, cudaSetDevice(c->device));
     const OctaveDev& q = c->P.oct[0];
     BlurArgs a{};
@@ -1120,8 +1273,7 @@ int sift_debug_blur_bench(SiftContext* c, int32_t scale, int32_t mode, int32_t i
     a.w = q.w; a.h = q.h; a.pitch = q.pitch;
     a.inFrameStride = a.outFrameStride = kGaussians * q.plane;
     a.dogFrameStride = kDogs * q.plane;
-    a.frames = c->curFrames;
-    a.debugMode = mode;
+    a.frames = c->last->frames;
     const bool dual = (mode & 8) != 0;   // tuning: the same launches split over two streams
     a.debugMode = mode & 7;
     cudaStream_t s2 = c->octStream[1];   // any second stream
@@ -1166,3 +1318,5 @@ int sift_debug_math(int device, int32_t op, const float* a, const float* b, floa
 }
 
 }  // extern "C"
+
+#include "capi_match.inc"

@@ -60,6 +60,20 @@ __host__ __device__ inline uint32_t packXYS(int x, int y, int s) {
     return (uint32_t)x | ((uint32_t)y << 15) | ((uint32_t)s << 30);
 }
 
+// Result columns (the wire format of include/siftcuda.h: SiftKeypointColumns /
+// SiftDescriptorColumns). The pointers are device memory (staged path) or pinned host memory
+// mapped into the device address space (host-buffer calls: the kernels' own stores are the D2H).
+struct KeypointColumnsDev {
+    float *absX, *absY, *sigma, *value, *subScale;
+    short2* scaledXY;
+    uchar2* octaveScale;
+};
+struct DescriptorColumnsDev {
+    uint8_t* features;   // [n][128]
+    float* theta;
+    int32_t* keypoint;
+};
+
 // Device-side counters of one execute (zeroed at its start).
 struct Counters {
     int nCandidates;
@@ -106,11 +120,11 @@ inline cudaError_t pdlLaunch(void (*kernel)(KArgs...), dim3 grid, dim3 block, si
 // ---- launchers (each returns cudaGetLastError of its launches) ---------------------------------
 
 // pyramid.cu
-cudaError_t launchGrayUpsample(const uint8_t* bgra, int pitchBytes, int64_t frameStrideBytes,
-                               float* gray, int W, int H, float* scaled, int w2, int h2,
-                               int pitch2, size_t scaledFrameStride, int frames,
-                               cudaStream_t st, int grayY0 = 0, int grayY1 = 0, int upY0 = 0,
-                               int upY1 = 0);
+// bytesPerPixel 4: BGRA8; 1: GRAY8 / the luma plane of NV12
+cudaError_t launchGrayUpsample(const uint8_t* pixels, int bytesPerPixel, int pitchBytes,
+                               int64_t frameStrideBytes, float* gray, int W, int H, float* scaled,
+                               int w2, int h2, int pitch2, size_t scaledFrameStride, int frames,
+                               cudaStream_t st);
 // out = blur(in); optional dog = out - in; optional decimated copy of out (every other pixel)
 struct BlurArgs {
     const float* in;
@@ -142,15 +156,24 @@ cudaError_t launchCandidateCompaction(const EngineParams& P, const uint32_t* mas
 cudaError_t launchRefine(const EngineParams& P, const Candidate* cands, int capCandidates,
                          SiftKeypoint* kpTmp, uint32_t* flagWords, int* blockSums,
                          SiftKeypoint* kps, int* kpSeg, int capKeypoints, const int* segCandStart,
-                         int* segKpStart, int nSegs, Counters* counters, cudaStream_t st);
+                         int* segKpStart, int nSegs, Counters* counters,
+                         const KeypointColumnsDev& hostCols, cudaStream_t st);
 
 // describe.cu
+// Descriptor records go to `cols` (device columns, always) and, when hostCols.features is not
+// null, to the pinned host columns as well.
 cudaError_t launchDescribe(const EngineParams& P, const SiftKeypoint* kps, const int* kpSeg,
                            int capKeypoints, const int* segKpStart, int* nOri, float* oriTmp,
-                           int* oriOffset, int* descKp, int* blockSums, SiftDescriptor* desc,
+                           int* oriOffset, int* descKp, int* blockSums,
+                           const DescriptorColumnsDev& cols, const DescriptorColumnsDev& hostCols,
                            int capDescriptors, int* segDescStart, int nSegs, Counters* counters,
-                           const int* kpIndexBase, int smCount, cudaStream_t stream,
-                           cudaEvent_t afterOrientation);
+                           int smCount, cudaStream_t stream, cudaEvent_t afterOrientation);
+
+// match.cu
+size_t matchScratchInts(int nSource, int nTarget, int smCount);
+cudaError_t launchMatch(const uint8_t* source, int nSource, const uint8_t* target, int nTarget,
+                        float absThr, float relThr, int* scratch, SiftMatch* rows, int smCount,
+                        cudaStream_t st);
 
 // math debug (capi.cu → describe.cu)
 cudaError_t launchMathDebug(int op, const float* a, const float* b, float* out, int64_t n,

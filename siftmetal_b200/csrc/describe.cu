@@ -14,6 +14,7 @@
 // *discontinuous* decision (bin index, window radius, sample coordinate, border filter) is
 // evaluated with the spec's exact operation sequence.
 #include <algorithm>
+#include <atomic>
 
 #include "common.cuh"
 #include "dev_math.cuh"
@@ -276,7 +277,6 @@ constexpr int kDescCopies = 32;    // lane-private histogram copies (16 KB per w
 constexpr int kDescWarps = 7;      // 112 KB of histograms per CTA, two CTAs (14 warps) per SM
 constexpr int kDescMaxSide = 128;  // 2·radius+1; radius <= 39 for detected keypoints
 constexpr int kDescBins = 128;
-constexpr int kDescDefaultWalk = 1;
 
 // Trilinear accumulation of one sample into the lane's histogram copy (addFeature,
 // SIFTDescriptor.metal:82-117). Two base addresses per sample (one per orientation bin); the
@@ -331,18 +331,18 @@ __device__ __forceinline__ void descAccumulate(char* const hl, const float2 gm, 
     if (c11) p1[DY + DX] = fmaf(v11, fb, t7);
 }
 
-// WALK = 0: lanes walk the flattened spans densely (x fastest, stride 32), one sample per step.
-// WALK = 1: the same walk in units of 16-byte aligned sample pairs (shipped: 0.41 vs 0.43 ms).
-// (Measured and dropped: the warp as a (32 / C)-row x C-column tile over row groups, C = 4, 8, 16 —
-// uniform control flow, but idle lane slots at the ragged span ends pay the full accumulation
-// cost: 0.60 / 0.63 / 0.74 ms against 0.46 ms for WALK 0 at the time.)
-template <int WALK, int NPAIRS = 3>
+// Lanes walk the flattened spans densely in units of 16-byte aligned sample pairs (x fastest,
+// stride 32 pairs): one LDG.128 and one row search per two samples.
+// (Measured and dropped: one sample per step, 0.43 vs 0.41 ms; the warp as a (32 / C)-row x
+// C-column tile over row groups, C = 4, 8, 16 — uniform control flow, but idle lane slots at the
+// ragged span ends pay the full accumulation cost: 0.60 / 0.63 / 0.74 ms against 0.46 ms.)
+template <int NPAIRS>
 __global__ void __launch_bounds__(kDescWarps * 32, 2)
 descriptorKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __restrict__ kps,
                  const int* __restrict__ kpSeg, const int* __restrict__ segKpStart,
                  Counters* __restrict__ counters, const int* __restrict__ oriOffset,
                  const float* __restrict__ oriTmp, const int* __restrict__ descKp,
-                 SiftDescriptor* __restrict__ desc, int capacity, const int* __restrict__ kpIndexBase) {
+                 const DescriptorColumnsDev cols, const DescriptorColumnsDev hostCols, int capacity) {
     pdlPrologue();
     extern __shared__ __align__(16) float sDesc[];  // [warp][128 bins][32 copies]
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -350,7 +350,7 @@ descriptorKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __r
     const int nKp = counters->nKeypoints;
     int nDesc = oriOffset[nKp];
     if (nDesc > capacity) nDesc = capacity;
-    const int warpsPerCta = blockDim.x >> 5;
+    constexpr int warpsPerCta = kDescWarps;
     // dynamic work queue, as in the orientation kernel (descriptor windows differ up to 4x in area)
     const int gridWarps = gridDim.x * warpsPerCta;
     int dNext = 0;
@@ -404,57 +404,9 @@ descriptorKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __r
         __syncwarp();
         char* const hl = reinterpret_cast<char*>(hist + lane);
 
-        if constexpr (WALK == 0) {
-            // lane state: row i, first x offset jlo of the row's span, span length n, position pos,
-            // gradient row pointer (already offset by ipx)
-            int i = iMin, jlo = 0, n = 0, pos = lane;
-            const float2* __restrict__ grow = g;
-            auto rowBounds = [&]() {
-                const float fi = (float)i;
-                const float lo = fmaxf(fmaxf(fmaf(fi, s1, -c1), fmaf(fi, s2, -c2)), xlo);
-                const float hi = fminf(fminf(fmaf(fi, s1, c1), fmaf(fi, s2, c2)), xhi);
-                jlo = (int)ceilf(lo - 1.0f);                 // widened by < 1 on each side, still in the plane
-                jlo = max(jlo, -ipx);
-                n = max(min((int)floorf(hi + 1.0f), o.w - 1 - ipx) - jlo + 1, 0);
-                grow = g + (size_t)(ipy + min(i, iMax)) * o.pitch + ipx;
-            };
-            auto settle = [&]() {   // move to the row that contains position pos
-                while (i <= iMax && pos >= n) {
-                    pos -= n;
-                    i++;
-                    rowBounds();
-                }
-            };
-            rowBounds();
-            settle();
-            while (__any_sync(0xffffffffu, i <= iMax)) {
-                // phase 1: four samples per lane, coordinates + gather issued back to back
-                float2 gm[4];
-                float bxs[4], bys[4], r2s[4];
-                bool ok[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int j = jlo + pos;
-                    const float fj = (float)j, fi = (float)i;
-                    const float rx = fj * a - fi * b;
-                    const float ry = fj * b + fi * a;
-                    // addValue drops cells outside [0, 4): nothing lands unless -1 < rx + 1.5 < 4, same in y
-                    ok[u] = (i <= iMax) && fabsf(rx) < 2.5f && fabsf(ry) < 2.5f;
-                    gm[u] = __ldg(grow + (ok[u] ? j : -ipx));
-                    bxs[u] = rx + 1.5f;
-                    bys[u] = ry + 1.5f;
-                    r2s[u] = rx * rx + ry * ry;
-                    pos += 32;
-                    settle();
-                }
-                // phase 2: trilinear accumulation
-#pragma unroll
-                for (int u = 0; u < 4; u++) descAccumulate(hl, gm[u], bxs[u], bys[u], r2s[u], ok[u], theta);
-            }
-        } else if constexpr (WALK == 1) {
-            // Flattened like WALK 0, but in units of 16-byte aligned sample PAIRS (even absolute x):
-            // one LDG.128 and one row search per two samples. Rows are padded to whole pairs; the
-            // padding samples fail the exact cull (or the plane check) below.
+        {
+            // Sample PAIRS start at even absolute x. Rows are padded to whole pairs; the padding
+            // samples fail the exact cull (or the plane check) below.
             int i = iMin, xs = 0, np = 0, q = lane;
             float fi = smallIntToFloat(iMin);
             const float2* __restrict__ grow = g + (size_t)(ipy + iMin) * o.pitch;
@@ -550,15 +502,17 @@ descriptorKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __r
         for (int q = 0; q < 4; q++)
             bytes[q * 32 + lane] = (uint8_t)(int)fminf(255.0f, __fmul_rn(f[q], 512.0f));
         __syncwarp();
-        // one contiguous 136-byte record (the result array may be pinned host memory: the stores
-        // then leave over PCIe as whole records while the kernel keeps running)
-        uint32_t* rec = reinterpret_cast<uint32_t*>(desc + d);
-        rec[2 + lane] = reinterpret_cast<const uint32_t*>(bytes)[lane];
-        if (lane < 2) {
-            // index in the frame's keypoint array; kpIndexBase: keypoints of this frame that live in
-            // an earlier list (octave 0 is compacted separately on single large frames)
-            const int kIndex = k - segKpStart[frame * kOctaves] + (kpIndexBase ? *kpIndexBase : 0);
-            rec[lane] = lane == 0 ? (uint32_t)kIndex : __float_as_uint(theta);
+        // result columns: the 128 feature bytes as one coalesced 128-byte row of the dense
+        // [n][128] matrix (the operand layout of the matcher), theta and the keypoint's index in its
+        // frame beside it. hostCols (pinned host memory, when set) receives the same: those stores
+        // leave over PCIe as whole rows while the kernel keeps running — they are the D2H.
+        const uint32_t word = reinterpret_cast<const uint32_t*>(bytes)[lane];
+        const int kIndex = k - segKpStart[frame * kOctaves];
+        reinterpret_cast<uint32_t*>(cols.features + (size_t)d * kDescBins)[lane] = word;
+        if (lane == 0) { cols.theta[d] = theta; cols.keypoint[d] = kIndex; }
+        if (hostCols.features) {
+            reinterpret_cast<uint32_t*>(hostCols.features + (size_t)d * kDescBins)[lane] = word;
+            if (lane == 0) { hostCols.theta[d] = theta; hostCols.keypoint[d] = kIndex; }
         }
         __syncwarp();
     }
@@ -566,10 +520,10 @@ descriptorKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __r
 
 cudaError_t launchDescribe(const EngineParams& P, const SiftKeypoint* kps, const int* kpSeg,
                            int capKeypoints, const int* segKpStart, int* nOri, float* oriTmp,
-                           int* oriOffset, int* descKp, int* blockSums, SiftDescriptor* desc,
+                           int* oriOffset, int* descKp, int* blockSums,
+                           const DescriptorColumnsDev& cols, const DescriptorColumnsDev& hostCols,
                            int capDescriptors, int* segDescStart, int nSegs, Counters* counters,
-                           const int* kpIndexBase, int smCount, cudaStream_t st,
-                           cudaEvent_t afterOrientation) {
+                           int smCount, cudaStream_t st, cudaEvent_t afterOrientation) {
     SIFT_CUDA_TRY(pdlLaunch(orientationKernel, dim3(smCount * 4), dim3(kOriWarps * 32), 0, st, true, P, kps, kpSeg,
                             counters, nOri, oriTmp));
     const int nBlocks = (capKeypoints + 1 + kScanChunk - 1) / kScanChunk;
@@ -583,23 +537,19 @@ cudaError_t launchDescribe(const EngineParams& P, const SiftKeypoint* kps, const
                             kpSeg, segDescStart, nSegs));
     if (afterOrientation) SIFT_CUDA_TRY(cudaEventRecord(afterOrientation, st));
 
-    static const int warps = getenv("SIFTCUDA_DESC_WARPS")
-                                 ? std::max(1, std::min(atoi(getenv("SIFTCUDA_DESC_WARPS")), kDescWarps))
-                                 : kDescWarps;
-    const int perWarp = kDescBins * kDescCopies * (int)sizeof(float);
-    const int smemBytes = warps * perWarp;
+    const int smemBytes = kDescWarps * kDescBins * kDescCopies * (int)sizeof(float);
     const int ctasPerSm = (228 * 1024) / (smemBytes + 1024);
-    static const int walk = getenv("SIFTCUDA_DESC_WALK") ? atoi(getenv("SIFTCUDA_DESC_WALK")) : kDescDefaultWalk;
-    auto launch = [&](auto kernel) -> cudaError_t {
+    auto kernel = descriptorKernel<3>;
+    static std::atomic<unsigned long long> configured{0};   // per-device bit, as in launchBlurCfg
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!((configured.load(std::memory_order_acquire) >> (dev & 63)) & 1ull)) {
         SIFT_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes));
-        return pdlLaunch(kernel, dim3(smCount * ctasPerSm), dim3(warps * 32), (size_t)smemBytes, st, true, P, kps,
-                         kpSeg, segKpStart, counters, (const int*)oriOffset, (const float*)oriTmp,
-                         (const int*)descKp, desc, capDescriptors, kpIndexBase);
-    };
-    switch (walk) {
-        case 1: return launch(descriptorKernel<1>);
-        default: return launch(descriptorKernel<0>);
+        configured.fetch_or(1ull << (dev & 63), std::memory_order_release);
     }
+    return pdlLaunch(kernel, dim3(smCount * ctasPerSm), dim3(kDescWarps * 32), (size_t)smemBytes, st, true, P, kps,
+                     kpSeg, segKpStart, counters, (const int*)oriOffset, (const float*)oriTmp,
+                     (const int*)descKp, cols, hostCols, capDescriptors);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -534,7 +534,7 @@ scatterKeypointsKernel(const uint32_t* __restrict__ flags, const Counters* __res
                        const int* __restrict__ blockOffsets, const Candidate* __restrict__ cands,
                        const SiftKeypoint* __restrict__ kpTmp, SiftKeypoint* __restrict__ kps,
                        int* __restrict__ kpSeg, int capacity, const int* __restrict__ candSegStart,
-                       int* __restrict__ kpSegStart, int nSegs) {
+                       int* __restrict__ kpSegStart, int nSegs, const KeypointColumnsDev hc) {
     pdlPrologue();
     const int n = counters->nCandidates;
     const int i = blockIdx.x * kRefineThreads + threadIdx.x;
@@ -560,15 +560,28 @@ scatterKeypointsKernel(const uint32_t* __restrict__ flags, const Counters* __res
     int pos = blockOffsets[blockIdx.x] + __popc(mine & ((1u << lane) - 1u));
     for (int k = 0; k < wid; k++) pos += __popc(w[k]);
     if (pos < capacity) {
-        kps[pos] = kpTmp[i];
+        const SiftKeypoint k = kpTmp[i];
+        kps[pos] = k;
         kpSeg[pos] = cands[i].seg;
+        if (hc.absX) {
+            // result columns (SiftKeypointColumns), usually pinned host memory: these stores are the
+            // D2H of the keypoints; consecutive threads write consecutive slots of each column
+            hc.absX[pos] = k.absoluteX;
+            hc.absY[pos] = k.absoluteY;
+            hc.sigma[pos] = k.sigma;
+            hc.value[pos] = k.value;
+            hc.subScale[pos] = k.subScale;
+            hc.scaledXY[pos] = make_short2((short)k.scaledX, (short)k.scaledY);
+            hc.octaveScale[pos] = make_uchar2((unsigned char)k.octave, (unsigned char)k.scale);
+        }
     }
 }
 
 cudaError_t launchRefine(const EngineParams& P, const Candidate* cands, int capCandidates,
                          SiftKeypoint* kpTmp, uint32_t* flagWords, int* blockSums,
                          SiftKeypoint* kps, int* kpSeg, int capKeypoints, const int* segCandStart,
-                         int* segKpStart, int nSegs, Counters* counters, cudaStream_t st) {
+                         int* segKpStart, int nSegs, Counters* counters,
+                         const KeypointColumnsDev& hostCols, cudaStream_t st) {
     const int nBlocks = (capCandidates + kRefineThreads - 1) / kRefineThreads;
     SIFT_CUDA_TRY(pdlLaunch(refineKernel, dim3(nBlocks), dim3(kRefineThreads), 0, st, true, P, cands,
                             (const Counters*)counters, kpTmp, flagWords, blockSums));
@@ -576,7 +589,8 @@ cudaError_t launchRefine(const EngineParams& P, const Candidate* cands, int capC
                                     &counters->overflow, 2, st));
     return pdlLaunch(scatterKeypointsKernel, dim3(nBlocks), dim3(kRefineThreads), 0, st, true,
                      (const uint32_t*)flagWords, (const Counters*)counters, (const int*)blockSums, cands,
-                     (const SiftKeypoint*)kpTmp, kps, kpSeg, capKeypoints, segCandStart, segKpStart, nSegs);
+                     (const SiftKeypoint*)kpTmp, kps, kpSeg, capKeypoints, segCandStart, segKpStart, nSegs,
+                     hostCols);
 }
 
 }  // namespace sift

@@ -8,6 +8,7 @@
 //   Subtract.metal:12-21, NearestNeighborDownScale.metal:15-22            → blurKernel
 //   SIFTGradient.metal:15-39                                              → gradientKernel
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -41,74 +42,9 @@ __device__ __forceinline__ int symmetrized(int i, int l) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Gray conversion: 4 pixels per thread. byte/255 has only 256 values, so the (exactly rounded)
-// quotients are tabulated once per CTA in shared memory instead of 12 IEEE divisions per thread.
-__global__ void __launch_bounds__(256)
-grayKernel(const uint8_t* __restrict__ bgra, int pitchBytes, int64_t frameStrideBytes,
-           float* __restrict__ gray, int W, int H, int yBegin) {
-    __shared__ float lut[256];
-    lut[threadIdx.x] = (float)threadIdx.x / 255.0f;
-    __syncthreads();
-    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int y = yBegin + blockIdx.y, f = blockIdx.z;
-    if (x4 >= W) return;
-    const uint8_t* row = bgra + (size_t)f * frameStrideBytes + (size_t)y * pitchBytes;
-    float* out = gray + ((size_t)f * H + y) * W;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int x = x4 + k;
-        if (x < W) {
-            const uchar4 p = *reinterpret_cast<const uchar4*>(row + 4 * x);  // b, g, r, a
-            const float b = lut[p.x], g = lut[p.y], r = lut[p.z];
-            out[x] = ((0.0f + (0.212639005871510f * r)) + (0.715168678767756f * g)) +
-                     (0.072192315360734f * b);
-        }
-    }
-}
-
-// 2x bilinear upsample (BilinearUpScale.metal:12-64), the reference's general formula evaluated
-// per output pixel; 4 consecutive outputs per thread.
-__global__ void __launch_bounds__(256)
-upsampleKernel(const float* __restrict__ gray, int W, int H, float* __restrict__ scaled, int w2,
-               int h2, int pitch2, size_t scaledFrameStride, int yBegin) {
-    const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int j = yBegin + blockIdx.y, f = blockIdx.z;
-    if (i0 >= w2) return;
-    const float* __restrict__ src = gray + (size_t)f * W * H;
-    const float dx = (float)W / (float)w2;
-    const float dy = (float)H / (float)h2;
-    const float y = (float)j * dy;
-    int jm = (int)y, jp = jm + 1;
-    if (jp >= H) jp = 2 * H - 1 - jp;
-    if (jm >= H) jm = 2 * H - 1 - jm;
-    const float fy = y - floorf(y);
-    const float* __restrict__ rowP = src + (size_t)jp * W;
-    const float* __restrict__ rowM = src + (size_t)jm * W;
-    float o[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int i = i0 + k;
-        const float x = (float)i * dx;
-        int im = (int)x, ip = im + 1;
-        if (ip >= W) ip = 2 * W - 1 - ip;
-        if (im >= W) im = 2 * W - 1 - im;
-        const float fx = x - floorf(x);
-        const float c0 = __ldg(rowP + ip), c1 = __ldg(rowM + ip);
-        const float c2 = __ldg(rowP + im), c3 = __ldg(rowM + im);
-        const float a = (fy * c0) + ((1 - fy) * c1);
-        const float b = (fy * c2) + ((1 - fy) * c3);
-        o[k] = (fx * a) + ((1 - fx) * b);
-    }
-    float* dst = scaled + (size_t)f * scaledFrameStride + (size_t)j * pitch2 + i0;
-    if (i0 + 3 < w2) {
-        *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-    } else {
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-            if (i0 + k < w2) dst[k] = o[k];
-    }
-}
-
+// Seed stage. byte/255 has only 256 values, so the (exactly rounded) quotients are tabulated once
+// per CTA in shared memory instead of IEEE divisions per pixel.
+//
 // Gray conversion + exact 2x upsample in one pass (w2 = 2W, h2 = 2H: the only ratio the pipeline
 // uses). A thread owns gray pixels (2n, 2n + 1) of row m: it converts the 3 x 2 BGRA patch
 // (columns 2n .. 2n + 2, rows m, m + 1, mirrored at the edges), writes its two gray pixels and
@@ -177,32 +113,88 @@ grayUpsample2xKernel(const uint8_t* __restrict__ bgra, int pitchBytes, int64_t f
     }
 }
 
-// Gray rows [grayY0, grayY1) and upsampled rows [upY0, upY1) (0, 0 = all): a large single frame
-// arrives in two row chunks, each converted as soon as it has landed.
-cudaError_t launchGrayUpsample(const uint8_t* bgra, int pitchBytes, int64_t frameStrideBytes,
-                               float* gray, int W, int H, float* scaled, int w2, int h2,
-                               int pitch2, size_t scaledFrameStride, int frames,
-                               cudaStream_t st, int grayY0, int grayY1, int upY0, int upY1) {
-    if (grayY1 <= 0) { grayY0 = 0; grayY1 = H; }
-    if (upY1 <= 0) { upY0 = 0; upY1 = h2; }
-    if (w2 == 2 * W && h2 == 2 * H && !(upY0 & 1) && !(upY1 & 1) && W >= 2 && H >= 2) {
-        // fused: gray rows [upY0 / 2, upY1 / 2) and their upsampled rows (needs input row upY1 / 2 too)
-        const int m0 = upY0 / 2, m1 = upY1 / 2;
-        if (m1 > m0) {
-            dim3 g((unsigned)(((W + 1) / 2 + 255) / 256), (unsigned)(m1 - m0), (unsigned)frames);
-            grayUpsample2xKernel<<<g, 256, 0, st>>>(bgra, pitchBytes, frameStrideBytes, gray, W, H, scaled,
-                                                    pitch2, scaledFrameStride, m0);
+// GRAY8 / NV12-luma input (include/siftcuda.h SIFT_INPUT_GRAY8): a gray byte v is converted as
+// the BGRA pixel (v, v, v) would be — the same luminance expression on l = v / 255, tabulated per
+// CTA — so the planes are bit-identical to the BGRA path on the gray-expanded frame, at 1 byte
+// instead of 4 read per pixel. A thread owns gray pixels 4n .. 4n + 3 of row m: it reads the 5 x 2
+// byte patch (columns 4n .. 4n + 4, rows m, m + 1, mirrored at the edges) and writes its four
+// gray pixels and the 8 x 2 block of upsampled pixels that depend on nothing else.
+__global__ void __launch_bounds__(256)
+gray8Upsample2xKernel(const uint8_t* __restrict__ luma, int pitchBytes, int64_t frameStrideBytes,
+                      float* __restrict__ gray, int W, int H, float* __restrict__ scaled, int pitch2,
+                      size_t scaledFrameStride) {
+    __shared__ float lut[256];
+    {
+        const float l = (float)threadIdx.x / 255.0f;
+        lut[threadIdx.x] = ((0.0f + (0.212639005871510f * l)) + (0.715168678767756f * l)) +
+                           (0.072192315360734f * l);
+    }
+    __syncthreads();
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = blockIdx.y, f = blockIdx.z;
+    const int c0 = 4 * n;
+    if (c0 >= W) return;
+    const int w2 = 2 * W;
+    int mp = m + 1;
+    if (mp >= H) mp = 2 * H - 1 - mp;
+    const uint8_t* img = luma + (size_t)f * frameStrideBytes;
+    float g[2][5];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const uint8_t* row = img + (size_t)(r == 0 ? m : mp) * pitchBytes;
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            int c = c0 + k;
+            if (c >= W) c = 2 * W - 1 - c;      // ip = im + 1 mirrored (BilinearUpScale.metal:36-48)
+            c = max(c, 0);
+            g[r][k] = lut[__ldg(row + c)];
         }
-        return cudaGetLastError();
     }
-    if (grayY1 > grayY0) {
-        dim3 g1((W + 1023) / 1024, grayY1 - grayY0, frames);
-        grayKernel<<<g1, 256, 0, st>>>(bgra, pitchBytes, frameStrideBytes, gray, W, H, grayY0);
-        SIFT_CUDA_TRY(cudaGetLastError());
+    float* grow = gray + ((size_t)f * H + m) * W;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (c0 + k < W) grow[c0 + k] = g[0][k];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const float fy = r ? 0.5f : 0.0f;
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int im = k >> 1, ip = im + 1;
+            const float fx = (k & 1) ? 0.5f : 0.0f;
+            const float a = (fy * g[1][ip]) + ((1 - fy) * g[0][ip]);
+            const float b = (fy * g[1][im]) + ((1 - fy) * g[0][im]);
+            o[k] = (fx * a) + ((1 - fx) * b);
+        }
+        float* dst = scaled + (size_t)f * scaledFrameStride + (size_t)(2 * m + r) * pitch2 + 8 * n;
+        if (8 * n + 7 < w2) {
+            reinterpret_cast<float4*>(dst)[0] = make_float4(o[0], o[1], o[2], o[3]);
+            reinterpret_cast<float4*>(dst)[1] = make_float4(o[4], o[5], o[6], o[7]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                if (8 * n + k < w2) dst[k] = o[k];
+        }
     }
-    if (upY1 > upY0) {
-        dim3 g2((w2 + 1023) / 1024, upY1 - upY0, frames);
-        upsampleKernel<<<g2, 256, 0, st>>>(gray, W, H, scaled, w2, h2, pitch2, scaledFrameStride, upY0);
+}
+
+// DifferenceOfGaussians.encodeSeedTexture (:357-389) up to the blur: luminosity + 2x bilinear.
+// The pyramid always doubles exactly (w2 = Int(W / 0.5) = 2 W, DifferenceOfGaussians.swift:235-238).
+cudaError_t launchGrayUpsample(const uint8_t* pixels, int bytesPerPixel, int pitchBytes,
+                               int64_t frameStrideBytes, float* gray, int W, int H, float* scaled,
+                               int w2, int h2, int pitch2, size_t scaledFrameStride, int frames,
+                               cudaStream_t st) {
+    if (w2 != 2 * W || h2 != 2 * H || W < 2 || H < 2) return cudaErrorInvalidValue;
+    if (bytesPerPixel == 4) {
+        dim3 g((unsigned)(((W + 1) / 2 + 255) / 256), (unsigned)H, (unsigned)frames);
+        grayUpsample2xKernel<<<g, 256, 0, st>>>(pixels, pitchBytes, frameStrideBytes, gray, W, H, scaled,
+                                                pitch2, scaledFrameStride, 0);
+    } else if (bytesPerPixel == 1) {
+        dim3 g((unsigned)(((W + 3) / 4 + 255) / 256), (unsigned)H, (unsigned)frames);
+        gray8Upsample2xKernel<<<g, 256, 0, st>>>(pixels, pitchBytes, frameStrideBytes, gray, W, H, scaled,
+                                                 pitch2, scaledFrameStride);
+    } else {
+        return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
 }
@@ -449,13 +441,15 @@ static cudaError_t launchBlurCfg(const BlurArgs& a, const Taps& taps, cudaStream
     static_assert(C::IN_W % 4 == 0 && C::IP % 8 == 4 && C::TP % 8 == 4, "bank layout");
     static_assert(TX % C::XSEG == 0 && C::RY >= 1 && TY % C::RY == 0 && C::NG == 3, "tile shape");
     const int smemBytes = C::SMEM_FLOATS * (int)sizeof(float);
-    static unsigned long long configured = 0;  // per-device bit: the attribute is per device
+    // per-device bit (the attribute is per device); contexts on separate host threads may race
+    // here, so the word is atomic — setting the attribute twice is harmless, losing a bit is not
+    static std::atomic<unsigned long long> configured{0};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (!((configured >> (dev & 63)) & 1ull)) {
+    if (!((configured.load(std::memory_order_acquire) >> (dev & 63)) & 1ull)) {
         SIFT_CUDA_TRY(cudaFuncSetAttribute(blurKernel<NTAPS, TX, TY, NT, DOG, HALF>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes));
-        configured |= 1ull << (dev & 63);
+        configured.fetch_or(1ull << (dev & 63), std::memory_order_release);
     }
     const int rows = (a.yEnd > 0 ? a.yEnd : a.h) - a.yBegin;
     const long nTiles = (long)((a.w + TX - 1) / TX) * ((rows + TY - 1) / TY) * a.frames;

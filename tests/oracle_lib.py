@@ -46,6 +46,8 @@ def lib():
         L.oracle_get_plane.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.oracle_get_info.argtypes = [C.c_void_p, C.POINTER(_abi.SiftInfo)]
         L.oracle_math.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+        L.oracle_match.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_void_p]
+        L.oracle_match.restype = C.c_int64
         _lib = L
     return _lib
 
@@ -147,3 +149,13 @@ def oracle_math(op, a, b=None):
     out = np.zeros_like(a)
     lib().oracle_math(op, a.ctypes.data, b.ctypes.data, out.ctypes.data, a.size)
     return out
+
+
+def oracle_match(source, target, absolute_threshold=300.0, relative_threshold=0.6):
+    """SIFTDescriptor.match (SIFTDescriptor.swift:298-361) on [n, 128] uint8 feature matrices."""
+    a = np.ascontiguousarray(source, dtype=np.uint8).reshape(-1, 128)
+    b = np.ascontiguousarray(target, dtype=np.uint8).reshape(-1, 128)
+    out = np.zeros(max(len(a), 1), dtype=_abi.MATCH_DTYPE)
+    n = lib().oracle_match(a.ctypes.data, len(a), b.ctypes.data, len(b), absolute_threshold, relative_threshold,
+                           out.ctypes.data)
+    return out[:n].copy()

@@ -72,3 +72,60 @@ def test_two_rank_gloo_gather(tmp_path):
     line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
     out = json.loads(line)
     assert out["world"] == 2 and out["frames"] == list(range(37)) and out["max_time"] == 1.5
+
+
+def test_two_rank_shared_memory_gather(tmp_path):
+    """ShmGather (the bench's host gather): two gloo ranks publish fake result columns of their frame
+    shards; rank 0 reads every frame of the job in frame order from the mapped segments."""
+    script = tmp_path / "gworker.py"
+    script.write_text(textwrap.dedent(
+        """
+        import os, sys, json
+        sys.path.insert(0, %r)
+        import numpy as np
+        import torch.distributed as dist
+        from siftmetal_b200.sharding import ShmGather, shard_range
+        from siftmetal_b200.api import BatchResult, KeypointColumns, DescriptorColumns
+        dist.init_process_group("gloo")
+        rank, world = dist.get_rank(), dist.get_world_size()
+        total = 9
+        a, b = shard_range(total, rank, world)
+        sizes = np.ones((7, 2), np.float32)
+
+        def fake(frames, step):      # frame f owns f + 1 keypoints in octave 0, each with one descriptor
+            n = sum(f + 1 for f in frames)
+            kc = np.zeros((len(frames), 7), np.int32); kc[:, 0] = [f + 1 for f in frames]
+            ids = np.concatenate([np.full(f + 1, 100 * step + f, np.float32) for f in frames])
+            kv = KeypointColumns(ids, ids, ids, ids, ids, np.zeros((n, 2), np.int16), np.zeros((n, 2), np.uint8), sizes)
+            dv = DescriptorColumns(np.repeat(ids.astype(np.uint8)[:, None], 128, 1), ids, np.arange(n, dtype=np.int32))
+            return BatchResult(kv, dv, kc, kc.copy(), kc.copy())
+
+        g = ShmGather(rank, world, n_local=b - a, cap_kp=64, cap_desc=64, tag="t%%d" %% os.getpid() if world == 1 else os.environ["MASTER_PORT"])
+        out = []
+        for step in range(3):
+            mine = list(range(a, b))
+            half = len(mine) // 2               # two calls (chunks) per step
+            g.publish(fake(mine[:half], step), 0)
+            g.publish(fake(mine[half:], step), half)
+            g.step_done()
+            if rank == 0:
+                for f in range(total):
+                    kp, desc = g.frame(f)
+                    assert len(kp["sigma"]) == f + 1 and np.all(kp["sigma"] == 100 * step + f), (step, f)
+                    assert desc["features"].shape == (f + 1, 128) and np.all(desc["theta"] == 100 * step + f)
+                out.append(int(g.last["keypoint_counts"].sum()))
+        if rank == 0:
+            print(json.dumps({"sums": out, "stats": g.summary()}))
+        g.close()
+        dist.destroy_process_group()
+        """ % ROOT))
+    port = _free_port()
+    r = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+         "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+        capture_output=True, text=True, timeout=240, env={**os.environ, "OMP_NUM_THREADS": "1"})
+    assert r.returncode == 0, r.stderr[-3000:]
+    import json
+
+    out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert out["sums"] == [45, 45, 45] and out["stats"]["frames"] == 27 and out["stats"]["keypoints"] == 135
