@@ -920,12 +920,15 @@ int checkImages(SiftContext* c, const void* const* images, int n, int pitchBytes
     return SIFT_OK;
 }
 
-int submitHost(SiftContext* c, const void* const* images, int n, int pitchBytes, bool withDescribe) {
+int submitHost(SiftContext* c, const void* const* images, int n, int pitchBytes, bool withDescribe, bool synchronous) {
     int r = checkImages(c, images, n, pitchBytes, "submit: bad arguments");
     if (r != SIFT_OK) return r;
     if (c->nPending >= 2) return fail(c, SIFT_ERR_BUSY, "both in-flight slots are taken: call sift_wait first");
     CTX_TRY(c, cudaSetDevice(c->device));
-    if (c->nPending == 0) c->head = c->next = 0;   // purely synchronous callers never touch slot 1
+    // synchronous callers only ever use slot 0 (slot 1 is allocated by the first overlapping
+    // submit); pipelined callers alternate, so a result stays valid across the next submit
+    if (synchronous) c->next = 0;
+    if (c->nPending == 0) c->head = c->next;
     const int s = c->next;
     r = ensureSlot(c, s);
     if (r != SIFT_OK) return r;
@@ -969,7 +972,7 @@ extern "C" {
 
 int sift_submit(SiftContext* c, const void* const* images, int32_t n, int32_t pitchBytes) {
     if (!c) return SIFT_ERR_INVALID_ARGUMENT;
-    return submitHost(c, images, n, pitchBytes, true);
+    return submitHost(c, images, n, pitchBytes, true, false);
 }
 
 int sift_wait(SiftContext* c, SiftBatchResult* out) {
@@ -981,7 +984,7 @@ int sift_detect_and_describe_batch(SiftContext* c, const void* const* images, in
                                    int32_t pitchBytes, SiftBatchResult* out) {
     if (!c || !out) return SIFT_ERR_INVALID_ARGUMENT;
     if (c->nPending) return fail(c, SIFT_ERR_BUSY, "synchronous call with submitted work in flight");
-    const int r = submitHost(c, images, n, pitchBytes, true);
+    const int r = submitHost(c, images, n, pitchBytes, true, true);
     if (r != SIFT_OK) return r;
     return waitOldest(c, out);
 }
@@ -1108,7 +1111,7 @@ int sift_detect(SiftContext* c, const void* pixels, int32_t pitchBytes,
     if (!c || !pixels || !outKps || !counts) return SIFT_ERR_INVALID_ARGUMENT;
     if (c->nPending) return fail(c, SIFT_ERR_BUSY, "synchronous call with submitted work in flight");
     const void* imgs[1] = {pixels};
-    int r = submitHost(c, imgs, 1, pitchBytes, false);
+    int r = submitHost(c, imgs, 1, pitchBytes, false, true);
     if (r != SIFT_OK) return r;
     SiftBatchResult res;
     const int re = waitOldest(c, &res);
