@@ -79,6 +79,7 @@ def load_library():
     L.sift_last_error_string.argtypes = [vp]
     L.sift_last_error_string.restype = C.c_char_p
     L.sift_set_stage_timing.argtypes = [vp, i32]
+    L.sift_set_graph_replay.argtypes = [vp, i32]
     L.sift_last_timings.argtypes = [vp, C.POINTER(SiftTimings)]
     L.sift_debug_download.argtypes = [vp, i32, i32, i32, i32, vp, i64]
     L.sift_debug_candidates.argtypes = [vp, i32, i32, vp, i64]
@@ -94,7 +95,7 @@ EXPORTED_SYMBOLS = (
     "sift_detect_and_describe_batch sift_submit sift_wait sift_pending sift_batch_upload "
     "sift_batch_set_device_input sift_batch_execute sift_batch_download sift_materialize_keypoints "
     "sift_materialize_descriptors sift_match sift_match_frames sift_status_string "
-    "sift_last_error_string sift_set_stage_timing sift_last_timings sift_debug_download "
+    "sift_last_error_string sift_set_stage_timing sift_set_graph_replay sift_last_timings sift_debug_download "
     "sift_debug_candidates sift_debug_math sift_debug_blur_bench"
 ).split()
 
@@ -414,6 +415,9 @@ class Engine:
 
     def set_stage_timing(self, enabled):
         self._check(self.L.sift_set_stage_timing(self.ctx, int(enabled)))
+
+    def set_graph_replay(self, enabled):
+        self._check(self.L.sift_set_graph_replay(self.ctx, int(enabled)))
 
     def blur_bench(self, scale, mode=0, iters=20):
         ms = C.c_float()

@@ -4,9 +4,12 @@
 //   GaussianKernel / GaussianSeriesKernel taps (GaussianKernel.swift:20-43, GaussianSeriesKernel.swift:27-51)
 //   SIFT.getKeypoints / getDescriptors         (SIFT.swift:147-238)
 // One context = one device, one compute stream (+ forked octave / band streams) and one copy
-// stream. A call's whole device work — ~70 kernels on a fork / join DAG of streams — is recorded
-// once per (slot, batch size, input) as a CUDA graph and replayed with a single launch, the way
-// the reference encodes its 102 dispatches into one command buffer (SIFT.swift:157-172). Results
+// stream. A call's whole device work — ~70 kernels on a fork / join DAG of streams — can be
+// recorded once per (slot, batch size, input) as a CUDA graph and replayed with a single launch,
+// the way the reference encodes its 102 dispatches into one command buffer (SIFT.swift:157-172);
+// measured on B200 the replay costs the host ~10x less but runs ~4 % longer on the device than
+// the same launches with programmatic dependent launch and prioritised streams, so it is opt-in
+// (sift_set_graph_replay) for hosts that drive many GPUs. Results
 // leave the device through the kernels' own stores into pinned host columns, so nothing but a
 // 24-byte counter block and the segment starts is copied after the last kernel. Two in-flight
 // slots (input arena + result columns each) let the upload of call i + 1 run under the kernels of
@@ -80,6 +83,7 @@ struct SiftContext {
     // octave o >= 1 runs its blur chain + gradient + extrema mask on its own stream as soon as
     // octave o-1 has produced Gaussian slice 3 (fork / join around the main stream)
     cudaStream_t octStream[kOctaves]{};
+    int octPriority[kOctaves]{};
 
     // Large octaves are split into row bands that run as independent chains of blur launches
     // (each band recomputes the few halo rows the later scales need, so there is no dependency
@@ -98,6 +102,8 @@ struct SiftContext {
     int seedNtaps = 0;
     Taps taps[kGaussians - 1]{};
     int ntaps[kGaussians - 1]{};
+    BlurTmaSet seedTma{};              // tensor maps of the upsampled plane (seed blur input)
+    BlurTmaSet octTma[kOctaves]{};     // ... and of every octave's Gaussian stack
 
     int B = 1;       // max_batch
     int nSegs = 0;   // B * 7
@@ -134,8 +140,8 @@ struct SiftContext {
     int curFrames = 0;
     bool executed = false;      // pyramid + gradients of the last call are on the device
 
-    // CUDA graphs
-    bool graphsEnabled = true;
+    // CUDA graphs (opt-in: sift_set_graph_replay / SIFTCUDA_GRAPH=1)
+    bool graphsEnabled = false;
     std::vector<GraphEntry> graphs;
     uint64_t useCounter = 0;
 
@@ -515,6 +521,15 @@ int sift_create(const SiftConfig* cfg, int device, SiftContext** out) {
         A(devAlloc(c, &block, columnsBytes((size_t)c->capKp, (size_t)c->capDesc)));
         if (e == cudaSuccess) c->dev = carveColumns(block, (size_t)c->capKp, (size_t)c->capDesc);
     }
+    if (e == cudaSuccess) {
+        // TMA descriptors for the blur's interior tiles (cuTensorMapEncodeTiled through the runtime's
+        // driver entry point); a plane set too small for any interior tile just keeps cp.async loads
+        A(makeBlurTmaSet(&c->seedTma, c->dScaled, c->P.oct[0].pitch, c->P.oct[0].h, (int)B, c->P.oct[0].plane));
+        for (int o = 0; o < kOctaves; o++) {
+            const OctaveDev& q = c->P.oct[o];
+            if (q.w >= 1 && q.h >= 1) A(makeBlurTmaSet(&c->octTma[o], q.G, q.pitch, q.h, (int)B * kGaussians, q.plane));
+        }
+    }
     if (e == cudaSuccess) A(cudaMemset(c->dMask, 0, maskWords * sizeof(uint32_t)));
     // row padding (columns w..pitch) is read by the extrema kernel's full-warp loads and masked
     // afterwards: give it defined contents once
@@ -545,7 +560,9 @@ int sift_create(const SiftConfig* cfg, int device, SiftContext** out) {
         // smaller octaves form a long dependent chain of tiny launches: give their streams a higher
         // priority so that their CTAs are placed ahead of the big octave-0 kernels' when SM slots
         // free up (the chain is latency-critical, octave 0 is throughput-bound)
-        if (o > 0) A(cudaStreamCreateWithPriority(&c->octStream[o], cudaStreamNonBlocking, std::max(prioHigh, prioLow - o)));
+        // (0 = "no explicit priority" in BlurArgs: octave 0 keeps the default)
+        c->octPriority[o] = std::max(prioHigh, prioLow - o);
+        if (o > 0) A(cudaStreamCreateWithPriority(&c->octStream[o], cudaStreamNonBlocking, c->octPriority[o]));
         A(cudaEventCreateWithFlags(&c->evSeeded[o], cudaEventDisableTiming));
         A(cudaEventCreateWithFlags(&c->evOctDone[o], cudaEventDisableTiming));
     }
@@ -577,6 +594,12 @@ int sift_get_info(const SiftContext* c, SiftInfo* out) {
 int sift_set_stage_timing(SiftContext* c, int32_t enabled) {
     if (!c) return SIFT_ERR_INVALID_ARGUMENT;
     c->stageTiming = enabled != 0;
+    return SIFT_OK;
+}
+
+int sift_set_graph_replay(SiftContext* c, int32_t enabled) {
+    if (!c) return SIFT_ERR_INVALID_ARGUMENT;
+    c->graphsEnabled = enabled != 0;
     return SIFT_OK;
 }
 
@@ -648,6 +671,9 @@ int enqueuePipeline(SiftContext* c, const RunArgs& r, bool T) {
         seed.inFrameStride = o0.plane;
         seed.outFrameStride = kGaussians * o0.plane;
         seed.frames = F;
+        seed.tmaSet = &c->seedTma;
+        seed.tmaZ0 = 0;
+        seed.tmaZStride = 1;
         CTX_TRY(c, launchBlur(seed, c->seedTaps, c->seedNtaps, st));
         c->launches += 2;
         if (T) CTX_TRY(c, cudaEventRecord(c->ev[1], st));
@@ -706,6 +732,10 @@ int enqueuePipeline(SiftContext* c, const RunArgs& r, bool T) {
                         a.halfFrameStride = kGaussians * nx.plane;
                     }
                     a.frames = F;
+                    a.tmaSet = &c->octTma[o];
+                    a.tmaZ0 = s;
+                    a.tmaZStride = kGaussians;
+                    a.priority = c->octPriority[o];
                     // small planes: scale s + 1 launches under scale s (programmatic dependent launch)
                     static const int pdlMaxTiles = getenv("SIFTCUDA_PDL_TILES") ? atoi(getenv("SIFTCUDA_PDL_TILES")) : 160;
                     a.pdl = (s > 0 && !banded && (long)((q.w + 31) / 32) * ((q.h + 31) / 32) * F <= pdlMaxTiles) ? 1 : 0;
@@ -722,10 +752,11 @@ int enqueuePipeline(SiftContext* c, const RunArgs& r, bool T) {
             }
             if (o == 0) c->bandedOctave0 = banded;
             if (T && o == 0) CTX_TRY(c, cudaEventRecord(c->evBlur0[kGaussians - 1], so));
-            if (!(dbgSkip & 1)) CTX_TRY(c, launchGradient(q, F, so));
+            const int prio = c->octPriority[o] ? c->octPriority[o] : kNoPriority;
+            if (!(dbgSkip & 1)) CTX_TRY(c, launchGradient(q, F, so, 0, 0, prio));
             c->launches++;
             if (q.w >= 3 && q.h >= 3 && !(dbgSkip & 2)) {
-                CTX_TRY(c, launchExtremaMask(c->P, o, c->dMask, F, so));
+                CTX_TRY(c, launchExtremaMask(c->P, o, c->dMask, F, so, 0, 0, prio));
                 c->launches++;
             }
             if (o > 0) CTX_TRY(c, cudaEventRecord(c->evOctDone[o], so));
@@ -1277,6 +1308,9 @@ int sift_debug_blur_bench(SiftContext* c, int32_t scale, int32_t mode, int32_t i
     a.inFrameStride = a.outFrameStride = kGaussians * q.plane;
     a.dogFrameStride = kDogs * q.plane;
     a.frames = c->last->frames;
+    a.tmaSet = &c->octTma[0];
+    a.tmaZ0 = scale;
+    a.tmaZStride = kGaussians;
     const bool dual = (mode & 8) != 0;   // tuning: the same launches split over two streams
     a.debugMode = mode & 7;
     cudaStream_t s2 = c->octStream[1];   // any second stream
@@ -1297,7 +1331,7 @@ int sift_debug_blur_bench(SiftContext* c, int32_t scale, int32_t mode, int32_t i
     float ms = 0;
     CTX_TRY(c, cudaEventElapsedTime(&ms, c->evBlur0[0], c->evBlur0[1]));
     *outMs = ms / iters;
-    c->executed = false;   // planes were overwritten in debug modes: force a fresh execute
+    if (a.debugMode) c->executed = false;   // planes were overwritten in debug modes: force a fresh execute
     return SIFT_OK;
 }
 

@@ -1,7 +1,9 @@
 // common.cuh — shared declarations of the sm_100a SIFT engine (libsiftcuda.so).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/siftcuda.h"
 
@@ -94,20 +96,36 @@ __device__ __forceinline__ void pdlPrologue() {
     asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     asm volatile("griddepcontrol.wait;\n" ::: "memory");
 }
+// Every launch that needs an attribute goes through here. `priority` (kNoPriority = leave the
+// stream's) is set as a per-launch attribute as well as through the stream it is launched on: a
+// stream's priority is not carried into the kernel nodes of a captured CUDA graph, a launch
+// attribute is.
+constexpr int kNoPriority = 1 << 30;
 template <class... KArgs, class... Args>
-inline cudaError_t pdlLaunch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
-                             bool pdl, Args... args) {
+inline cudaError_t launchKernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                bool pdl, int priority, Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
+    static const bool pdlEnabled = !(getenv("SIFTCUDA_PDL") && atoi(getenv("SIFTCUDA_PDL")) == 0);   // tuning switch
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
-    cfg.attrs = attr;
+    attr[0].val.programmaticStreamSerializationAllowed = (pdl && pdlEnabled) ? 1 : 0;
     cfg.numAttrs = 1;
+    if (priority != kNoPriority) {
+        attr[1].id = cudaLaunchAttributePriority;
+        attr[1].val.priority = priority;
+        cfg.numAttrs = 2;
+    }
+    cfg.attrs = attr;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+template <class... KArgs, class... Args>
+inline cudaError_t pdlLaunch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                             bool pdl, Args... args) {
+    return launchKernel(kernel, grid, block, smem, st, pdl, kNoPriority, args...);
 }
 #endif
 
@@ -125,6 +143,15 @@ cudaError_t launchGrayUpsample(const uint8_t* pixels, int bytesPerPixel, int pit
                                int64_t frameStrideBytes, float* gray, int W, int H, float* scaled,
                                int w2, int h2, int pitch2, size_t scaledFrameStride, int frames,
                                cudaStream_t st);
+// TMA tensor maps of one stack of planes for every blur configuration: [tap count 11/15/17/21/27]
+// [tile 64 / 32][full row group / last row group]. Host memory; the two maps a launch needs
+// travel as __grid_constant__ kernel parameters.
+struct BlurTmaSet {
+    CUtensorMap map[5][2][2];
+    int valid;
+};
+cudaError_t makeBlurTmaSet(BlurTmaSet* set, const float* base, int pitch, int h, int nz, size_t planeFloats);
+
 // out = blur(in); optional dog = out - in; optional decimated copy of out (every other pixel)
 struct BlurArgs {
     const float* in;
@@ -140,13 +167,19 @@ struct BlurArgs {
     int debugMode;   // 0 normal; 1 skip the X/Y FMA loops; 2 skip the stores; 3 both (tuning only)
     int pdl;         // 1: programmatic dependent launch behind the previous kernel of the stream
                      //    (small planes: the launch latency of scale s + 1 overlaps scale s)
+    // TMA tile loads: `in` = slice tmaZ0 (+ frame * tmaZStride) of the stack tmaSet describes
+    const BlurTmaSet* tmaSet;   // host pointer, null = cp.async loads only
+    int tmaZ0, tmaZStride;
+    int tma;                    // set by the launcher
+    int priority;               // launch priority (kNoPriority / 0 = the stream's)
 };
 cudaError_t launchBlur(const BlurArgs& a, const Taps& taps, int ntaps, cudaStream_t st);
-cudaError_t launchGradient(const OctaveDev& o, int frames, cudaStream_t st, int yBegin = 0, int yEnd = 0);
+cudaError_t launchGradient(const OctaveDev& o, int frames, cudaStream_t st, int yBegin = 0, int yEnd = 0,
+                           int priority = kNoPriority);
 
 // detect.cu
 cudaError_t launchExtremaMask(const EngineParams& P, int octave, uint32_t* mask, int frames,
-                              cudaStream_t st, int yBegin = 0, int yEnd = 0);
+                              cudaStream_t st, int yBegin = 0, int yEnd = 0, int priority = kNoPriority);
 // mask blocks [blockBegin, blockBegin + nBlocks) → ordered candidates; segStart[nSegs + 1] receives
 // the per-(frame, octave) list offsets
 cudaError_t launchCandidateCompaction(const EngineParams& P, const uint32_t* mask,

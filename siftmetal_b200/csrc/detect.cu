@@ -197,7 +197,7 @@ extremaMaskSmallKernel(const OctaveDev o, float softThreshold, uint32_t* __restr
 // Mask rows [yBegin, yEnd) ∩ [1, h - 1) of one octave (0, 0 = all rows): a row band of octave 0
 // gets its mask as soon as that band's blur chain is done.
 cudaError_t launchExtremaMask(const EngineParams& P, int octave, uint32_t* mask, int frames,
-                              cudaStream_t st, int yBegin, int yEnd) {
+                              cudaStream_t st, int yBegin, int yEnd, int priority) {
     const OctaveDev& o = P.oct[octave];
     if (o.w < 3 || o.h < 3) return cudaSuccess;
     const bool all = yEnd <= 0;
@@ -205,8 +205,8 @@ cudaError_t launchExtremaMask(const EngineParams& P, int octave, uint32_t* mask,
     if (yB <= yA) return cudaSuccess;
     if (all && (long)o.w * o.h * frames <= 96 * 1024) {
         dim3 grid((o.maskRowWords * 32 + 255) / 256, o.h, frames);
-        extremaMaskSmallKernel<<<grid, 256, 0, st>>>(o, P.dogThreshold * 0.8f, mask, P.blocksPerFrame);
-        return cudaGetLastError();
+        return launchKernel(extremaMaskSmallKernel, grid, dim3(256), 0, st, false, priority, o, P.dogThreshold * 0.8f,
+                            mask, P.blocksPerFrame);
     }
     // rows per warp (multiple of 3): long strips amortise the 2-row halo on large planes; small
     // planes get short strips so that the serial row loop does not bound the launch
@@ -215,8 +215,8 @@ cudaError_t launchExtremaMask(const EngineParams& P, int octave, uint32_t* mask,
     int rows = kExtRows;
     while (rows > 6 && (long)gx * ((nRows + rows - 1) / rows) * frames < 592) rows -= 6;
     dim3 grid(gx, (nRows + rows - 1) / rows, frames);
-    extremaMaskKernel<<<grid, kExtWarps * 32, 0, st>>>(o, P.dogThreshold * 0.8f, mask, P.blocksPerFrame, rows, yA, yB);
-    return cudaGetLastError();
+    return launchKernel(extremaMaskKernel, grid, dim3(kExtWarps * 32), 0, st, false, priority, o, P.dogThreshold * 0.8f,
+                        mask, P.blocksPerFrame, rows, yA, yB);
 }
 
 // ------------------------------------------------------------------------------------------

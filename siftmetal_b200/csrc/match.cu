@@ -25,13 +25,11 @@
 // Work item = (block of 128 source rows, contiguous segment of target tiles); segments of one
 // row block are merged in target order by matchFinishKernel with the same sequential rule, so
 // the split does not change the result.
-#include <cuda.h>
-#include <cudaTypedefs.h>
-
 #include <algorithm>
 #include <atomic>
 
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace sift {
 
@@ -49,34 +47,6 @@ constexpr uint32_t kABytes = kM * kK;
 constexpr uint32_t kBBytes = kN * kK;
 constexpr size_t kSmemBytes = 1024 /* alignment slack */ + kABytes + kStages * kBBytes + 256 /* barriers */;
 
-__device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbarInit(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbarExpectTx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbarArrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smemAddr(bar)) : "memory");
-}
-__device__ __forceinline__ void mbarWait(uint64_t* bar, uint32_t parity) {
-    const uint32_t a = smemAddr(bar);
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t"
-        "}" ::"r"(a), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tmaLoad2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smemAddr(dst)), "l"((uint64_t)map), "r"(smemAddr(bar)), "r"(c0), "r"(c1) : "memory");
-}
 __device__ __forceinline__ void umma(uint32_t tmemD, uint64_t descA, uint64_t descB, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t"
@@ -154,7 +124,7 @@ matchKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         mbarInit(fullA, 1);
         mbarInit(emptyA, 1);
         for (int s = 0; s < kAccStages; s++) { mbarInit(&tmemFull[s], 1); mbarInit(&tmemEmpty[s], 4); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbarInitFence();
     } else if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smemAddr(tmemBaseSlot)),
                      "r"((uint32_t)(kAccStages * kN)) : "memory");
@@ -318,19 +288,6 @@ matchFinishKernel(const MatchParams p, const int* __restrict__ normA, float absT
         if (dBest < absThr && dBest < __fmul_rn(dSecond, relThr)) r.target = index;
     }
     rows[i] = r;
-}
-
-PFN_cuTensorMapEncodeTiled_v12000 tensorMapEncoder() {
-    static std::atomic<void*> cached{nullptr};
-    void* fn = cached.load(std::memory_order_acquire);
-    if (!fn) {
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
-            q != cudaDriverEntryPointSuccess)
-            return nullptr;
-        cached.store(fn, std::memory_order_release);
-    }
-    return (PFN_cuTensorMapEncodeTiled_v12000)fn;
 }
 
 // [rows][128] uint8, box = `boxRows` whole rows, 128-byte swizzle (one row = one swizzle span).

@@ -13,6 +13,7 @@
 
 #include "common.cuh"
 #include "dev_math.cuh"
+#include "tma.cuh"
 
 namespace sift {
 
@@ -229,7 +230,11 @@ struct BlurCfg {
     static constexpr int SMEM_FLOATS = IN_H * IP + IN_H * TP;
     static constexpr int XSEG = 8;                   // outputs per thread in the X pass
     static constexpr int NG = 3;                     // row groups of the pipelined tile load
-    static constexpr int GH = (IN_H + NG - 1) / NG;  // rows per group
+    // rows per group: a multiple of 8, so that every group starts on a 128-byte boundary of the
+    // tile (row pitch = 16 bytes x odd) — the alignment a TMA destination needs
+    static constexpr int GH = (IN_H + 8 * NG - 1) / (8 * NG) * 8;
+    static constexpr int GH_LAST = IN_H - (NG - 1) * GH;   // rows of the last group
+    static constexpr int SMEM_BYTES = SMEM_FLOATS * 4 + NG * 8;   // + one mbarrier per group
 };
 
 template <int N>
@@ -239,16 +244,23 @@ __device__ __forceinline__ void cpAsyncWaitGroup() {
 
 template <int NTAPS, int TX, int TY, int NT, bool DOG, bool HALF>
 __global__ void __launch_bounds__(NT)
-blurKernel(const BlurArgs a, const __grid_constant__ Taps taps) {
+blurKernel(const BlurArgs a, const __grid_constant__ Taps taps, const __grid_constant__ CUtensorMap mapFull,
+           const __grid_constant__ CUtensorMap mapLast) {
     using C = BlurCfg<NTAPS, TX, TY, NT>;
     constexpr int R = C::R, RP = C::RP, IN_W = C::IN_W, IN_H = C::IN_H, IP = C::IP, TP = C::TP;
     constexpr int NG = C::NG, GH = C::GH;
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     float* const sIn = smem;
     float* const sTmp = smem + IN_H * IP;
+    uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + C::SMEM_FLOATS);   // [NG], TMA path only
 
-    pdlPrologue();   // small planes are launched behind their predecessor (a.pdl)
     const int tid = threadIdx.x;
+    if (a.tma && tid == 0) {
+#pragma unroll
+        for (int g = 0; g < NG; g++) mbarInit(&bars[g], 1);
+        mbarInitFence();
+    }
+    pdlPrologue();   // small planes are launched behind their predecessor (a.pdl)
     const int w = a.w, h = a.h, pitch = a.pitch;
     // output rows [yB, yE): the whole plane, or one row band of it (bands of one plane run as
     // independent launches on separate streams; the mirror boundary still refers to the plane)
@@ -265,6 +277,24 @@ blurKernel(const BlurArgs a, const __grid_constant__ Taps taps) {
     // ---- asynchronous load of the input tile with halo, NG row groups ----------------------
     const bool interior = (x0 - RP >= 0) && (x0 + TX + RP <= w) && (y0 - R >= 0) &&
                           (y0 + TY + R <= h);
+    // Interior tiles (the bulk of a large plane): the tile + halo is three TMA box copies
+    // (cp.async.bulk.tensor.3d: x, y, slice), issued by one thread, each completing on the mbarrier
+    // of its row group — no per-thread address arithmetic, no LDGSTS issue slots. The box is IP
+    // floats wide, i.e. it writes the padded row pitch directly (the 4 surplus columns are never
+    // read). Edge tiles need the mirror boundary per element and keep the cp.async path.
+    const bool useTma = a.tma && interior;   // CTA-uniform
+    if (a.tma) __syncthreads();              // barrier initialisation visible before anyone waits
+    if (useTma) {
+        if (tid == 0) {
+            const int z = a.tmaZ0 + f * a.tmaZStride;
+#pragma unroll
+            for (int g = 0; g < NG; g++) {
+                const int rows = g + 1 < NG ? GH : C::GH_LAST;
+                mbarExpectTx(&bars[g], (uint32_t)(rows * IP * 4));
+                tmaLoad3d(g + 1 < NG ? &mapFull : &mapLast, &bars[g], sIn + g * GH * IP, x0 - RP, y0 - R + g * GH, z);
+            }
+        }
+    } else
 #pragma unroll
     for (int g = 0; g < NG; g++) {
         const int rBeg = g * GH, rEnd = min(rBeg + GH, IN_H);
@@ -308,6 +338,10 @@ blurKernel(const BlurArgs a, const __grid_constant__ Taps taps) {
     }
 
     if (a.debugMode & 4) {   // tuning: tile load only
+        if (useTma) {
+#pragma unroll
+            for (int g = 0; g < NG; g++) mbarWait(&bars[g], 0);
+        }
         cpAsyncWaitGroup<0>();
         __syncthreads();
         if (sIn[tid] == 1.2345e30f) a.out[0] = 1.0f;
@@ -316,10 +350,14 @@ blurKernel(const BlurArgs a, const __grid_constant__ Taps taps) {
     // ---- X pass, group by group: one row, 8 consecutive outputs per task --------------------
 #pragma unroll
     for (int g = 0; g < NG; g++) {
-        if (g == 0) cpAsyncWaitGroup<NG - 1>();
-        else if (g == 1) cpAsyncWaitGroup<NG - 2>();
-        else cpAsyncWaitGroup<0>();
-        __syncthreads();
+        if (useTma) {
+            mbarWait(&bars[g], 0);   // the group's bytes have landed (and are visible to the waiter)
+        } else {
+            if (g == 0) cpAsyncWaitGroup<NG - 1>();
+            else if (g == 1) cpAsyncWaitGroup<NG - 2>();
+            else cpAsyncWaitGroup<0>();
+            __syncthreads();
+        }
         const int rBeg = g * GH, rows = min(rBeg + GH, IN_H) - rBeg;
         constexpr int SEGS = TX / C::XSEG;
         constexpr int NV = (C::XSEG + 2 * RP) / 4;
@@ -435,12 +473,15 @@ blurKernel(const BlurArgs a, const __grid_constant__ Taps taps) {
     }
 }
 
+constexpr int tapIndex(int ntaps) { return ntaps == 11 ? 0 : ntaps == 15 ? 1 : ntaps == 17 ? 2 : ntaps == 21 ? 3 : 4; }
+
 template <int NTAPS, int TX, int TY, int NT, bool DOG, bool HALF>
-static cudaError_t launchBlurCfg(const BlurArgs& a, const Taps& taps, cudaStream_t st) {
+static cudaError_t launchBlurCfg(const BlurArgs& a0, const Taps& taps, cudaStream_t st) {
     using C = BlurCfg<NTAPS, TX, TY, NT>;
     static_assert(C::IN_W % 4 == 0 && C::IP % 8 == 4 && C::TP % 8 == 4, "bank layout");
     static_assert(TX % C::XSEG == 0 && C::RY >= 1 && TY % C::RY == 0 && C::NG == 3, "tile shape");
-    const int smemBytes = C::SMEM_FLOATS * (int)sizeof(float);
+    static_assert(C::GH % 8 == 0 && C::GH_LAST >= 1 && C::GH_LAST <= C::GH && C::SMEM_FLOATS % 2 == 0, "row groups");
+    const int smemBytes = C::SMEM_BYTES;
     // per-device bit (the attribute is per device); contexts on separate host threads may race
     // here, so the word is atomic — setting the attribute twice is harmless, losing a bit is not
     static std::atomic<unsigned long long> configured{0};
@@ -451,14 +492,53 @@ static cudaError_t launchBlurCfg(const BlurArgs& a, const Taps& taps, cudaStream
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes));
         configured.fetch_or(1ull << (dev & 63), std::memory_order_release);
     }
+    BlurArgs a = a0;
+    static const bool tmaEnabled = !(getenv("SIFTCUDA_BLUR_TMA") && atoi(getenv("SIFTCUDA_BLUR_TMA")) == 0);   // tuning switch
+    const BlurTmaSet* set = a.tmaSet;
+    // planes narrower or lower than one tile + halo have no interior tile at all
+    a.tma = (tmaEnabled && set && set->valid && a.w >= TX + 2 * C::RP && a.h >= TY + 2 * C::R) ? 1 : 0;
+    static const CUtensorMap noMap{};
+    const CUtensorMap& mFull = a.tma ? set->map[tapIndex(NTAPS)][TX == 64 ? 0 : 1][0] : noMap;
+    const CUtensorMap& mLast = a.tma ? set->map[tapIndex(NTAPS)][TX == 64 ? 0 : 1][1] : noMap;
     const int rows = (a.yEnd > 0 ? a.yEnd : a.h) - a.yBegin;
     const long nTiles = (long)((a.w + TX - 1) / TX) * ((rows + TY - 1) / TY) * a.frames;
     if (nTiles > 2147483647L || rows < 1) return cudaErrorInvalidValue;
-    if (a.pdl)
-        return pdlLaunch(blurKernel<NTAPS, TX, TY, NT, DOG, HALF>, dim3((unsigned)nTiles), dim3(NT), (size_t)smemBytes,
-                         st, true, a, taps);
-    blurKernel<NTAPS, TX, TY, NT, DOG, HALF><<<(unsigned)nTiles, NT, smemBytes, st>>>(a, taps);
-    return cudaGetLastError();
+    return launchKernel(blurKernel<NTAPS, TX, TY, NT, DOG, HALF>, dim3((unsigned)nTiles), dim3(NT), (size_t)smemBytes,
+                        st, a.pdl != 0, a.priority ? a.priority : kNoPriority, a, taps, mFull, mLast);
+}
+
+// Tensor maps of one stack of planes [nz][h][pitch] for every blur configuration: box = (IP
+// columns, GH or GH_LAST rows, 1 slice). Columns beyond the plane's pitch / rows beyond h are
+// never requested by interior tiles (out-of-bounds elements would be zero-filled).
+template <int NTAPS, int TX, int TY, int NT>
+static cudaError_t makeBlurMaps(BlurTmaSet* set, const float* base, int pitch, int h, int nz, size_t planeFloats) {
+    using C = BlurCfg<NTAPS, TX, TY, NT>;
+    auto enc = tensorMapEncoder();
+    if (!enc) return cudaErrorNotSupported;
+    const cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)h, (cuuint64_t)nz};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch * 4, (cuuint64_t)planeFloats * 4};
+    const cuuint32_t elem[3] = {1, 1, 1};
+    for (int kind = 0; kind < 2; kind++) {
+        const cuuint32_t box[3] = {(cuuint32_t)C::IP, (cuuint32_t)(kind == 0 ? C::GH : C::GH_LAST), 1};
+        const CUresult r = enc(&set->map[tapIndex(NTAPS)][TX == 64 ? 0 : 1][kind], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                               const_cast<float*>(base), dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    }
+    return cudaSuccess;
+}
+
+cudaError_t makeBlurTmaSet(BlurTmaSet* set, const float* base, int pitch, int h, int nz, size_t planeFloats) {
+    set->valid = 0;
+    if (pitch < 32 || h < 1 || nz < 1) return cudaSuccess;
+#define SIFT_MAPS(T)                                                                     \
+    SIFT_CUDA_TRY((makeBlurMaps<T, 64, 64, 256>(set, base, pitch, h, nz, planeFloats))); \
+    SIFT_CUDA_TRY((makeBlurMaps<T, 32, 32, 128>(set, base, pitch, h, nz, planeFloats)));
+    SIFT_MAPS(11) SIFT_MAPS(15) SIFT_MAPS(17) SIFT_MAPS(21) SIFT_MAPS(27)
+#undef SIFT_MAPS
+    set->valid = 1;
+    return cudaSuccess;
 }
 
 template <int NTAPS, int TX, int TY, int NT>
@@ -546,14 +626,13 @@ __global__ void __launch_bounds__(256) gradientKernel(const OctaveDev o, int yBe
     }
 }
 
-cudaError_t launchGradient(const OctaveDev& o, int frames, cudaStream_t st, int yBegin, int yEnd) {
+cudaError_t launchGradient(const OctaveDev& o, int frames, cudaStream_t st, int yBegin, int yEnd, int priority) {
     if (yEnd <= 0) { yBegin = 0; yEnd = o.h; }
     yBegin &= ~1;
     yEnd = std::min(yEnd, o.h);
     if (yEnd <= yBegin) return cudaSuccess;
     dim3 grid((o.w + 1023) / 1024, (yEnd - yBegin + 1) / 2, kScales * frames);
-    gradientKernel<<<grid, 256, 0, st>>>(o, yBegin, yEnd);
-    return cudaGetLastError();
+    return launchKernel(gradientKernel, grid, dim3(256), 0, st, false, priority, o, yBegin, yEnd);
 }
 
 }  // namespace sift

@@ -86,7 +86,11 @@ def test_graph_replay_equals_launch_by_launch():
     w, h = 960, 540
     imgs = [pink_noise_bgra(w, h, i) for i in range(2)]
     eng = Engine(w, h)
+    base = [eng.detect_and_describe([imgs[i]]) for i in range(2)]
+    assert not eng.timings()["graph_replay"]              # opt-in
+    eng.set_graph_replay(True)
     r = [eng.detect_and_describe([imgs[i % 2]]) for i in range(6)]
+    assert _same(r[0], base[0]) and _same(r[1], base[1])
     t = eng.timings()
     assert t["graph_replay"] and not t["stage_timing_enabled"] and t["total_ms"] > 0
     assert t["kernel_launches"] > 40

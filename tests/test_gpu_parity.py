@@ -402,11 +402,12 @@ def test_config2_vga256_batch_against_oracle():
     eng.close()
 
 
-@pytest.mark.parametrize("switch", ["SIFTCUDA_GRAPH=0", "SIFTCUDA_BANDS=1", "SIFTCUDA_BANDS=3", "SIFTCUDA_PDL_TILES=0"])
+@pytest.mark.parametrize("switch", ["SIFTCUDA_GRAPH=1", "SIFTCUDA_BANDS=1", "SIFTCUDA_BANDS=3", "SIFTCUDA_PDL=0",
+                                    "SIFTCUDA_BLUR_TMA=0"])
 def test_tuning_switches_do_not_change_results(switch):
-    """Alternative schedules (launch by launch instead of graph replay; no row bands; three row
-    bands; no programmatic dependent launch on the small-plane blur chains) must give the same
-    result arrays as the default, call after call (first call eager, second captured, third replayed)."""
+    """Alternative schedules (CUDA-graph replay instead of stream launches; no row bands; three row
+    bands; no programmatic dependent launch; cp.async instead of TMA tile loads) must give the same
+    result arrays as the default, call after call (graph: first call eager, second captured, third replayed)."""
     import os
     import subprocess
     import sys
@@ -431,8 +432,8 @@ def test_tuning_switches_do_not_change_results(switch):
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
         outs.append(np.load(path))
     a, b = outs
-    assert int(a["g"]) == 1                                   # the default replays a CUDA graph
-    assert int(b["g"]) == (0 if "GRAPH=0" in switch else 1)
+    assert int(a["g"]) == 0                                   # the default launches on streams
+    assert int(b["g"]) == (1 if "GRAPH=1" in switch else 0)
     assert int(a["c"]) == int(b["c"])
     for key in ("k", "d", "kc", "dc"):
         assert np.array_equal(a[key], b[key]), key
