@@ -538,7 +538,10 @@ cudaError_t launchDescribe(const EngineParams& P, const SiftKeypoint* kps, const
     if (afterOrientation) SIFT_CUDA_TRY(cudaEventRecord(afterOrientation, st));
 
     const int smemBytes = kDescWarps * kDescBins * kDescCopies * (int)sizeof(float);
-    const int ctasPerSm = (228 * 1024) / (smemBytes + 1024);
+    // two CTAs (14 warps) per SM use all of its shared memory; SIFTCUDA_DESC_CTAS=1 leaves half of it
+    // to kernels of another context running beside this one (two contexts per device, frames alternating)
+    static const int ctasEnv = getenv("SIFTCUDA_DESC_CTAS") ? atoi(getenv("SIFTCUDA_DESC_CTAS")) : 0;
+    const int ctasPerSm = ctasEnv > 0 ? std::min(ctasEnv, 2) : (228 * 1024) / (smemBytes + 1024);
     auto kernel = descriptorKernel<3>;
     static std::atomic<unsigned long long> configured{0};   // per-device bit, as in launchBlurCfg
     int dev = 0;

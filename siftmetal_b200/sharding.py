@@ -67,6 +67,14 @@ class ShmGather:
         self.peers = []
         if rank == 0:
             self.peers = [self.own] + [shared_memory.SharedMemory(name=self.name(r)) for r in range(1, world)]
+            # attaching registers the segment with this process's resource tracker (Python < 3.13),
+            # which would unlink it a second time at exit: the owner rank unlinks its own segment
+            try:
+                from multiprocessing import resource_tracker
+                for p in self.peers[1:]:
+                    resource_tracker.unregister(p._name, "shared_memory")
+            except Exception:
+                pass
         self.step = 0
         self._reset_cursor()
         self.stats = {"steps": 0, "frames": 0, "keypoints": 0, "descriptors": 0}
