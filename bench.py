@@ -332,12 +332,28 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e: host buffers through the public pipelined calls, results gathered on rank 0 ----------
-    gather = ShmGather(rank, world, eng, n_local) if (distributed and sharded) else None
+    graph_mode = os.environ.get("SIFTCUDA_GRAPH", "0") not in ("", "0")
+    gather = None
+    if distributed and sharded:
+        # a recorded graph carries the result pointers: no region rotation under graph replay
+        gather = ShmGather(rank, world, eng, max_frames_per_call=chunk, calls_per_step=len(chunks),
+                           regions=2 if graph_mode else 4)
     e2e_counts = [0, 0]
 
-    def publish(result_counts):
-        e2e_counts[0] += result_counts[0]
-        e2e_counts[1] += result_counts[1]
+    def finish_call(pci):
+        r = eng.wait(copy=False)
+        e2e_counts[0] += len(r.keypoint_columns)
+        e2e_counts[1] += len(r.descriptor_columns)
+        if gather is not None:
+            gather.publish(r, chunks[pci][0])
+            gather.call_done()                             # barrier: this call of every rank is visible on rank 0
+
+    def pad_calls(pci):
+        # ranks whose shard needs fewer calls per step still meet the others at every barrier
+        if gather is not None and pci == len(chunks) - 1:
+            for _ in range(gather.calls_per_step - len(chunks)):
+                gather.publish_empty()
+                gather.call_done()
 
     def step_e2e_pipelined(steps):
         """`steps` steps with two calls in flight across chunk and step boundaries."""
@@ -346,23 +362,17 @@ def main():
         for st, ci in seq:
             if len(inflight) == 2:
                 pst, pci = inflight.pop(0)
-                r = eng.wait(copy=False)
-                if gather is not None:
-                    gather.publish(r, chunks[pci][0])
-                publish((len(r.keypoint_columns), len(r.descriptor_columns)))
-                if gather is not None and pci == len(chunks) - 1:
-                    gather.step_done()                     # barrier: the step's shards are all visible
+                finish_call(pci)
+                pad_calls(pci)
             s, n = chunks[ci]
+            if gather is not None:
+                gather.before_submit()                     # the slot's columns go straight into shared memory
             eng.submit_ptrs(ptr_arrays[ci], n, w * bpp)
             inflight.append((st, ci))
         while inflight:
             pst, pci = inflight.pop(0)
-            r = eng.wait(copy=False)
-            if gather is not None:
-                gather.publish(r, chunks[pci][0])
-            publish((len(r.keypoint_columns), len(r.descriptor_columns)))
-            if gather is not None and pci == len(chunks) - 1:
-                gather.step_done()
+            finish_call(pci)
+            pad_calls(pci)
 
     def step_e2e_sync():
         nk = nd = 0
@@ -375,7 +385,8 @@ def main():
     e2e_steps = 2 if args.quick else max(5, args.steps // 2)
     sync_steps = 1 if args.quick else max(3, min(e2e_steps, 50))
     step_e2e_pipelined(2)                                    # warm-up: slot 1 allocation, its graph
-    step_e2e_sync()
+    if gather is None:
+        step_e2e_sync()
     barrier()
     e2e_counts[:] = [0, 0]
     t0 = time.perf_counter()
@@ -383,12 +394,22 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
     nk_total, nd_total = e2e_counts
+    gathered = gather.summary() if gather is not None else None
+    if gather is not None:
+        # give the slots their own pinned blocks back for the synchronous leg
+        gather.close()
+        gather = None
+        eng.close()
+        eng = Engine(w, h, device=local, max_batch=chunk,
+                     input_format=_abi.INPUT_GRAY8 if gray else _abi.INPUT_BGRA8)
+        step_device()
+        step_e2e_sync()
+        barrier()
     t0 = time.perf_counter()
     for _ in range(sync_steps):
         step_e2e_sync()
     barrier()
     sync_s = time.perf_counter() - t0
-    gathered = gather.summary() if gather is not None else None
 
     # ---- diagnostic region: the same steps launch by launch with per-stage events --------------------
     diag = {"stage": np.zeros(6), "blur": np.zeros(5), "graph": 0}
@@ -478,8 +499,9 @@ def main():
                                           + len(chunks) * (24 + 3 * 4 * (7 * chunk + 1)),
                     "steps": e2e_steps,
                     "timing": "wall clock around sift_submit / sift_wait with two calls in flight, pinned host frames, "
-                              "result columns in pinned host memory" + (", shards gathered on rank 0 through shared memory"
-                                                                        if gather is not None else ""),
+                              "result columns in pinned host memory" + (", every call's shards visible on rank 0 in frame order "
+                                                                        "(kernels store into shared-memory segments)"
+                                                                        if gathered is not None else ""),
                     "ms_per_step": 1000.0 * e2e_s_max / e2e_steps,
                     "sync_call": {"value": frames_per_step_job * sync_steps / sync_s_max, "steps": sync_steps,
                                   "ms_per_step": 1000.0 * sync_s_max / sync_steps,

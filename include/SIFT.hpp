@@ -11,6 +11,8 @@
 //   SIFT(device, configuration)                               SIFT.swift:112-143
 //   getKeypoints(bgra8, bytesPerRow)  -> [[SIFTKeypoint]]     SIFT.swift:147-152 (7 octave lists)
 //   getDescriptors(keypointOctaves)   -> [[SIFTDescriptor]]   SIFT.swift:207-238
+//   match(source, target, abs, rel)   -> [SiftMatch]          SIFTDescriptor.swift:298-361
+// plus the batch / pipelined calls and lazy views over the column wire format (siftcuda.h).
 //
 // Where the reference aborts (try!, precondition, fatalError), this mirror throws
 // siftcuda::Error carrying the C status; there is no CPU fallback anywhere.
@@ -64,8 +66,8 @@ struct IntVector {
     }
 };
 
-// SIFTDescriptor.swift:12-35 (stored properties; the index keys of :43-89 serve the matcher,
-// which is outside the hot path)
+// SIFTDescriptor.swift:12-35 (stored properties; the index keys of :43-89 are a permutation of
+// the features for the trie matcher and do not change a distance)
 struct SIFTDescriptor {
     SIFTKeypoint keypoint;
     float theta;
@@ -148,7 +150,113 @@ public:
 
     SiftContext* context() { return ctx_; }
 
+    // ---- beyond the reference's two calls: batches, the pipelined form, matching --------------
+    // Lazy views over the column wire format (SiftBatchResult): nothing is converted until an
+    // element is indexed — the reference builds one object per keypoint / descriptor up front
+    // (SIFTOctave.swift:257-286, :470-489; SIFTDescriptor.swift:36-89). Views borrow the
+    // context-owned pinned columns: valid until the slot is reused (see siftcuda.h).
+    class KeypointView {
+    public:
+        KeypointView() = default;
+        KeypointView(SiftContext* ctx, const SiftBatchResult& r, int64_t first, int64_t count)
+            : ctx_(ctx), r_(r), first_(first), count_(count) {}
+        int64_t size() const { return count_; }
+        SIFTKeypoint operator[](int64_t i) const {
+            SiftKeypoint p;
+            check(sift_materialize_keypoints(ctx_, &r_, first_ + i, 1, &p), nullptr);
+            return fromPod(p);
+        }
+        // raw columns of this view
+        const float* absoluteX() const { return r_.keypoints.absolute_x + first_; }
+        const float* absoluteY() const { return r_.keypoints.absolute_y + first_; }
+        const float* sigma() const { return r_.keypoints.sigma + first_; }
+    private:
+        SiftContext* ctx_ = nullptr;
+        SiftBatchResult r_{};
+        int64_t first_ = 0, count_ = 0;
+    };
+
+    class DescriptorView {
+    public:
+        DescriptorView() = default;
+        DescriptorView(const SiftBatchResult& r, int64_t first, int64_t count, KeypointView keypoints)
+            : r_(r), first_(first), count_(count), keypoints_(keypoints) {}
+        int64_t size() const { return count_; }
+        SIFTDescriptor operator[](int64_t i) const {
+            SiftDescriptor d;
+            check(sift_materialize_descriptors(&r_, first_ + i, 1, &d), nullptr);
+            SIFTDescriptor out;
+            out.keypoint = keypoints_[d.keypoint];
+            out.theta = d.theta;
+            out.features.components.assign(d.features, d.features + SIFT_DESCRIPTOR_FEATURE_COUNT);
+            return out;
+        }
+        // dense [size()][128] uint8 feature matrix: the operand layout of match()
+        const uint8_t* features() const { return r_.descriptors.features + first_ * SIFT_DESCRIPTOR_FEATURE_COUNT; }
+        const float* theta() const { return r_.descriptors.theta + first_; }
+    private:
+        SiftBatchResult r_{};
+        int64_t first_ = 0, count_ = 0;
+        KeypointView keypoints_;
+    };
+
+    struct FrameResult {
+        KeypointView keypoints;
+        DescriptorView descriptors;
+        std::array<int32_t, SIFT_NUM_OCTAVES> keypointCounts{}, descriptorCounts{};
+    };
+
+    // getKeypoints + getDescriptors for a batch of frames in one call (no host round trip).
+    std::vector<FrameResult> detectAndDescribe(const std::vector<const void*>& frames, int bytesPerRow) {
+        SiftBatchResult r;
+        check(sift_detect_and_describe_batch(ctx_, frames.data(), (int32_t)frames.size(), bytesPerRow, &r), ctx_);
+        return split(r);
+    }
+    // Pipelined form: up to two calls in flight; wait() returns them in submission order.
+    void submit(const std::vector<const void*>& frames, int bytesPerRow) {
+        check(sift_submit(ctx_, frames.data(), (int32_t)frames.size(), bytesPerRow), ctx_);
+    }
+    std::vector<FrameResult> wait() {
+        SiftBatchResult r;
+        check(sift_wait(ctx_, &r), ctx_);
+        return split(r);
+    }
+
+    // SIFTDescriptor.match(source:target:absoluteThreshold:relativeThreshold:)
+    // (SIFTDescriptor.swift:298-361) on feature matrices; correspondences in source order.
+    std::vector<SiftMatch> match(const uint8_t* source, int64_t nSource, const uint8_t* target, int64_t nTarget,
+                                 float absoluteThreshold = 300.0f, float relativeThreshold = 0.6f) {
+        const SiftMatch* m = nullptr;
+        int64_t n = 0;
+        check(sift_match(ctx_, source, nSource, target, nTarget, absoluteThreshold, relativeThreshold, &m, &n), ctx_);
+        return std::vector<SiftMatch>(m, m + n);
+    }
+    std::vector<SiftMatch> match(const DescriptorView& source, const DescriptorView& target,
+                                 float absoluteThreshold = 300.0f, float relativeThreshold = 0.6f) {
+        return match(source.features(), source.size(), target.features(), target.size(), absoluteThreshold,
+                     relativeThreshold);
+    }
+
 private:
+    std::vector<FrameResult> split(const SiftBatchResult& r) {
+        std::vector<FrameResult> out((size_t)r.n_frames);
+        int64_t k = 0, d = 0;
+        for (int f = 0; f < r.n_frames; f++) {
+            int64_t nk = 0, nd = 0;
+            for (int o = 0; o < SIFT_NUM_OCTAVES; o++) {
+                out[(size_t)f].keypointCounts[(size_t)o] = r.keypoint_counts[f * SIFT_NUM_OCTAVES + o];
+                out[(size_t)f].descriptorCounts[(size_t)o] = r.descriptor_counts[f * SIFT_NUM_OCTAVES + o];
+                nk += r.keypoint_counts[f * SIFT_NUM_OCTAVES + o];
+                nd += r.descriptor_counts[f * SIFT_NUM_OCTAVES + o];
+            }
+            out[(size_t)f].keypoints = KeypointView(ctx_, r, k, nk);
+            out[(size_t)f].descriptors = DescriptorView(r, d, nd, out[(size_t)f].keypoints);
+            k += nk;
+            d += nd;
+        }
+        return out;
+    }
+
     static SIFTKeypoint fromPod(const SiftKeypoint& p) {
         return SIFTKeypoint{p.octave, p.scale, p.subScale, {p.scaledX, p.scaledY},
                             {p.absoluteX, p.absoluteY}, {p.normalizedX, p.normalizedY}, p.sigma, p.value};

@@ -153,6 +153,8 @@ typedef struct SiftBatchResult {
                                         /* above the 0.8·C_DoG pre-threshold                      */
     int64_t total_keypoints;
     int64_t total_descriptors;
+    int32_t slot;                       /* in-flight slot (0 / 1) that holds these columns         */
+    int32_t reserved;
     SiftKeypointColumns keypoints;
     SiftDescriptorColumns descriptors;
 } SiftBatchResult;
@@ -258,6 +260,25 @@ int sift_detect_and_describe_batch(SiftContext* context, const void* const* imag
 int sift_submit(SiftContext* context, const void* const* images, int32_t n, int32_t pitch_bytes);
 int sift_wait(SiftContext* context, SiftBatchResult* out_result);
 int sift_pending(const SiftContext* context);   /* number of submitted, not yet waited calls   */
+int sift_next_slot(const SiftContext* context); /* slot the next sift_submit will use (0 / 1)  */
+
+/* Where a slot's result columns live. By default each slot owns a pinned block; a caller that
+ * gathers results across processes (one process per GPU) can bind a slot to its own
+ * memory instead — e.g. a POSIX shared-memory mapping another process reads — so that the kernels'
+ * stores ARE the gather: nothing is copied on the host. sift_register_host_memory pins a range
+ * once (cudaHostRegister; unregistered by sift_destroy; it must outlive the context);
+ * sift_bind_result_memory points a slot with no call in flight at a 256-byte aligned block of at
+ * least sift_result_layout().bytes inside a registered range — cheap, so a caller may rotate a
+ * slot through several blocks to keep older results alive. offset[] locates the ten columns in a
+ * block, in the order of SiftKeypointColumns then SiftDescriptorColumns. */
+typedef struct SiftResultLayout {
+    int64_t bytes;
+    int64_t capacity_keypoints, capacity_descriptors;   /* rows each column can hold (whole batch) */
+    int64_t offset[10];
+} SiftResultLayout;
+int sift_result_layout(const SiftContext* context, SiftResultLayout* out_layout);
+int sift_register_host_memory(SiftContext* context, void* base, int64_t bytes);
+int sift_bind_result_memory(SiftContext* context, int32_t slot, void* base, int64_t bytes);
 
 /* The same work split so that device-resident inputs can be timed apart from PCIe:
  *   upload (H2D into the context's input arena; the copy has completed when the call returns, so
@@ -303,6 +324,26 @@ int sift_match(SiftContext* context, const uint8_t* source_features, int64_t n_s
 int sift_match_frames(SiftContext* context, int32_t source_frame, int32_t target_frame,
                       float absolute_threshold, float relative_threshold,
                       const SiftMatch** out_matches, int64_t* out_count);
+
+/* SIFTDescriptor.matchGeometry(source:target:absoluteThreshold:relativeThreshold:)
+ * (SIFTDescriptor.swift:104-296; defaults 1.176 / 0.6): brute-force matches on the device, then —
+ * on the host, as in the reference — the geometric-consistency score of the first 80 of them
+ * (0 when fewer than 7 matched). `*_xy` are the absoluteCoordinate (x, y) pairs of the keypoint
+ * each descriptor row belongs to, interleaved. */
+int sift_match_geometry(SiftContext* context, const uint8_t* source_features, const float* source_xy,
+                        int64_t n_source, const uint8_t* target_features, const float* target_xy,
+                        int64_t n_target, float absolute_threshold, float relative_threshold,
+                        float* out_score);
+
+/* SIFTDescriptor.approximateMatch(source:target:absoluteThreshold:relativeThreshold:)
+ * (SIFTDescriptor.swift:362-417) over the reference's approximate-nearest-neighbour trie
+ * (Utilities/Trie.swift: 8 bins, keys = the 16 per-cell feature means, radius 10, k 2). A host
+ * stage in the reference and here (it visits ~21 leaves per query); kept as a flat sorted-key
+ * table instead of a pointer trie. Same leaf order, same visiting order, same results. */
+int sift_approximate_match(SiftContext* context, const uint8_t* source_features, int64_t n_source,
+                           const uint8_t* target_features, int64_t n_target,
+                           float absolute_threshold, float relative_threshold,
+                           const SiftMatch** out_matches, int64_t* out_count);
 
 /* ---- diagnostics -------------------------------------------------------------------------- */
 

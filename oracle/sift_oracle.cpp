@@ -922,4 +922,232 @@ int64_t oracle_match(const uint8_t* source, int64_t nSource, const uint8_t* targ
     return n;
 }
 
+// ---- SIFTDescriptor.matchGeometry / compareGeometry (SIFTDescriptor.swift:104-296) --------------
+// Geometric consistency score of the first 80 brute-force matches: for consecutive quadruples of
+// matches the vector m0->m1 is compared with m2->m3 in the source and in the target image (length
+// ratio and angle), the squared similarities are averaged after dropping outliers beyond two
+// standard deviations. Coordinates are keypoint.absoluteCoordinate (makeCoordinate, :145-159).
+// Oracle-defined: simd_length = sqrtf(x*x + y*y), simd_normalize = v / length, simd_dot =
+// a.x*b.x + a.y*b.y, each a single IEEE operation in this order (Apple's simd library leaves the
+// rounding of its fast paths unspecified).
+namespace {
+inline float geoClamp01(float v) { return v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v); }
+}  // namespace
+
+float oracle_compare_geometry(const SiftMatch* matches, int64_t nMatches, const float* sourceXY,
+                              const float* targetXY, int minimumSampleSize) {
+    const float minimumLength = 2;
+    float sum = 0;
+    int count = 0;
+    std::vector<float> scores;
+    auto coord = [](const float* xy, int32_t i, float& x, float& y) { x = xy[2 * i]; y = xy[2 * i + 1]; };
+    for (int64_t i = 0; i < nMatches - 3; i++) {   // stride(from: 0, to: matches.count - 3, by: 1)
+        const SiftMatch &m0 = matches[i], &m1 = matches[i + 1], &m2 = matches[i + 2], &m3 = matches[i + 3];
+        float ax, ay, bx, by;
+        coord(sourceXY, m1.source, ax, ay); coord(sourceXY, m0.source, bx, by);
+        const float sbx = ax - bx, sby = ay - by;
+        coord(targetXY, m1.target, ax, ay); coord(targetXY, m0.target, bx, by);
+        const float tbx = ax - bx, tby = ay - by;
+        const float sourceBaseLength = std::sqrt((sbx * sbx) + (sby * sby));
+        const float targetBaseLength = std::sqrt((tbx * tbx) + (tby * tby));
+        if (!(sourceBaseLength >= minimumLength)) continue;
+        if (!(targetBaseLength >= minimumLength)) continue;
+        const float sbnx = sbx / sourceBaseLength, sbny = sby / sourceBaseLength;
+        const float tbnx = tbx / targetBaseLength, tbny = tby / targetBaseLength;
+        coord(sourceXY, m3.source, ax, ay); coord(sourceXY, m2.source, bx, by);
+        const float stx = ax - bx, sty = ay - by;
+        coord(targetXY, m3.target, ax, ay); coord(targetXY, m2.target, bx, by);
+        const float ttx = ax - bx, tty = ay - by;
+        const float sourceTestLength = std::sqrt((stx * stx) + (sty * sty));
+        const float targetTestLength = std::sqrt((ttx * ttx) + (tty * tty));
+        if (!(sourceTestLength >= minimumLength)) continue;
+        if (!(targetTestLength >= minimumLength)) continue;
+        const float stnx = stx / sourceTestLength, stny = sty / sourceTestLength;
+        const float ttnx = ttx / targetTestLength, ttny = tty / targetTestLength;
+        const float sourceRatio = sourceTestLength / sourceBaseLength;
+        const float targetRatio = targetTestLength / targetBaseLength;
+        // dotProduct (:161-163): clamp(dot * 0.5 + 0.5, 0, 1)
+        const float sourceDot = geoClamp01((((stnx * sbnx) + (stny * sbny)) * 0.5f) + 0.5f);
+        const float targetDot = geoClamp01((((ttnx * tbnx) + (ttny * tbny)) * 0.5f) + 0.5f);
+        const float orientationSimilarity = 1.0f - std::fabs(sourceDot - targetDot);
+        float scaleSimilarity;
+        if (sourceRatio < targetRatio) scaleSimilarity = geoClamp01(sourceRatio / targetRatio);
+        else scaleSimilarity = geoClamp01(targetRatio / sourceRatio);
+        const float similarity = orientationSimilarity * scaleSimilarity;
+        const float score = similarity * similarity;
+        scores.push_back(score);
+        sum += score;
+        count += 1;
+    }
+    if (count < minimumSampleSize) return 0;
+    const float mean = sum / (float)count;
+    float error = 0;
+    for (float score : scores) {
+        const float delta = score - mean;
+        error += (delta * delta);
+    }
+    const float variance = error / (float)(count - 1);
+    const float standardDeviation = std::sqrt(variance);
+    float fairMeanSum = 0, fairMeanCount = 0;
+    for (float score : scores) {
+        const float zscore = std::fabs((score - mean) / standardDeviation);
+        if (zscore <= 2) {   // NaN (all scores equal: 0 / 0) compares false, as in Swift
+            fairMeanSum += score;
+            fairMeanCount += 1;
+        }
+    }
+    return fairMeanSum / fairMeanCount;
+}
+
+// matchGeometry (:104-143): brute-force matches (defaults 1.176 / 0.6), at least 7 of them, the
+// first 80 go to compareGeometry.
+float oracle_match_geometry(const uint8_t* source, const float* sourceXY, int64_t nSource, const uint8_t* target,
+                            const float* targetXY, int64_t nTarget, float absoluteThreshold,
+                            float relativeThreshold) {
+    const int minimumSampleSize = 7;
+    const int maximumSampleSize = std::max(minimumSampleSize, 80);
+    std::vector<SiftMatch> m((size_t)std::max<int64_t>(nSource, 1));
+    const int64_t n = oracle_match(source, nSource, target, nTarget, absoluteThreshold, relativeThreshold, m.data());
+    if (n < minimumSampleSize) return 0;
+    return oracle_compare_geometry(m.data(), std::min<int64_t>(n, maximumSampleSize), sourceXY, targetXY,
+                                   minimumSampleSize);
+}
+
+// ---- Trie ANN (Utilities/Trie.swift) + SIFTDescriptor.approximateMatch (SIFTDescriptor.swift:362-417) ----
+// Restated as the reference builds it: a recursive 8-ary trie keyed by the 16 components of
+// indexKey (one per histogram cell, in the reference's re-ordered cell sequence
+// SIFTDescriptor.swift:55-77), values in the leaves in insertion order, leaves linked left /
+// right in depth-first bin order (Trie.swift:119-128,142-157), nearest(key:query:radius:k:)
+// visiting the key's leaf, then `radius` leaves to the left, then `radius` to the right
+// (:229-253) with a FiniteQueue of capacity k that a value enters only when it beats the current
+// best (:287-300).
+// Oracle-defined: indexKey[c] = mean of the cell's 8 raw features f / 255 (vDSP.mean, rounding
+// unspecified) only matters through binIndex = Int((value * 7).rounded()) (:313-320); with S the
+// integer sum of the cell's 8 features that is round-half-away(7 S / 2040), evaluated exactly in
+// integers. Distances are compared as exact integers as in oracle_match.
+namespace {
+
+const int kTrieCellOrder[16] = {5, 6, 9, 10, 0, 3, 12, 15, 1, 2, 4, 7, 8, 11, 13, 14};   // SIFTDescriptor.swift:57-77
+const int kTrieBins = 8;
+
+void trieKey(const uint8_t* f, int key[16]) {
+    for (int c = 0; c < 16; c++) {
+        int S = 0;
+        for (int b = 0; b < 8; b++) S += f[kTrieCellOrder[c] * 8 + b];
+        key[c] = (14 * S + 2040) / 4080;   // round-half-up of 7 S / 2040, S >= 0
+    }
+}
+
+struct TrieNode {
+    TrieNode* child[kTrieBins] = {};
+    bool hasNodes = false;
+    std::vector<int32_t> values;
+    TrieNode *left = nullptr, *right = nullptr;
+    ~TrieNode() { for (auto* c : child) delete c; }
+};
+
+void trieInsert(TrieNode* n, const int* key, int depth, int32_t value) {
+    if (depth == 16) { n->values.push_back(value); return; }
+    TrieNode*& c = n->child[key[depth]];
+    if (!c) { c = new TrieNode(); n->hasNodes = true; }
+    trieInsert(c, key, depth + 1, value);
+}
+
+void trieLeaves(TrieNode* n, std::vector<TrieNode*>& out) {
+    if (n->hasNodes) { for (auto* c : n->child) if (c) trieLeaves(c, out); }
+    else out.push_back(n);
+}
+
+int trieWrap(int input) {   // wrapBinIndex (:338-350)
+    int output = input;
+    const int n = kTrieBins - 1;
+    if (output < 0) output += n;
+    else if (output >= n) output -= n;
+    return output;
+}
+
+TrieNode* trieClosest(TrieNode* n, int bin) {   // closestNode (:270-285)
+    if (n->child[bin]) return n->child[bin];
+    int bestDistance = INT32_MAX;
+    TrieNode* best = nullptr;
+    for (int j = 0; j < kTrieBins; j++) {
+        if (!n->child[j]) continue;
+        const int distance = trieWrap(std::abs(j - bin));   // binDifference (:303-309)
+        if (distance < bestDistance) { bestDistance = distance; best = n->child[j]; }
+    }
+    return best;
+}
+
+struct TrieQueue {   // FiniteQueue<Match>(capacity: 2) (:201-226): newest first
+    int32_t value[2];
+    int32_t d2[2];
+    int count = 0;
+    void insert(int32_t v, int32_t d) {
+        value[1] = value[0]; d2[1] = d2[0];
+        value[0] = v; d2[0] = d;
+        if (count < 2) count++;
+    }
+};
+
+void trieNearestValue(const TrieNode* n, const uint8_t* query, const uint8_t* target, TrieQueue& q) {   // (:287-300)
+    int32_t best = q.count ? q.d2[0] : INT32_MAX;
+    for (int32_t v : n->values) {
+        const uint8_t* b = target + (int64_t)v * 128;
+        int32_t d2 = 0;
+        for (int k = 0; k < 128; k++) { const int32_t d = (int32_t)b[k] - (int32_t)query[k]; d2 += d * d; }
+        if (d2 < best) { best = d2; q.insert(v, d2); }
+    }
+}
+
+}  // namespace
+
+int64_t oracle_approximate_match(const uint8_t* source, int64_t nSource, const uint8_t* target, int64_t nTarget,
+                                 float absoluteThreshold, float relativeThreshold, SiftMatch* out) {
+    if (nTarget < 1) return 0;   // link() of an empty trie leaves the root unlinked; nothing can match
+    TrieNode root;
+    int key[16];
+    for (int64_t j = 0; j < nTarget; j++) {
+        trieKey(target + j * 128, key);
+        trieInsert(&root, key, 0, (int32_t)j);
+    }
+    std::vector<TrieNode*> leaves;
+    trieLeaves(&root, leaves);
+    for (size_t i = 0; i < leaves.size(); i++) {   // link (:119-128)
+        TrieNode* a = leaves[i];
+        TrieNode* b = leaves[(i + 1) % leaves.size()];
+        a->right = b;
+        b->left = a;
+    }
+    int64_t n = 0;
+    const int radius = 10;
+    for (int64_t i = 0; i < nSource; i++) {
+        const uint8_t* q = source + i * 128;
+        trieKey(q, key);
+        TrieNode* bin = &root;   // nearestNode (:255-268)
+        for (int d = 0; d < 16; d++) {
+            if (!bin->hasNodes) break;
+            TrieNode* next = trieClosest(bin, key[d]);
+            if (!next) break;
+            bin = next;
+        }
+        TrieQueue queue;
+        trieNearestValue(bin, q, target, queue);
+        TrieNode* node = bin;
+        for (int r = 0; r < radius; r++) { node = node->left; trieNearestValue(node, q, target, queue); }
+        node = bin;
+        for (int r = 0; r < radius; r++) { node = node->right; trieNearestValue(node, q, target, queue); }
+        if (queue.count != 2) continue;   // guard matches.count == 2 (:394-396)
+        const float dBest = std::sqrt((float)queue.d2[0]) / 255.0f;
+        const float dSecond = std::sqrt((float)queue.d2[1]) / 255.0f;
+        if (!(dBest < absoluteThreshold)) continue;
+        if (!(dBest < (dSecond * relativeThreshold))) continue;
+        SiftMatch m;
+        m.source = (int32_t)i;
+        m.target = queue.value[0];
+        m.distance = dBest;
+        out[n++] = m;
+    }
+    return n;
+}
+
 }  // extern "C"

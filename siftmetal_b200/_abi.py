@@ -119,9 +119,16 @@ class SiftBatchResult(C.Structure):
         ("candidate_counts", C.POINTER(C.c_int32)),
         ("total_keypoints", C.c_int64),
         ("total_descriptors", C.c_int64),
+        ("slot", C.c_int32),
+        ("reserved", C.c_int32),
         ("keypoints", SiftKeypointColumns),
         ("descriptors", SiftDescriptorColumns),
     ]
+
+
+class SiftResultLayout(C.Structure):
+    _fields_ = [("bytes", C.c_int64), ("capacity_keypoints", C.c_int64), ("capacity_descriptors", C.c_int64),
+                ("offset", C.c_int64 * 10)]
 
 
 class SiftMatch(C.Structure):

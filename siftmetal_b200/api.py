@@ -66,6 +66,10 @@ def load_library():
     L.sift_submit.argtypes = [vp, C.POINTER(vp), i32, i32]
     L.sift_wait.argtypes = [vp, C.POINTER(SiftBatchResult)]
     L.sift_pending.argtypes = [vp]
+    L.sift_next_slot.argtypes = [vp]
+    L.sift_result_layout.argtypes = [vp, C.POINTER(_abi.SiftResultLayout)]
+    L.sift_register_host_memory.argtypes = [vp, vp, i64]
+    L.sift_bind_result_memory.argtypes = [vp, i32, vp, i64]
     L.sift_batch_upload.argtypes = [vp, C.POINTER(vp), i32, i32]
     L.sift_batch_set_device_input.argtypes = [vp, vp, i32, i32, i64]
     L.sift_batch_execute.argtypes = [vp]
@@ -74,6 +78,8 @@ def load_library():
     L.sift_materialize_descriptors.argtypes = [C.POINTER(SiftBatchResult), i64, i64, vp]
     L.sift_match.argtypes = [vp, vp, i64, vp, i64, f32, f32, C.POINTER(vp), C.POINTER(i64)]
     L.sift_match_frames.argtypes = [vp, i32, i32, f32, f32, C.POINTER(vp), C.POINTER(i64)]
+    L.sift_match_geometry.argtypes = [vp, vp, vp, i64, vp, vp, i64, f32, f32, C.POINTER(f32)]
+    L.sift_approximate_match.argtypes = [vp, vp, i64, vp, i64, f32, f32, C.POINTER(vp), C.POINTER(i64)]
     L.sift_status_string.argtypes = [C.c_int]
     L.sift_status_string.restype = C.c_char_p
     L.sift_last_error_string.argtypes = [vp]
@@ -92,9 +98,11 @@ def load_library():
 
 EXPORTED_SYMBOLS = (
     "sift_config_default sift_create sift_destroy sift_get_info sift_detect sift_describe "
-    "sift_detect_and_describe_batch sift_submit sift_wait sift_pending sift_batch_upload "
+    "sift_detect_and_describe_batch sift_submit sift_wait sift_pending sift_next_slot sift_result_layout "
+    "sift_register_host_memory sift_bind_result_memory sift_batch_upload "
     "sift_batch_set_device_input sift_batch_execute sift_batch_download sift_materialize_keypoints "
-    "sift_materialize_descriptors sift_match sift_match_frames sift_status_string "
+    "sift_materialize_descriptors sift_match sift_match_frames sift_match_geometry "
+    "sift_approximate_match sift_status_string "
     "sift_last_error_string sift_set_stage_timing sift_set_graph_replay sift_last_timings sift_debug_download "
     "sift_debug_candidates sift_debug_math sift_debug_blur_bench"
 ).split()
@@ -197,13 +205,14 @@ class BatchResult:
     `.descriptors` give record arrays (KEYPOINT_DTYPE / DESCRIPTOR_DTYPE), built on first use."""
 
     def __init__(self, keypoint_columns, descriptor_columns, keypoint_counts, descriptor_counts, candidate_counts,
-                 status=0):
+                 status=0, slot=0):
         self.keypoint_columns = keypoint_columns
         self.descriptor_columns = descriptor_columns
         self.keypoint_counts = keypoint_counts        # [n_frames, 7]
         self.descriptor_counts = descriptor_counts    # [n_frames, 7]
         self.candidate_counts = candidate_counts      # [n_frames, 7]
         self.status = status
+        self.slot = slot                              # in-flight slot that holds the (uncopied) columns
         self._kp_records = self._desc_records = None
 
     @property
@@ -386,6 +395,22 @@ class Engine:
     def pending(self):
         return int(self.L.sift_pending(self.ctx))
 
+    def next_slot(self):
+        return int(self.L.sift_next_slot(self.ctx))
+
+    def result_layout(self):
+        lay = _abi.SiftResultLayout()
+        self._check(self.L.sift_result_layout(self.ctx, C.byref(lay)))
+        return lay
+
+    def register_host_memory(self, address, nbytes):
+        self._check(self.L.sift_register_host_memory(self.ctx, address, nbytes))
+
+    def bind_result_memory(self, slot, address, nbytes):
+        """Slot `slot` (0 / 1) writes its result columns into caller memory (e.g. a shared-memory
+        mapping read by another process) instead of its own pinned block."""
+        self._check(self.L.sift_bind_result_memory(self.ctx, slot, address, nbytes))
+
     # -- matching (SIFTDescriptor.match, SIFTDescriptor.swift:298-361) ----------------------------
     def match(self, source_features, target_features, absolute_threshold=300.0, relative_threshold=0.6):
         a = np.ascontiguousarray(source_features, dtype=np.uint8).reshape(-1, 128)
@@ -399,6 +424,30 @@ class Engine:
         out, n = C.c_void_p(), C.c_int64()
         self._check(self.L.sift_match_frames(self.ctx, source_frame, target_frame, absolute_threshold,
                                              relative_threshold, C.byref(out), C.byref(n)))
+        return _view(out.value, n.value, _abi.MATCH_DTYPE).copy()
+
+    def match_geometry(self, source_features, source_xy, target_features, target_xy, absolute_threshold=1.176,
+                       relative_threshold=0.6):
+        """SIFTDescriptor.matchGeometry (SIFTDescriptor.swift:104-296): geometric-consistency score."""
+        a = np.ascontiguousarray(source_features, dtype=np.uint8).reshape(-1, 128)
+        b = np.ascontiguousarray(target_features, dtype=np.uint8).reshape(-1, 128)
+        axy = np.ascontiguousarray(source_xy, dtype=np.float32).reshape(-1, 2)
+        bxy = np.ascontiguousarray(target_xy, dtype=np.float32).reshape(-1, 2)
+        if len(axy) != len(a) or len(bxy) != len(b):
+            raise ValueError("one (x, y) pair per descriptor row")
+        score = C.c_float()
+        self._check(self.L.sift_match_geometry(self.ctx, a.ctypes.data, axy.ctypes.data, len(a), b.ctypes.data,
+                                               bxy.ctypes.data, len(b), absolute_threshold, relative_threshold,
+                                               C.byref(score)))
+        return score.value
+
+    def approximate_match(self, source_features, target_features, absolute_threshold=300.0, relative_threshold=0.6):
+        """SIFTDescriptor.approximateMatch over the trie ANN (SIFTDescriptor.swift:362-417, Utilities/Trie.swift)."""
+        a = np.ascontiguousarray(source_features, dtype=np.uint8).reshape(-1, 128)
+        b = np.ascontiguousarray(target_features, dtype=np.uint8).reshape(-1, 128)
+        out, n = C.c_void_p(), C.c_int64()
+        self._check(self.L.sift_approximate_match(self.ctx, a.ctypes.data, len(a), b.ctypes.data, len(b),
+                                                  absolute_threshold, relative_threshold, C.byref(out), C.byref(n)))
         return _view(out.value, n.value, _abi.MATCH_DTYPE).copy()
 
     # -- diagnostics -----------------------------------------------------------------------------
@@ -474,7 +523,7 @@ class Engine:
                                _view(d.keypoint, nd, "<i4"))
         if copy:   # the pinned columns are reused by a later call
             kv, dv = kv.copy(), dv.copy()
-        return BatchResult(kv, dv, kc, dc, cc, status=int(r.status))
+        return BatchResult(kv, dv, kc, dc, cc, status=int(r.status), slot=int(r.slot))
 
 
 def device_math(op, a, b=None, device=0):

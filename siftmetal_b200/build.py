@@ -25,6 +25,7 @@ SOURCES = {
     "detect.cu": ["-fmad=false"],
     "describe.cu": (["-DSIFT_DEBUG_DESC"] if os.environ.get("SIFT_DEBUG_DESC") else []),
     "match.cu": [],
+    "geometry.cu": ["-Xcompiler", "-ffp-contract=off", "-fmad=false"],
     "capi.cu": [],
 }
 HEADERS = ["common.cuh", "dev_math.cuh", "scan.cuh", "capi_match.inc", os.path.join(ROOT, "include", "siftcuda.h")]

@@ -49,6 +49,8 @@ struct Slot {
     uint8_t* dInput = nullptr;          // device input arena (max_batch frames)
     bool allocated = false;
     ResultColumns host{};               // pinned host memory, device-addressable (UVA)
+    void* hostBlock = nullptr;          // start of the block the columns are carved from
+    bool hostBlockExternal = false;     // caller memory (sift_bind_result_memory), not ours to free
     Counters* hCounters = nullptr;      // pinned
     int* hSegStarts = nullptr;          // pinned: [3][nSegs + 1] candidates, keypoints, descriptors
     cudaEvent_t evUploaded = nullptr, evStart = nullptr, evEnd = nullptr;
@@ -131,6 +133,7 @@ struct SiftContext {
 
     Slot slot[2];
     int head = 0, next = 0, nPending = 0;
+    std::vector<std::pair<char*, size_t>> registered;   // caller memory pinned by sift_register_host_memory
     Slot* last = nullptr;       // slot holding the results of the last completed call
 
     // staged path input
@@ -252,7 +255,11 @@ int ensureSlot(SiftContext* c, int s) {
     A(devAlloc(c, &S.dInput, (size_t)c->B * frameBytes));
     void* block = nullptr;
     A(cudaMallocHost(&block, columnsBytes((size_t)c->capKp, (size_t)c->capDesc)));
-    if (e == cudaSuccess) S.host = carveColumns(block, (size_t)c->capKp, (size_t)c->capDesc);
+    if (e == cudaSuccess) {
+        S.host = carveColumns(block, (size_t)c->capKp, (size_t)c->capDesc);
+        S.hostBlock = block;
+        S.hostBlockExternal = false;
+    }
     A(cudaMallocHost(&S.hCounters, sizeof(Counters)));
     A(cudaMallocHost(&S.hSegStarts, 3 * (size_t)(c->nSegs + 1) * sizeof(int)));
     A(cudaEventCreateWithFlags(&S.evUploaded, cudaEventDisableTiming));
@@ -299,8 +306,9 @@ void destroy(SiftContext* c) {
     for (auto& g : c->graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
     for (void* p : c->allocations) cudaFree(p);
+    for (auto& r : c->registered) cudaHostUnregister(r.first);
     for (auto& S : c->slot) {
-        if (S.host.kp.absX) cudaFreeHost(S.host.kp.absX);   // first column = start of the block
+        if (S.hostBlock && !S.hostBlockExternal) cudaFreeHost(S.hostBlock);
         if (S.hCounters) cudaFreeHost(S.hCounters);
         if (S.hSegStarts) cudaFreeHost(S.hSegStarts);
         if (S.evUploaded) cudaEventDestroy(S.evUploaded);
@@ -611,6 +619,68 @@ int sift_last_timings(const SiftContext* c, SiftTimings* out) {
 
 int sift_pending(const SiftContext* c) { return c ? c->nPending : 0; }
 
+int sift_next_slot(const SiftContext* c) { return c ? c->next : 0; }
+
+int sift_result_layout(const SiftContext* c, SiftResultLayout* out) {
+    if (!c || !out) return SIFT_ERR_INVALID_ARGUMENT;
+    memset(out, 0, sizeof *out);
+    out->bytes = (int64_t)columnsBytes((size_t)c->capKp, (size_t)c->capDesc);
+    out->capacity_keypoints = c->capKp;
+    out->capacity_descriptors = c->capDesc;
+    const ResultColumns r = carveColumns(nullptr, (size_t)c->capKp, (size_t)c->capDesc);
+    const void* cols[10] = {r.kp.absX, r.kp.absY, r.kp.sigma, r.kp.value, r.kp.subScale, r.kp.scaledXY,
+                            r.kp.octaveScale, r.desc.features, r.desc.theta, r.desc.keypoint};
+    for (int i = 0; i < 10; i++) out->offset[i] = (int64_t)(uintptr_t)cols[i];
+    return SIFT_OK;
+}
+
+int sift_register_host_memory(SiftContext* c, void* base, int64_t bytes) {
+    if (!c || !base || bytes < 1) return SIFT_ERR_INVALID_ARGUMENT;
+    CTX_TRY(c, cudaSetDevice(c->device));
+    // the kernels store result columns through the device mapping of this memory
+    CTX_TRY(c, cudaHostRegister(base, (size_t)bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+    void* dptr = nullptr;
+    const cudaError_t e = cudaHostGetDevicePointer(&dptr, base, 0);
+    if (e != cudaSuccess || dptr != base) {   // unified addressing: the device uses the host pointer
+        cudaHostUnregister(base);
+        return fail(c, SIFT_ERR_CUDA, "registered memory is not addressable by its host pointer", e);
+    }
+    c->registered.emplace_back((char*)base, (size_t)bytes);
+    return SIFT_OK;
+}
+
+int sift_bind_result_memory(SiftContext* c, int32_t slot, void* base, int64_t bytes) {
+    if (!c || slot < 0 || slot > 1 || !base || ((uintptr_t)base & 255)) return SIFT_ERR_INVALID_ARGUMENT;
+    if (c->slot[slot].pending) return fail(c, SIFT_ERR_BUSY, "sift_bind_result_memory: the slot has a call in flight");
+    const size_t need = columnsBytes((size_t)c->capKp, (size_t)c->capDesc);
+    if (bytes < (int64_t)need)
+        return fail(c, SIFT_ERR_INVALID_ARGUMENT, "sift_bind_result_memory: block smaller than sift_result_layout().bytes");
+    bool inside = false;
+    for (auto& r : c->registered)
+        inside = inside || ((char*)base >= r.first && (char*)base + need <= r.first + r.second);
+    if (!inside)
+        return fail(c, SIFT_ERR_INVALID_ARGUMENT, "sift_bind_result_memory: not inside memory given to sift_register_host_memory");
+    CTX_TRY(c, cudaSetDevice(c->device));
+    const int r = ensureSlot(c, slot);
+    if (r != SIFT_OK) return r;
+    Slot& S = c->slot[slot];
+    if (S.hostBlock && !S.hostBlockExternal) cudaFreeHost(S.hostBlock);
+    S.hostBlock = base;
+    S.hostBlockExternal = true;
+    S.host = carveColumns(base, (size_t)c->capKp, (size_t)c->capDesc);
+    // recorded graphs of this slot carry the old pointers
+    for (size_t i = 0; i < c->graphs.size();) {
+        if (c->graphs[i].slot == slot) {
+            if (c->graphs[i].exec) cudaGraphExecDestroy(c->graphs[i].exec);
+            c->graphs.erase(c->graphs.begin() + (long)i);
+        } else {
+            i++;
+        }
+    }
+    if (c->last == &S) { c->last = nullptr; c->executed = false; }
+    return SIFT_OK;
+}
+
 }  // extern "C"
 
 namespace {
@@ -910,9 +980,10 @@ int finishSlot(SiftContext* c, Slot& S) {
 }
 
 void fillResult(const SiftContext* c, const Slot& S, SiftBatchResult* out) {
-    (void)c;
     out->n_frames = S.frames;
     out->status = S.status;
+    out->slot = (int32_t)(&S - c->slot);
+    out->reserved = 0;
     out->keypoint_counts = S.kpCounts.data();
     out->descriptor_counts = S.descCounts.data();
     out->candidate_counts = S.candCounts.data();

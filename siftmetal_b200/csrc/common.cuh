@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <vector>
+
 #include "../../include/siftcuda.h"
 
 namespace sift {
@@ -207,6 +209,11 @@ size_t matchScratchInts(int nSource, int nTarget, int smCount);
 cudaError_t launchMatch(const uint8_t* source, int nSource, const uint8_t* target, int nTarget,
                         float absThr, float relThr, int* scratch, SiftMatch* rows, int smCount,
                         cudaStream_t st);
+
+// geometry.cu (host stages: SIFTDescriptor.compareGeometry, the trie ANN matcher)
+float compareGeometry(const SiftMatch* m, int64_t n, const float* sourceXY, const float* targetXY, int minimumSampleSize);
+void approximateMatch(const uint8_t* source, int64_t nSource, const uint8_t* target, int64_t nTarget, float absThr,
+                      float relThr, std::vector<SiftMatch>& out);
 
 // math debug (capi.cu → describe.cu)
 cudaError_t launchMathDebug(int op, const float* a, const float* b, float* out, int64_t n,

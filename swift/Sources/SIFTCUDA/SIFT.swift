@@ -138,4 +138,108 @@ public final class SIFT {
         }
         return result
     }
+
+    // MARK: - Beyond the reference's two calls (ABI v2): batches, pipelining, lazy views, matching
+
+    /// getKeypoints + getDescriptors for several frames in one call; results as lazy views over the
+    /// column wire format (`SiftBatchResult`): a `SIFTKeypoint` / `SIFTDescriptor` is only built when
+    /// an element is indexed (the reference pays SIFTDescriptor.init per descriptor, SIFTDescriptor.swift:36-89).
+    public func detectAndDescribe(frames: [UnsafeRawPointer?], bytesPerRow: Int) -> [FrameResult] {
+        var r = SiftBatchResult()
+        let status = frames.withUnsafeBufferPointer {
+            sift_detect_and_describe_batch(context, $0.baseAddress, Int32(frames.count), Int32(bytesPerRow), &r)
+        }
+        precondition(status == SIFT_OK, String(cString: sift_last_error_string(context)))
+        return split(r)
+    }
+
+    /// Pipelined form (CoreVideoMetalCache.swift:23-31 hands over one texture per camera frame): up to two
+    /// calls in flight, `wait()` returns them in submission order. The frames must stay valid until then.
+    public func submit(frames: [UnsafeRawPointer?], bytesPerRow: Int) {
+        let status = frames.withUnsafeBufferPointer {
+            sift_submit(context, $0.baseAddress, Int32(frames.count), Int32(bytesPerRow))
+        }
+        precondition(status == SIFT_OK, String(cString: sift_last_error_string(context)))
+    }
+
+    public func wait() -> [FrameResult] {
+        var r = SiftBatchResult()
+        let status = sift_wait(context, &r)
+        precondition(status == SIFT_OK, String(cString: sift_last_error_string(context)))
+        return split(r)
+    }
+
+    /// SIFTDescriptor.match(source:target:absoluteThreshold:relativeThreshold:) (SIFTDescriptor.swift:298-361)
+    /// on the dense feature matrices of two descriptor views; (source row, target row, featureDistance).
+    public func match(source: DescriptorView, target: DescriptorView,
+                      absoluteThreshold: Float = 300, relativeThreshold: Float = 0.6) -> [SiftMatch] {
+        var out: UnsafePointer<SiftMatch>?
+        var n: Int64 = 0
+        let status = sift_match(context, source.features, Int64(source.count), target.features, Int64(target.count),
+                                absoluteThreshold, relativeThreshold, &out, &n)
+        precondition(status == SIFT_OK, String(cString: sift_last_error_string(context)))
+        return Array(UnsafeBufferPointer(start: out, count: Int(n)))
+    }
+
+    private func split(_ r: SiftBatchResult) -> [FrameResult] {
+        var out = [FrameResult]()
+        var k: Int64 = 0
+        var d: Int64 = 0
+        for f in 0 ..< Int(r.n_frames) {
+            var nk: Int64 = 0
+            var nd: Int64 = 0
+            for o in 0 ..< Int(SIFT_NUM_OCTAVES) {
+                nk += Int64(r.keypoint_counts[f * Int(SIFT_NUM_OCTAVES) + o])
+                nd += Int64(r.descriptor_counts[f * Int(SIFT_NUM_OCTAVES) + o])
+            }
+            let kv = KeypointView(context: context, result: r, first: k, count: Int(nk))
+            out.append(FrameResult(keypoints: kv, descriptors: DescriptorView(result: r, first: d, count: Int(nd), keypoints: kv)))
+            k += nk
+            d += nd
+        }
+        return out
+    }
 }
+
+/// Lazy random-access view of the keypoint columns of one frame.
+public struct KeypointView: RandomAccessCollection {
+    let context: OpaquePointer?
+    let result: SiftBatchResult
+    let first: Int64
+    public let count: Int
+    public var startIndex: Int { 0 }
+    public var endIndex: Int { count }
+    public subscript(index: Int) -> SIFTKeypoint {
+        var p = SiftKeypoint()
+        var r = result
+        let status = sift_materialize_keypoints(context, &r, first + Int64(index), 1, &p)
+        precondition(status == SIFT_OK)
+        return SIFTKeypoint(p)
+    }
+}
+
+/// Lazy random-access view of the descriptor columns of one frame.
+public struct DescriptorView: RandomAccessCollection {
+    let result: SiftBatchResult
+    let first: Int64
+    public let count: Int
+    let keypoints: KeypointView
+    public var startIndex: Int { 0 }
+    public var endIndex: Int { count }
+    /// dense [count][128] uint8 feature matrix
+    public var features: UnsafePointer<UInt8>? { result.descriptors.features.map { $0 + Int(first) * 128 } }
+    public subscript(index: Int) -> SIFTDescriptor {
+        var d = SiftDescriptor()
+        var r = result
+        let status = sift_materialize_descriptors(&r, first + Int64(index), 1, &d)
+        precondition(status == SIFT_OK)
+        let features = withUnsafeBytes(of: d.features) { $0.map { Int($0) } }
+        return SIFTDescriptor(keypoint: keypoints[Int(d.keypoint)], theta: d.theta, features: IntVector(features))
+    }
+}
+
+public struct FrameResult {
+    public let keypoints: KeypointView
+    public let descriptors: DescriptorView
+}
+

@@ -48,6 +48,11 @@ def lib():
         L.oracle_math.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
         L.oracle_match.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_void_p]
         L.oracle_match.restype = C.c_int64
+        L.oracle_approximate_match.argtypes = L.oracle_match.argtypes
+        L.oracle_approximate_match.restype = C.c_int64
+        L.oracle_match_geometry.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+                                            C.c_float, C.c_float]
+        L.oracle_match_geometry.restype = C.c_float
         _lib = L
     return _lib
 
@@ -159,3 +164,23 @@ def oracle_match(source, target, absolute_threshold=300.0, relative_threshold=0.
     n = lib().oracle_match(a.ctypes.data, len(a), b.ctypes.data, len(b), absolute_threshold, relative_threshold,
                            out.ctypes.data)
     return out[:n].copy()
+
+
+def oracle_approximate_match(source, target, absolute_threshold=300.0, relative_threshold=0.6):
+    """SIFTDescriptor.approximateMatch over the reference's trie (SIFTDescriptor.swift:362-417, Trie.swift)."""
+    a = np.ascontiguousarray(source, dtype=np.uint8).reshape(-1, 128)
+    b = np.ascontiguousarray(target, dtype=np.uint8).reshape(-1, 128)
+    out = np.zeros(max(len(a), 1), dtype=_abi.MATCH_DTYPE)
+    n = lib().oracle_approximate_match(a.ctypes.data, len(a), b.ctypes.data, len(b), absolute_threshold,
+                                       relative_threshold, out.ctypes.data)
+    return out[:n].copy()
+
+
+def oracle_match_geometry(source, source_xy, target, target_xy, absolute_threshold=1.176, relative_threshold=0.6):
+    """SIFTDescriptor.matchGeometry (SIFTDescriptor.swift:104-296)."""
+    a = np.ascontiguousarray(source, dtype=np.uint8).reshape(-1, 128)
+    b = np.ascontiguousarray(target, dtype=np.uint8).reshape(-1, 128)
+    axy = np.ascontiguousarray(source_xy, dtype=np.float32).reshape(-1, 2)
+    bxy = np.ascontiguousarray(target_xy, dtype=np.float32).reshape(-1, 2)
+    return float(lib().oracle_match_geometry(a.ctypes.data, axy.ctypes.data, len(a), b.ctypes.data, bxy.ctypes.data,
+                                             len(b), absolute_threshold, relative_threshold))

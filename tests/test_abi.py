@@ -31,7 +31,7 @@ def lib():
 
 def test_library_exports_every_declared_symbol(lib):
     names = _declared_functions()
-    assert len(names) >= 18
+    assert len(names) >= 26
     for n in names:
         assert hasattr(lib, n), f"{n} declared in siftcuda.h but not exported"
     assert sorted(api.EXPORTED_SYMBOLS) == names
@@ -60,7 +60,12 @@ def test_cpp_host_mirror_compiles(tmp_path):
     prog = tmp_path / "use.cpp"
     prog.write_text(
         '#include "SIFT.hpp"\n#include <cstdio>\n'
-        "int main(){ try { siftcuda::SIFT s(0, siftcuda::SIFT::Configuration(siftcuda::IntegralSize{64,48})); }\n"
+        "int main(){ try { siftcuda::SIFT s(0, siftcuda::SIFT::Configuration(siftcuda::IntegralSize{64,48}));\n"
+        "  std::vector<unsigned char> px(64 * 48 * 4, 7); std::vector<const void*> fr{px.data()};\n"
+        "  auto res = s.detectAndDescribe(fr, 64 * 4); s.submit(fr, 64 * 4); auto res2 = s.wait();\n"
+        "  auto m = s.match(res[0].descriptors, res2[0].descriptors);\n"
+        "  if (res[0].keypoints.size() > 0) { auto k = res[0].keypoints[0]; (void)k; }\n"
+        "  std::printf(\"%zu %zu\\n\", res.size(), m.size()); }\n"
         " catch (const std::exception& e) { std::printf(\"%s\\n\", e.what()); return 3; } return 0; }\n"
     )
     exe = tmp_path / "use"

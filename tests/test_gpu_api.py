@@ -191,3 +191,104 @@ def test_staged_path_and_partial_batches():
     k2, d2 = part.frame(0)
     assert np.array_equal(k1, k2) and np.array_equal(d1, d2) and part.keypoint_counts.shape == (2, 7)
     eng.close()
+
+
+def test_cpp_host_mirror_runs(tmp_path):
+    """include/SIFT.hpp on the device: batch call, pipelined submit / wait, lazy views, match."""
+    import os
+    import subprocess
+
+    from conftest import ROOT
+    from siftmetal_b200 import api
+    from siftmetal_b200.synth import pink_noise_bgra
+
+    img = pink_noise_bgra(320, 240, 2)
+    raw = tmp_path / "frame.bgra"
+    raw.write_bytes(img.tobytes())
+    prog = tmp_path / "run.cpp"
+    prog.write_text(
+        '#include "SIFT.hpp"\n#include <cstdio>\n#include <vector>\n'
+        "int main(int argc, char** argv){ std::vector<unsigned char> px(320 * 240 * 4);\n"
+        " FILE* f = std::fopen(argv[1], \"rb\"); if (!f || std::fread(px.data(), 1, px.size(), f) != px.size()) return 2;\n"
+        " siftcuda::SIFT s(0, siftcuda::SIFT::Configuration(siftcuda::IntegralSize{320, 240}));\n"
+        " std::vector<const void*> fr{px.data()};\n"
+        " auto a = s.detectAndDescribe(fr, 320 * 4); s.submit(fr, 320 * 4); auto b = s.wait();\n"
+        " auto m = s.match(a[0].descriptors, b[0].descriptors);\n"
+        " auto k = a[0].keypoints[3]; auto d = a[0].descriptors[5];\n"
+        " auto octs = s.getKeypoints(px.data(), 320 * 4); size_t nk = 0; for (auto& o : octs) nk += o.size();\n"
+        " std::printf(\"%lld %lld %zu %zu %d %d\\n\", (long long)a[0].keypoints.size(), (long long)a[0].descriptors.size(),\n"
+        "   m.size(), nk, k.scaledCoordinate[0], (int)d.features.components.size()); return 0; }\n")
+    exe = tmp_path / "run"
+    libdir = os.path.dirname(api.LIB_PATH)
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe),
+                    "-L", libdir, "-lsiftcuda", f"-Wl,-rpath,{libdir}"], check=True)
+    r = subprocess.run([str(exe), str(raw)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    nk, nd, nm, nk2, x, nf = [int(v) for v in r.stdout.split()]
+    from siftmetal_b200 import Engine
+
+    e = Engine(320, 240)
+    ref = e.detect_and_describe([img])
+    assert nk == len(ref.keypoints) == nk2 and nd == len(ref.descriptors) and nf == 128
+    assert x == int(ref.keypoints["scaledX"][3])
+    # a descriptor set matched against itself: every descriptor whose nearest neighbour is itself at
+    # distance 0 and passes 0 < 0.6 * second is kept unless an earlier duplicate exists
+    assert nm == len(e.match(ref.descriptor_columns.features, ref.descriptor_columns.features))
+    e.close()
+
+
+def test_results_stored_into_caller_memory():
+    """sift_register_host_memory / sift_bind_result_memory: the slots' result columns live in
+    caller memory (here a POSIX shared-memory segment, as the multi-process gather uses) and the
+    kernels store into it directly; rotating a slot through several blocks keeps older results."""
+    import ctypes as C
+    from multiprocessing import shared_memory
+
+    from siftmetal_b200 import Engine, SiftError
+    from siftmetal_b200.sharding import _COLS, block_layout
+    from siftmetal_b200.synth import pink_noise_bgra
+
+    w, h = 320, 240
+    imgs = [pink_noise_bgra(w, h, 60 + i) for i in range(4)]
+    eng = Engine(w, h)
+    ref = [eng.detect_and_describe([im]) for im in imgs]
+    lay = eng.result_layout()
+    offsets, nbytes = block_layout(int(lay.capacity_keypoints), int(lay.capacity_descriptors))
+    assert offsets == list(lay.offset) and nbytes == int(lay.bytes)
+    blocks = 4
+    stride = (nbytes + 4095) // 4096 * 4096
+    shm = shared_memory.SharedMemory(create=True, size=blocks * stride + 4096)
+    try:
+        base = C.addressof(C.c_char.from_buffer(shm.buf))
+        pad = (-base) % 4096
+        with pytest.raises(SiftError):
+            eng.bind_result_memory(0, base + pad, nbytes)            # not registered yet
+        eng.register_host_memory(base + pad, blocks * stride)
+        for i, im in enumerate(imgs):                                # four pipelined calls, a block each
+            if eng.pending() == 2:
+                eng.wait(copy=False)
+            eng.bind_result_memory(eng.next_slot(), base + pad + i * stride, nbytes)
+            eng.submit([im])
+        while eng.pending():
+            eng.wait(copy=False)
+        for i in range(blocks):                                      # every block still holds its call's columns
+            r = ref[i]
+            nk, nd = len(r.keypoints), len(r.descriptors)
+            got = {}
+            for (group, name, dtype, per), off in zip(_COLS, offsets):
+                rows = nk if group == "kp" else nd
+                got[name] = np.ndarray((rows, per) if per > 1 else (rows,), dtype, shm.buf, pad + i * stride + off)
+            assert np.array_equal(got["absolute_x"], r.keypoint_columns.absolute_x)
+            assert np.array_equal(got["scaled_xy"], r.keypoint_columns.scaled_xy)
+            assert np.array_equal(got["octave_scale"], r.keypoint_columns.octave_scale)
+            assert np.array_equal(got["features"], r.descriptor_columns.features)
+            assert np.array_equal(got["theta"], r.descriptor_columns.theta)
+            assert np.array_equal(got["keypoint"], r.descriptor_columns.keypoint)
+            del got
+        eng.close()
+    finally:
+        try:
+            shm.close()
+        except BufferError:
+            pass
+        shm.unlink()

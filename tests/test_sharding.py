@@ -75,8 +75,9 @@ def test_two_rank_gloo_gather(tmp_path):
 
 
 def test_two_rank_shared_memory_gather(tmp_path):
-    """ShmGather (the bench's host gather): two gloo ranks publish fake result columns of their frame
-    shards; rank 0 reads every frame of the job in frame order from the mapped segments."""
+    """ShmGather (the bench's host gather) in copy mode: two gloo ranks publish fake result columns
+    of their frame shards call by call; rank 0 reads every frame of the job in frame order from the
+    mapped segments. (The zero-copy mode, slots bound to the segment, needs a GPU.)"""
     script = tmp_path / "gworker.py"
     script.write_text(textwrap.dedent(
         """
@@ -84,7 +85,7 @@ def test_two_rank_shared_memory_gather(tmp_path):
         sys.path.insert(0, %r)
         import numpy as np
         import torch.distributed as dist
-        from siftmetal_b200.sharding import ShmGather, shard_range
+        from siftmetal_b200.sharding import ShmGather, shard_range, block_layout
         from siftmetal_b200.api import BatchResult, KeypointColumns, DescriptorColumns
         dist.init_process_group("gloo")
         rank, world = dist.get_rank(), dist.get_world_size()
@@ -100,22 +101,25 @@ def test_two_rank_shared_memory_gather(tmp_path):
             dv = DescriptorColumns(np.repeat(ids.astype(np.uint8)[:, None], 128, 1), ids, np.arange(n, dtype=np.int32))
             return BatchResult(kv, dv, kc, kc.copy(), kc.copy())
 
-        g = ShmGather(rank, world, n_local=b - a, cap_kp=64, cap_desc=64, tag="t%%d" %% os.getpid() if world == 1 else os.environ["MASTER_PORT"])
+        g = ShmGather(rank, world, max_frames_per_call=3, calls_per_step=2, cap_kp=64, cap_desc=64)
+        starts = [shard_range(total, r, world)[0] for r in range(world)]
         out = []
         for step in range(3):
             mine = list(range(a, b))
-            half = len(mine) // 2               # two calls (chunks) per step
-            g.publish(fake(mine[:half], step), 0)
-            g.publish(fake(mine[half:], step), half)
-            g.step_done()
+            half = len(mine) // 2               # two calls per step
+            for part, off in ((mine[:half], 0), (mine[half:], half)):
+                g.before_submit()
+                g.publish(fake(part, step), off)
+                g.call_done()
             if rank == 0:
                 for f in range(total):
-                    kp, desc = g.frame(f)
+                    r = max(i for i in range(world) if starts[i] <= f)
+                    kp, desc = g.frame(r, f - starts[r])
                     assert len(kp["sigma"]) == f + 1 and np.all(kp["sigma"] == 100 * step + f), (step, f)
                     assert desc["features"].shape == (f + 1, 128) and np.all(desc["theta"] == 100 * step + f)
-                out.append(int(g.last["keypoint_counts"].sum()))
+                out.append(g.stats["keypoints"])
         if rank == 0:
-            print(json.dumps({"sums": out, "stats": g.summary()}))
+            print(json.dumps({"sums": out, "stats": g.summary(), "layout": block_layout(1000, 2000)[1]}))
         g.close()
         dist.destroy_process_group()
         """ % ROOT))
@@ -128,4 +132,5 @@ def test_two_rank_shared_memory_gather(tmp_path):
     import json
 
     out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
-    assert out["sums"] == [45, 45, 45] and out["stats"]["frames"] == 27 and out["stats"]["keypoints"] == 135
+    assert out["sums"] == [45, 90, 135] and out["stats"]["frames"] == 27 and out["stats"]["calls"] == 6
+    assert out["layout"] == 5 * 4096 + 4096 + 2048 + 256000 + 2 * 8192
