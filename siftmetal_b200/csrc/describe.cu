@@ -277,6 +277,7 @@ constexpr int kDescCopies = 32;    // lane-private histogram copies (16 KB per w
 constexpr int kDescWarps = 7;      // 112 KB of histograms per CTA, two CTAs (14 warps) per SM
 constexpr int kDescMaxSide = 128;  // 2·radius+1; radius <= 39 for detected keypoints
 constexpr int kDescBins = 128;
+constexpr int kDescDefaultParts = 4;
 
 // Trilinear accumulation of one sample into the lane's histogram copy (addFeature,
 // SIFTDescriptor.metal:82-117). Two base addresses per sample (one per orientation bin); the
@@ -336,7 +337,7 @@ __device__ __forceinline__ void descAccumulate(char* const hl, const float2 gm, 
 // (Measured and dropped: one sample per step, 0.43 vs 0.41 ms; the warp as a (32 / C)-row x
 // C-column tile over row groups, C = 4, 8, 16 — uniform control flow, but idle lane slots at the
 // ragged span ends pay the full accumulation cost: 0.60 / 0.63 / 0.74 ms against 0.46 ms.)
-template <int NPAIRS>
+template <int NPAIRS, int PARTS>
 __global__ void __launch_bounds__(kDescWarps * 32, 2)
 descriptorKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __restrict__ kps,
                  const int* __restrict__ kpSeg, const int* __restrict__ segKpStart,
@@ -400,11 +401,73 @@ descriptorKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __r
         const int iMax = min(min(radius, iExt), o.h - 1 - ipy);
 
 #pragma unroll 8
-        for (int bb = 0; bb < 128 * kDescCopies / 32; bb++) hist[bb * 32 + lane] = 0.0f;
+        for (int bb = 0; bb < kDescBins * kDescCopies / 128; bb++)     // 32 x STS.128 per lane
+            reinterpret_cast<float4*>(hist)[bb * 32 + lane] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         __syncwarp();
         char* const hl = reinterpret_cast<char*>(hist + lane);
 
-        {
+        if constexpr (PARTS > 0) {
+            // Walk by UNITS: unit u = part (u % PARTS) of window row (u / PARTS); a lane takes unit
+            // lane + 32 k and walks its run of 16-byte aligned sample pairs along the row, one pair
+            // per iteration with the next pair's gather already in flight. The row bounds are
+            // evaluated once per unit and never inside the walk (the flattened walk below re-derives
+            // them, ~26 instructions, every time a lane crosses a row: ~1.6 times per pair), and the
+            // rotated coordinates advance by a multiply-add per pair. The 32 lanes of a step cover
+            // 32 / PARTS neighbouring rows of almost equal length, so few lane slots idle.
+            const int xLast = o.w - 1;
+            const int nUnits = (iMax - iMin + 1) * PARTS;
+            const float a2 = a + a, b2 = b + b;
+            for (int u0 = 0; u0 < nUnits; u0 += 32) {
+                const int u = u0 + lane;
+                int len = 0, x = 0;
+                float rx0 = 0.0f, ry0 = 0.0f;
+                const float2* __restrict__ gp = g;
+                if (u < nUnits) {
+                    const int row = u / PARTS, part = u - row * PARTS;
+                    const int i = iMin + row;
+                    const float fi = smallIntToFloat(i);
+                    const float lo = fmaxf(fmaxf(fmaf(fi, s1, -c1), fmaf(fi, s2, -c2)), xlo);
+                    const float hi = fminf(fminf(fmaf(fi, s1, c1), fmaf(fi, s2, c2)), xhi);
+                    const int xs = (ipx + max(ceilToInt(lo - 1.0f), -ipx)) & ~1;
+                    const int xe = min(ipx + floorToInt(hi + 1.0f), xLast);
+                    const int np = max((xe - xs + 2) >> 1, 0);
+                    const int seg = (np + PARTS - 1) / PARTS;
+                    const int p0 = part * seg;
+                    len = max(min(p0 + seg, np) - p0, 0);
+                    x = xs + 2 * p0;
+                    const float fj = smallIntToFloat(x - ipx);
+                    rx0 = fj * a - fi * b;
+                    ry0 = fj * b + fi * a;
+                    gp = g + (size_t)(ipy + i) * o.pitch + x;
+                }
+                // two pairs per iteration, the gathers of the following two already in flight (a
+                // distance of ~300 issue slots of this warp: the gradient planes mostly come from DRAM)
+                auto gather = [&](int k) -> float4 {
+                    return k < len ? __ldg(reinterpret_cast<const float4*>(gp + 2 * k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                };
+                auto pairAt = [&](const float4 v, int k, float kf) {
+                    const bool live = k < len;
+                    const float rx = fmaf(kf, a2, rx0), ry = fmaf(kf, b2, ry0);
+                    const float rx1 = rx + a, ry1 = ry + b;
+                    const bool ok0 = live && fabsf(rx) < 2.5f && fabsf(ry) < 2.5f;
+                    const bool ok1 = live && fabsf(rx1) < 2.5f && fabsf(ry1) < 2.5f && (x + 2 * k < xLast);
+                    descAccumulate(hl, make_float2(v.x, v.y), rx + 1.5f, ry + 1.5f, rx * rx + ry * ry, ok0, theta);
+                    descAccumulate(hl, make_float2(v.z, v.w), rx1 + 1.5f, ry1 + 1.5f, rx1 * rx1 + ry1 * ry1, ok1, theta);
+                };
+                float4 va = gather(0), vb = gather(1);
+                float kf = 0.0f;
+                for (int k = 0; __any_sync(0xffffffffu, k < len); k += 2) {
+                    const float4 vc = gather(k + 2);
+                    pairAt(va, k, kf);
+                    const float4 vd = gather(k + 3);
+                    pairAt(vb, k + 1, kf + 1.0f);
+                    kf += 2.0f;
+                    va = vc;
+                    vb = vd;
+                }
+            }
+        } else {
+            // Flattened walk (PARTS == 0): lanes stride through the concatenated spans of all rows.
             // Sample PAIRS start at even absolute x. Rows are padded to whole pairs; the padding
             // samples fail the exact cull (or the plane check) below.
             int i = iMin, xs = 0, np = 0, q = lane;
@@ -471,14 +534,19 @@ descriptorKernel(const __grid_constant__ EngineParams P, const SiftKeypoint* __r
         }
         __syncwarp();
         // reduce lane-private copies: lane owns bins lane, lane+32, lane+64, lane+96
+        // (8 x LDS.128 per bin; the start chunk is rotated by the lane so that a quarter-warp's eight
+        // 16-byte reads cover all 32 banks)
         float f[4];
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            const int bb = q * 32 + lane;
-            float s = 0.0f;
-#pragma unroll 8
-            for (int l = 0; l < kDescCopies; l++) s += hist[bb * kDescCopies + ((l + lane) & (kDescCopies - 1))];
-            f[q] = s;
+            const float4* row = reinterpret_cast<const float4*>(hist + (q * 32 + lane) * kDescCopies);
+            float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+#pragma unroll
+            for (int l = 0; l < kDescCopies / 4; l++) {
+                const float4 v = row[(l + lane) & (kDescCopies / 4 - 1)];
+                s0 += v.x; s1 += v.y; s2 += v.z; s3 += v.w;
+            }
+            f[q] = (s0 + s1) + (s2 + s3);
         }
         // normalize → clip 0.2 → normalize → quantize (SIFTDescriptor.metal:15-50, 227-230)
 #pragma unroll
@@ -542,17 +610,27 @@ cudaError_t launchDescribe(const EngineParams& P, const SiftKeypoint* kps, const
     // to kernels of another context running beside this one (two contexts per device, frames alternating)
     static const int ctasEnv = getenv("SIFTCUDA_DESC_CTAS") ? atoi(getenv("SIFTCUDA_DESC_CTAS")) : 0;
     const int ctasPerSm = ctasEnv > 0 ? std::min(ctasEnv, 2) : (228 * 1024) / (smemBytes + 1024);
-    auto kernel = descriptorKernel<3>;
-    static std::atomic<unsigned long long> configured{0};   // per-device bit, as in launchBlurCfg
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!((configured.load(std::memory_order_acquire) >> (dev & 63)) & 1ull)) {
-        SIFT_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes));
-        configured.fetch_or(1ull << (dev & 63), std::memory_order_release);
+    // walk variant: units of 1/PARTS of a window row (default) or the flattened span walk (0)
+    static const int parts = getenv("SIFTCUDA_DESC_PARTS") ? atoi(getenv("SIFTCUDA_DESC_PARTS")) : kDescDefaultParts;
+    auto launch = [&](auto kernel, int slot) -> cudaError_t {
+        static std::atomic<unsigned long long> configured[5];   // per-device bit per variant, as in launchBlurCfg
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!((configured[slot].load(std::memory_order_acquire) >> (dev & 63)) & 1ull)) {
+            SIFT_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes));
+            configured[slot].fetch_or(1ull << (dev & 63), std::memory_order_release);
+        }
+        return pdlLaunch(kernel, dim3(smCount * ctasPerSm), dim3(kDescWarps * 32), (size_t)smemBytes, st, true, P, kps,
+                         kpSeg, segKpStart, counters, (const int*)oriOffset, (const float*)oriTmp,
+                         (const int*)descKp, cols, hostCols, capDescriptors);
+    };
+    switch (parts) {
+        case 0: return launch(descriptorKernel<3, 0>, 0);
+        case 2: return launch(descriptorKernel<3, 2>, 2);
+        case 3: return launch(descriptorKernel<3, 3>, 3);
+        case 8: return launch(descriptorKernel<3, 8>, 1);
+        default: return launch(descriptorKernel<3, 4>, 4);
     }
-    return pdlLaunch(kernel, dim3(smCount * ctasPerSm), dim3(kDescWarps * 32), (size_t)smemBytes, st, true, P, kps,
-                     kpSeg, segKpStart, counters, (const int*)oriOffset, (const float*)oriTmp,
-                     (const int*)descKp, cols, hostCols, capDescriptors);
 }
 
 // ------------------------------------------------------------------------------------------

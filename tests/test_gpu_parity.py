@@ -437,3 +437,39 @@ def test_tuning_switches_do_not_change_results(switch):
     assert int(a["c"]) == int(b["c"])
     for key in ("k", "d", "kc", "dc"):
         assert np.array_equal(a[key], b[key]), key
+
+
+@pytest.mark.parametrize("parts", ["0", "3"])
+def test_descriptor_walk_variants_stay_within_tolerance(parts):
+    """SIFTCUDA_DESC_PARTS selects how a warp walks a descriptor window (0: flattened spans, n:
+    units of 1/n of a window row; 4 ships). The walks add the same samples in a different order,
+    so keypoints / orientations are identical and features agree within the ±1 of the parity bar —
+    each variant is also within ±1 of the oracle."""
+    import os
+    import subprocess
+    import sys
+
+    from siftmetal_b200.synth import pink_noise_bgra
+
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, '.');"
+        "from siftmetal_b200 import Engine; from siftmetal_b200.synth import pink_noise_bgra;"
+        "img = pink_noise_bgra(640, 480, 9); e = Engine(640, 480); r = e.detect_and_describe([img]);"
+        "np.savez(sys.argv[1], k=r.keypoints, d=r.descriptors)"
+    )
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = f"/tmp/sift_parts_{parts}.npz"
+    subprocess.run([sys.executable, "-c", code, path], check=True, env={**os.environ, "SIFTCUDA_DESC_PARTS": parts}, cwd=root)
+    v = np.load(path)
+    eng, ora = _engine(640, 480), _oracle(640, 480)
+    img = pink_noise_bgra(640, 480, 9)
+    res = eng.detect_and_describe([img])
+    assert np.array_equal(v["k"], res.keypoints)
+    assert np.array_equal(v["d"]["keypoint"], res.descriptors["keypoint"])
+    assert np.array_equal(v["d"]["theta"], res.descriptors["theta"])
+    df = np.abs(v["d"]["features"].astype(np.int16) - res.descriptors["features"].astype(np.int16))
+    assert df.max(initial=0) <= FEAT_TOL
+    ora.detect(img)
+    odesc, _ = ora.describe()
+    assert np.abs(v["d"]["features"].astype(np.int16) - odesc["features"].astype(np.int16)).max(initial=0) <= FEAT_TOL
+    eng.close()
