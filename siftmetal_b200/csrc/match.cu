@@ -12,14 +12,14 @@
 // keeping best (strict <), its first index and `second` = the best before the last improvement
 // (SIFTDescriptor.swift:339-343 — not the true second smallest).
 //
-// One persistent CTA per SM, warp-specialised:
-//   warp 0      TMA producer: A tile (128 rows x 128 B) per work item, B tiles (256 rows x 128 B)
-//               through a 4-stage ring, SWIZZLE_128B tensor maps, mbarrier complete_tx
-//   warp 1      MMA issuer: one elected lane issues 4 x tcgen05.mma (M 128, N 256, K 32) per B
-//               tile into one of two TMEM accumulator stages (2 x 256 columns = all of TMEM),
-//               tcgen05.commit frees the smem stage and publishes the accumulator
-//   warp 2      TMEM allocator
-//   warps 4..7  epilogue: tcgen05.ld 32 lanes x 32 columns at a time, v = ‖b‖² − 2 a·b (‖a‖² is
+// Two persistent CTAs per SM, warp-specialised:
+//   warp 0      TMEM allocation; TMA producer: A tile (128 rows x 128 B) per work item, B tiles (128 rows x 128 B)
+//               through a 3-stage ring, SWIZZLE_128B tensor maps, mbarrier complete_tx
+//   warp 1      MMA issuer: one elected lane issues 4 x tcgen05.mma (M 128, N 128, K 32) per B
+//               tile into one of two TMEM accumulator stages (2 x 128 columns; two CTAs per SM
+//               share the 512 TMEM columns), tcgen05.commit frees the smem stage and publishes
+//               the accumulator
+//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns at a time, v = ‖b‖² − 2 a·b (‖a‖² is
 //               constant per row and added at the end), min over groups of 8 columns and the
 //               sequential update only when some lane's group minimum improves its best
 // Work item = (block of 128 source rows, contiguous segment of target tiles); segments of one
@@ -36,11 +36,19 @@ namespace sift {
 namespace {
 
 constexpr int kM = 128;          // source rows per work item (TMEM lanes)
-constexpr int kN = 256;          // target rows per MMA tile (TMEM columns per accumulator stage)
+constexpr int kN = 128;          // target rows per MMA tile (TMEM columns per accumulator stage)
 constexpr int kK = 128;          // feature bytes per row = one swizzle row
-constexpr int kStages = 4;       // B tiles in flight
-constexpr int kAccStages = 2;
-constexpr int kThreads = 256;    // 8 warps
+#ifndef SIFT_MATCH_CTAS
+#define SIFT_MATCH_CTAS 4
+#endif
+// The epilogue (a compare-and-select scan per element on the CUDA cores) outweighs the MMA, and a
+// CTA has one epilogue warp per scheduler: several CTAs per SM put that many epilogue warps on
+// every scheduler to cover each other's latencies. Four CTAs: 6 warps (<= 85 registers), one
+// accumulator stage of 128 TMEM columns and two B stages (48 KB of shared memory) each.
+constexpr int kCtasPerSm = SIFT_MATCH_CTAS;
+constexpr int kStages = kCtasPerSm >= 4 ? 2 : 3;      // B tiles in flight
+constexpr int kAccStages = kCtasPerSm >= 3 ? 1 : 2;   // kCtasPerSm * kAccStages * kN <= 512 TMEM columns
+constexpr int kThreads = 192;    // warp 0 TMA + TMEM allocation, warp 1 MMA, warps 2..5 epilogue
 constexpr int kSentinel = 0x3fffffff;   // "no distance yet"; also the padded target norm
 
 constexpr uint32_t kABytes = kM * kK;
@@ -101,7 +109,7 @@ __device__ __forceinline__ void scanOne(int v, int j, int& best, int& index, int
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
 matchKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
             const MatchParams p) {
     extern __shared__ uint8_t smemRaw[];
@@ -125,7 +133,7 @@ matchKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         mbarInit(emptyA, 1);
         for (int s = 0; s < kAccStages; s++) { mbarInit(&tmemFull[s], 1); mbarInit(&tmemEmpty[s], 4); }
         mbarInitFence();
-    } else if (warp == 2) {
+    } else if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smemAddr(tmemBaseSlot)),
                      "r"((uint32_t)(kAccStages * kN)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -178,8 +186,8 @@ matchKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                 ummaCommit(emptyA);
             }
         }
-    } else if (warp >= 4) {
-        const int q = warp & 3;                        // TMEM lane quarter this warp may read
+    } else if (warp >= 2) {
+        const int q = warp & 3;                        // TMEM lane quarter this warp may read (warps 2..5: 2, 3, 0, 1)
         const uint32_t laneBase = (uint32_t)(q * 32) << 16;
         uint32_t it = 0;
         for (int item = blockIdx.x; item < nItems; item += gridDim.x) {
@@ -232,7 +240,7 @@ matchKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
 
     tcFenceBefore();
     __syncthreads();
-    if (warp == 2) {
+    if (warp == 0) {
         tcFenceAfter();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBase),
                      "r"((uint32_t)(kAccStages * kN)) : "memory");
@@ -308,7 +316,7 @@ cudaError_t featureMap(CUtensorMap* map, const uint8_t* base, int rows, int boxR
 
 size_t matchScratchInts(int nSource, int nTarget, int smCount) {
     const int nRowBlocks = (nSource + kM - 1) / kM, nColTiles = (nTarget + kN - 1) / kN;
-    const int nSegs = std::max(1, std::min(nColTiles, (2 * smCount + nRowBlocks - 1) / std::max(nRowBlocks, 1)));
+    const int nSegs = std::max(1, std::min(nColTiles, (2 * kCtasPerSm * smCount + nRowBlocks - 1) / std::max(nRowBlocks, 1)));
     return (size_t)nRowBlocks * kM /* normA */ + (size_t)nColTiles * kN /* normB */ +
            3 * (size_t)nSegs * nRowBlocks * kM;
 }
@@ -325,7 +333,7 @@ cudaError_t launchMatch(const uint8_t* source, int nSource, const uint8_t* targe
     p.nColTiles = (nTarget + kN - 1) / kN;
     // enough (row block, segment) items to fill the SMs about twice; one segment when the source
     // side alone does
-    p.nSegs = std::max(1, std::min(p.nColTiles, (2 * smCount + p.nRowBlocks - 1) / p.nRowBlocks));
+    p.nSegs = std::max(1, std::min(p.nColTiles, (2 * kCtasPerSm * smCount + p.nRowBlocks - 1) / p.nRowBlocks));
     p.tilesPerSeg = (p.nColTiles + p.nSegs - 1) / p.nSegs;
     p.nSegs = (p.nColTiles + p.tilesPerSeg - 1) / p.tilesPerSeg;
     int* normA = scratch;
@@ -350,7 +358,7 @@ cudaError_t launchMatch(const uint8_t* source, int nSource, const uint8_t* targe
         configured.fetch_or(1ull << (dev & 63), std::memory_order_release);
     }
     const int nItems = p.nRowBlocks * p.nSegs;
-    matchKernel<<<std::min(nItems, smCount), kThreads, kSmemBytes, st>>>(mapA, mapB, p);
+    matchKernel<<<std::min(nItems, kCtasPerSm * smCount), kThreads, kSmemBytes, st>>>(mapA, mapB, p);
     SIFT_CUDA_TRY(cudaGetLastError());
     matchFinishKernel<<<(nSource + 255) / 256, 256, 0, st>>>(p, normA, absThr, relThr, rows);
     return cudaGetLastError();
