@@ -10,20 +10,21 @@ orientation → descriptor) over one batch of synthetic 1/f-noise frames (SURVEY
 Default workload = BASELINE.json configs[1]: a single 1920×1080 frame per step per GPU.
 
   value      frames/s with the input already resident in HBM: device time between two CUDA events the
-             library records on its own stream around each call's work (one CUDA-graph launch),
-             summed over the K steps, L2 flushed between steps; max over ranks
+             library records on its own stream around each call's work, summed over the K steps, L2
+             flushed between steps; max over ranks
   e2e        frames/s through the public pipelined C-ABI calls (sift_submit / sift_wait, two calls
              in flight) with HOST (pinned) frames: every step's H2D of its frames and the arrival of
              its keypoint + descriptor columns in host memory are inside the wall-clock timed region
              (the kernels store the result columns straight into pinned memory; the upload of step
              i + 1 crosses PCIe under the kernels of step i). For a sharded workload on N > 1 GPUs
-             the host gather (every rank's result columns visible to rank 0 in frame order through
-             shared memory) is inside the region too. `sync_call` is the same through the
+             the host gather (every rank's result columns visible to rank 0 in frame order: the
+             slots are bound to shared-memory segments, one barrier per call) is inside the region too. `sync_call` is the same through the
              synchronous sift_detect_and_describe_batch (no overlap between calls).
   roofline   the dominant streaming kernel (octave-0 Gaussian blur + DoG, 5 scales per step):
              algorithmic bytes (12 B per octave-0 pixel per scale: read G[s], write G[s+1], write
-             DoG[s]) ÷ its mean time per scale from CUDA events over a second, launch-by-launch
-             region of the same steps (per-stage events cannot be recorded inside a graph replay)
+             DoG[s]) ÷ its mean time per scale from CUDA events over a second region of the same
+             steps with per-stage timing switched on (it costs ~20 event records per call, so the
+             timed region runs without it)
   cpu_baseline   the C++ oracle (a port of the reference's kernels + host stages; the Swift/Metal
              reference cannot run on Linux) on the host cores, bounded sample
 
@@ -469,8 +470,8 @@ def main():
             },
             "wall_ms_per_step": 1000 * wall_s_max / K,
             "stage_ms_per_step": {k: float(v) / diag_steps for k, v in zip(STAGES, diag["stage"])},
-            "stage_timing_note": f"launch-by-launch region with per-stage events, {diag_steps} steps, "
-                                 f"{diag_ms / diag_steps:.4f} ms per step (graph replay: {dev_ms_max / K:.4f})",
+            "stage_timing_note": f"second region with per-stage events, {diag_steps} steps, "
+                                 f"{diag_ms / diag_steps:.4f} ms per step (timed region: {dev_ms_max / K:.4f})",
             "frame_roofline": {
                 "model_B_GBps": frame_gbps,
                 "model_B_plus_grad_GBps": frame_gbps * model_bg_bytes / model_b_bytes,
