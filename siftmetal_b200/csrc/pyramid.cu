@@ -371,15 +371,28 @@ blurKernel(const BlurArgs a, const __grid_constant__ Taps taps, const __grid_con
                 v[4 * k + 0] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
             }
             float acc[C::XSEG];
-#pragma unroll
-            for (int k = 0; k < C::XSEG; k++) acc[k] = 0.0f;
             if (!(a.debugMode & 1)) {
+                // Packed FFMA2 on output pairs (2p, 2p + 1): tap i of the pair reads the input pair
+                // starting at m = 2p + (RP - R) + i. Walking m upwards, every input pair is formed
+                // once (free when m is even: the halves sit in an aligned register pair of the
+                // LDS.128; two moves when m is odd), feeds the up to four output pairs that need it
+                // and dies; each output still accumulates its taps in ascending order, and a
+                // packed FMA is two independent IEEE FMAs — bit-identical to the scalar chain.
+                constexpr int OFF = RP - R;
+                f32x2 acc2[C::XSEG / 2];
 #pragma unroll
-                for (int i = 0; i < NTAPS; i++) {
-                    const float wi = taps.w[i];
+                for (int p = 0; p < C::XSEG / 2; p++) acc2[p] = pack2(0.0f, 0.0f);
 #pragma unroll
-                    for (int k = 0; k < C::XSEG; k++) acc[k] = fmaf(wi, v[k + (RP - R) + i], acc[k]);
+                for (int m = OFF; m < OFF + NTAPS + C::XSEG - 2; m++) {
+                    const f32x2 pm = pack2(v[m], v[m + 1]);
+#pragma unroll
+                    for (int p = 0; p < C::XSEG / 2; p++) {
+                        const int i = m - OFF - 2 * p;
+                        if (i >= 0 && i < NTAPS) acc2[p] = fma2(pack2(taps.w[i], taps.w[i]), pm, acc2[p]);
+                    }
                 }
+#pragma unroll
+                for (int p = 0; p < C::XSEG / 2; p++) unpack2(acc2[p], acc[2 * p], acc[2 * p + 1]);
             } else {
 #pragma unroll
                 for (int k = 0; k < C::XSEG; k++) acc[k] = v[k + RP];
