@@ -20,7 +20,7 @@ idx = [i for i, n in enumerate(names) if "grayKernel" in n[0] or "grayUpsample2x
 step = names[idx[1]:idx[2]] if len(idx) > 2 else names[idx[-1]:]
 agg = collections.OrderedDict()
 for n, t in step:
-    if n.startswith("at::") or "at::native" in n:
+    if "at::" in n:
         continue   # torch's L2-flush fill between steps: not part of the device-timed region
     nm = re.sub(r"\(.*", "", n).replace("void ", "").replace("sift::", "")
     agg.setdefault(nm, []).append(t / 1000)
