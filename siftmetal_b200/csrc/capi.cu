@@ -106,6 +106,8 @@ struct SiftContext {
     int ntaps[kGaussians - 1]{};
     BlurTmaSet seedTma{};              // tensor maps of the upsampled plane (seed blur input)
     BlurTmaSet octTma[kOctaves]{};     // ... and of every octave's Gaussian stack
+    CUtensorMap dogTma[kOctaves]{};    // DoG stacks (extrema mask kernel of large planes)
+    bool dogTmaValid[kOctaves]{};
 
     int B = 1;       // max_batch
     int nSegs = 0;   // B * 7
@@ -536,6 +538,10 @@ int sift_create(const SiftConfig* cfg, int device, SiftContext** out) {
         for (int o = 0; o < kOctaves; o++) {
             const OctaveDev& q = c->P.oct[o];
             if (q.w >= 1 && q.h >= 1) A(makeBlurTmaSet(&c->octTma[o], q.G, q.pitch, q.h, (int)B * kGaussians, q.plane));
+            if (q.w >= 512 && q.h >= 128 && e == cudaSuccess) {
+                A(makeExtremaTmaMap(&c->dogTma[o], q.D, q.pitch, q.h, (int)B * kDogs, q.plane));
+                c->dogTmaValid[o] = (e == cudaSuccess);
+            }
         }
     }
     if (e == cudaSuccess) A(cudaMemset(c->dMask, 0, maskWords * sizeof(uint32_t)));
@@ -826,7 +832,7 @@ int enqueuePipeline(SiftContext* c, const RunArgs& r, bool T) {
             if (!(dbgSkip & 1)) CTX_TRY(c, launchGradient(q, F, so, 0, 0, prio));
             c->launches++;
             if (q.w >= 3 && q.h >= 3 && !(dbgSkip & 2)) {
-                CTX_TRY(c, launchExtremaMask(c->P, o, c->dMask, F, so, 0, 0, prio));
+                CTX_TRY(c, launchExtremaMask(c->P, o, c->dMask, F, so, 0, 0, prio, c->dogTmaValid[o] ? &c->dogTma[o] : nullptr));
                 c->launches++;
             }
             if (o > 0) CTX_TRY(c, cudaEventRecord(c->evOctDone[o], so));

@@ -181,7 +181,9 @@ cudaError_t launchGradient(const OctaveDev& o, int frames, cudaStream_t st, int 
 
 // detect.cu
 cudaError_t launchExtremaMask(const EngineParams& P, int octave, uint32_t* mask, int frames,
-                              cudaStream_t st, int yBegin = 0, int yEnd = 0, int priority = kNoPriority);
+                              cudaStream_t st, int yBegin = 0, int yEnd = 0, int priority = kNoPriority,
+                              const CUtensorMap* dogMap = nullptr);
+cudaError_t makeExtremaTmaMap(CUtensorMap* map, const float* base, int pitch, int h, int nz, size_t planeFloats);
 // mask blocks [blockBegin, blockBegin + nBlocks) → ordered candidates; segStart[nSegs + 1] receives
 // the per-(frame, octave) list offsets
 cudaError_t launchCandidateCompaction(const EngineParams& P, const uint32_t* mask,

@@ -8,10 +8,12 @@
 //   SIFTInterpolate.metal:17-300 siftInterpolate and helpers, Common.hpp:34-47 invert,
 //   SIFTOctave.interpolateKeypoints (SIFTOctave.swift:205-288)                      → refineKernel
 #include <algorithm>
+#include <atomic>
 
 #include "common.cuh"
 #include "dev_math.cuh"
 #include "scan.cuh"
+#include "tma.cuh"
 
 namespace sift {
 
@@ -146,6 +148,113 @@ extremaMaskKernel(const OctaveDev o, float softThreshold, uint32_t* __restrict__
     }
 }
 
+// Large planes: the same row march fed by TMA. A CTA owns 7 mask words (224 columns) x a strip of
+// rows; a producer warp streams blocks of 3 rows x 5 slices x (224 + 2 x 4 halo) columns into a
+// shared-memory ring with cp.async.bulk.tensor.3d (one copy per block, mbarrier full / empty per
+// ring slot), the 7 consumer warps read (left, centre, right) of their pixel from the tile and run
+// the window logic above. The 30 loads a lane keeps in flight in the kernel above become one TMA
+// issue by one thread several blocks ahead, and the loads the window logic waits on are
+// shared-memory reads. TMA's zero fill outside the plane is harmless here: border pixels are never
+// candidates, and every neighbour of a candidate lies inside the plane.
+constexpr int kExtTmaWarps = 7;                       // consumer warps = mask words per CTA
+constexpr int kExtTmaCols = kExtTmaWarps * 32 + 8;    // box width: 4 columns of halo on each side
+constexpr int kExtTmaRows = 3;                        // rows per block = window rotation period
+constexpr int kExtTmaRing = 5;                        // 70 KB per CTA: three CTAs (21 consumer warps) per SM
+constexpr int kExtTmaBlockFloats = (kDogs * kExtTmaRows * kExtTmaCols + 31) / 32 * 32;   // 128-byte multiple
+constexpr int kExtTmaSmemBytes = kExtTmaRing * kExtTmaBlockFloats * 4 + 2 * kExtTmaRing * 8;
+
+__global__ void __launch_bounds__((kExtTmaWarps + 1) * 32, 3)
+extremaMaskTmaKernel(const __grid_constant__ CUtensorMap map, const OctaveDev o, float softThreshold,
+                     uint32_t* __restrict__ mask, int blocksPerFrame, int rowsPerCta, int yBegin, int yEnd) {
+    extern __shared__ __align__(128) float ring[];
+    uint64_t* const full = reinterpret_cast<uint64_t*>(ring + kExtTmaRing * kExtTmaBlockFloats);
+    uint64_t* const empty = full + kExtTmaRing;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int f = blockIdx.z;
+    const int x0 = blockIdx.x * (kExtTmaWarps * 32);
+    const int yA = yBegin + blockIdx.y * rowsPerCta;           // first output row of this strip
+    const int yB = min(yA + rowsPerCta, yEnd);                 // one past its last output row
+    const int y0 = yA - 1;                                     // first input row
+    const int nRowsIn = yB - yA + 2;
+    const int nBlocks = (nRowsIn + kExtTmaRows - 1) / kExtTmaRows;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < kExtTmaRing; k++) {
+            mbarInit(&full[k], 1);
+            mbarInit(&empty[k], kExtTmaWarps);
+        }
+        mbarInitFence();
+    }
+    __syncthreads();
+    if (wid == kExtTmaWarps) {
+        // ---- producer ---------------------------------------------------------------------------
+        if (lane == 0) {
+            for (int j = 0; j < nBlocks; j++) {
+                const int slot = j % kExtTmaRing;
+                if (j >= kExtTmaRing) mbarWait(&empty[slot], ((j / kExtTmaRing) & 1) ^ 1);
+                mbarExpectTx(&full[slot], (uint32_t)(kDogs * kExtTmaRows * kExtTmaCols * 4));
+                tmaLoad3d(&map, &full[slot], ring + slot * kExtTmaBlockFloats, x0 - 4, y0 + j * kExtTmaRows, f * kDogs);
+            }
+        }
+        return;
+    }
+    // ---- consumers --------------------------------------------------------------------------------
+    const int xw = blockIdx.x * kExtTmaWarps + wid;
+    const bool store = xw < o.maskRowWords;
+    const int x = x0 + wid * 32 + lane;
+    const bool xInside = (x >= 1) && (x <= o.w - 2);
+    const int col = 4 + wid * 32 + lane;
+    uint32_t* __restrict__ m = mask + ((size_t)f * blocksPerFrame + o.maskBlockStart) * (size_t)kScanChunk;
+    // running mask addresses of the three scales (first output row yA), one word per row
+    uint32_t* mp[kScales];
+#pragma unroll
+    for (int sc = 0; sc < kScales; sc++) mp[sc] = m + ((size_t)sc * o.h + yA) * o.maskRowWords + min(xw, o.maskRowWords - 1);
+    RowPart win[kDogs][3];
+    for (int j = 0; j < nBlocks; j++) {
+        const int slot = j % kExtTmaRing;
+        mbarWait(&full[slot], (j / kExtTmaRing) & 1);
+        const float* blk = ring + slot * kExtTmaBlockFloats + col;
+#pragma unroll
+        for (int k = 0; k < kExtTmaRows; k++) {
+            // input row y0 + 3 j + k goes to window slot k; the output row is the one before it
+            const int prev = (k + 1) % 3, cur = (k + 2) % 3, next = k;
+#pragma unroll
+            for (int t = 0; t < kDogs; t++) {
+                const float* p = blk + (t * kExtTmaRows + k) * kExtTmaCols;
+                const float c = p[0], l = p[-1], r = p[1];
+                RowPart q;
+                q.c = c;
+                q.lrn = fminf(l, r);
+                q.lrx = fmaxf(l, r);
+                q.crn = fminf(c, r);
+                q.crx = fmaxf(c, r);
+                q.h3n = fminf(l, q.crn);
+                q.h3x = fmaxf(l, q.crx);
+                win[t][next] = q;
+            }
+            const int y = y0 + j * kExtTmaRows + k - 1;
+            if ((j > 0 || k == 2) && y < yB) {   // warp-uniform
+#pragma unroll
+                for (int s = 1; s <= kScales; s++) {
+                    const float v = win[s][cur].c;
+                    float mn = fminf(fminf(win[s][prev].h3n, win[s][next].h3n), win[s][cur].lrn);
+                    float mx = fmaxf(fmaxf(win[s][prev].h3x, win[s][next].h3x), win[s][cur].lrx);
+                    mn = fminf(mn, fminf(fminf(win[s + 1][prev].h3n, win[s + 1][cur].h3n), win[s + 1][next].h3n));
+                    mx = fmaxf(mx, fmaxf(fmaxf(win[s + 1][prev].h3x, win[s + 1][cur].h3x), win[s + 1][next].h3x));
+                    mn = fminf(mn, fminf(fminf(win[s - 1][prev].crn, win[s - 1][cur].h3n), win[s - 1][next].h3n));
+                    mx = fmaxf(mx, fmaxf(fmaxf(win[s - 1][prev].crx, win[s - 1][cur].h3x), win[s - 1][next].h3x));
+                    const bool cand = xInside && !(fabsf(v) <= softThreshold) && ((v < mn) || (v > mx));
+                    const uint32_t word = __ballot_sync(0xffffffffu, cand);
+                    if (lane == 0 && store) *mp[s - 1] = word;
+                    mp[s - 1] += o.maskRowWords;
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbarArrive(&empty[slot]);
+    }
+}
+
 // Small planes (deep octaves): one thread per pixel, every load independent. The marching
 // kernel above serialises >= 8 dependent row steps per warp, which is pure latency on a plane of a
 // few thousand pixels at the end of the octave chain; this form finishes in one memory round trip.
@@ -196,8 +305,22 @@ extremaMaskSmallKernel(const OctaveDev o, float softThreshold, uint32_t* __restr
 
 // Mask rows [yBegin, yEnd) ∩ [1, h - 1) of one octave (0, 0 = all rows): a row band of octave 0
 // gets its mask as soon as that band's blur chain is done.
+// Tensor map of one octave's DoG stack [nz][h][pitch] for extremaMaskTmaKernel.
+cudaError_t makeExtremaTmaMap(CUtensorMap* map, const float* base, int pitch, int h, int nz, size_t planeFloats) {
+    auto enc = tensorMapEncoder();
+    if (!enc) return cudaErrorNotSupported;
+    const cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)h, (cuuint64_t)nz};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch * 4, (cuuint64_t)planeFloats * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)kExtTmaCols, (cuuint32_t)kExtTmaRows, (cuuint32_t)kDogs};
+    const cuuint32_t elem[3] = {1, 1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, elem,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
 cudaError_t launchExtremaMask(const EngineParams& P, int octave, uint32_t* mask, int frames,
-                              cudaStream_t st, int yBegin, int yEnd, int priority) {
+                              cudaStream_t st, int yBegin, int yEnd, int priority, const CUtensorMap* dogMap) {
     const OctaveDev& o = P.oct[octave];
     if (o.w < 3 || o.h < 3) return cudaSuccess;
     const bool all = yEnd <= 0;
@@ -207,6 +330,38 @@ cudaError_t launchExtremaMask(const EngineParams& P, int octave, uint32_t* mask,
         dim3 grid((o.maskRowWords * 32 + 255) / 256, o.h, frames);
         return launchKernel(extremaMaskSmallKernel, grid, dim3(256), 0, st, false, priority, o, P.dogThreshold * 0.8f,
                             mask, P.blocksPerFrame);
+    }
+    static const bool tmaEnabled = !(getenv("SIFTCUDA_EXTREMA_TMA") && atoi(getenv("SIFTCUDA_EXTREMA_TMA")) == 0);   // tuning switch
+    // (measured: 58 against 70 us on the 3840 x 2160 plane, 2 - 3 % of the step on the batch and 8K
+    // workloads; on planes that cannot fill the SMs twice over with 24-row strips the register
+    // march below is as fast or faster)
+    const long tmaCtas = (long)((o.maskRowWords + kExtTmaWarps - 1) / kExtTmaWarps) * ((yB - yA + 23) / 24) * frames;
+    if (tmaEnabled && dogMap && all && o.w >= 512 && o.h >= 128 && tmaCtas >= 2L * 3 * 148) {
+        static std::atomic<unsigned long long> configured{0};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!((configured.load(std::memory_order_acquire) >> (dev & 63)) & 1ull)) {
+            SIFT_CUDA_TRY(cudaFuncSetAttribute(extremaMaskTmaKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kExtTmaSmemBytes));
+            configured.fetch_or(1ull << (dev & 63), std::memory_order_release);
+        }
+        const int colGroups = (o.maskRowWords + kExtTmaWarps - 1) / kExtTmaWarps;
+        const int nRows = yB - yA;
+        // strips: whole waves of the 3 x 148 resident CTAs when the plane is large enough, rows per
+        // strip >= 24 so that the two rows of prologue stay below 8 %
+        static const int rowsEnv = getenv("SIFTCUDA_EXTREMA_ROWS") ? atoi(getenv("SIFTCUDA_EXTREMA_ROWS")) : 0;
+        int strips = std::max(1, nRows / 60);
+        const long resident = 3L * 148;
+        const long ctas = (long)colGroups * strips * frames;
+        if (ctas > resident) {
+            const long waves = (ctas + resident - 1) / resident;
+            strips = (int)std::max<long>(1, waves * resident / ((long)colGroups * frames));
+        }
+        int rows = (nRows + strips - 1) / strips;
+        rows = std::max(rows, std::min(nRows, 24));
+        if (rowsEnv > 0) rows = rowsEnv;
+        dim3 grid(colGroups, (nRows + rows - 1) / rows, frames);
+        return launchKernel(extremaMaskTmaKernel, grid, dim3((kExtTmaWarps + 1) * 32), (size_t)kExtTmaSmemBytes, st, false,
+                            priority, *dogMap, o, P.dogThreshold * 0.8f, mask, P.blocksPerFrame, rows, yA, yB);
     }
     // rows per warp (multiple of 3): long strips amortise the 2-row halo on large planes; small
     // planes get short strips so that the serial row loop does not bound the launch
