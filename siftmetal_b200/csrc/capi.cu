@@ -761,10 +761,22 @@ int enqueuePipeline(SiftContext* c, const RunArgs& r, bool T) {
         bool forked[kOctaves] = {};
         static const int dbgMaxOctave = getenv("SIFTCUDA_DEBUG_MAX_OCTAVE") ? atoi(getenv("SIFTCUDA_DEBUG_MAX_OCTAVE")) : kOctaves;
         static const int dbgSkip = getenv("SIFTCUDA_DEBUG_SKIP") ? atoi(getenv("SIFTCUDA_DEBUG_SKIP")) : 0;  // 1 gradient, 2 extrema
+        const int tailStart = tailStartOctave(c->P);
         for (int o = 0; o < kOctaves; o++) {
             const OctaveDev& q = c->P.oct[o];
             if (q.w < 1 || q.h < 1 || o > dbgMaxOctave) continue;
             cudaStream_t so = c->octStream[o];
+            if (o == tailStart) {
+                // this octave and every deeper one: one launch, planes resident in shared memory
+                CTX_TRY(c, cudaStreamWaitEvent(so, c->evSeeded[o - 1], 0));
+                if (o == 1 && c->bandedOctave0)
+                    for (int b = 1; b < c->nBands; b++) CTX_TRY(c, cudaStreamWaitEvent(so, c->evBandSeeded[b], 0));
+                forked[o] = true;
+                CTX_TRY(c, launchTailOctaves(c->P, o, c->taps, c->ntaps, c->dMask, F, so, c->octPriority[o] ? c->octPriority[o] : kNoPriority));
+                c->launches++;
+                CTX_TRY(c, cudaEventRecord(c->evOctDone[o], so));
+                break;
+            }
             if (o > 0) {
                 CTX_TRY(c, cudaStreamWaitEvent(so, c->evSeeded[o - 1], 0));
                 if (o == 1 && c->bandedOctave0)

@@ -176,6 +176,10 @@ struct BlurArgs {
     int priority;               // launch priority (kNoPriority / 0 = the stream's)
 };
 cudaError_t launchBlur(const BlurArgs& a, const Taps& taps, int ntaps, cudaStream_t st);
+// octaves >= tailStartOctave(P) run whole in one launch (one CTA per frame, planes in shared memory)
+int tailStartOctave(const EngineParams& P);
+cudaError_t launchTailOctaves(const EngineParams& P, int oStart, const Taps* taps, const int* ntaps, uint32_t* mask,
+                              int frames, cudaStream_t st, int priority);
 cudaError_t launchGradient(const OctaveDev& o, int frames, cudaStream_t st, int yBegin = 0, int yEnd = 0,
                            int priority = kNoPriority);
 

@@ -648,4 +648,227 @@ cudaError_t launchGradient(const OctaveDev& o, int frames, cudaStream_t st, int 
     return launchKernel(gradientKernel, grid, dim3(256), 0, st, false, priority, o, yBegin, yEnd);
 }
 
+// ------------------------------------------------------------------------------------------
+// Tail octaves. The deepest octaves (a couple of thousand pixels each) are pure latency when run
+// as ~7 dependent launches per octave: at 1080p octaves 3 - 6 end the pyramid stage 47 us after the
+// large octaves are done. Here ONE CTA per frame keeps a whole octave in shared memory — the
+// current and the next Gaussian plane (rows extended by their mirrored halo), the X-pass plane
+// (extended by mirrored halo rows) and a ring of three DoG planes — and walks all five scales of
+// every tail octave in one launch: blur X / Y (the same ascending fma chain; the mirror boundary
+// is materialised once per pass instead of per tap), DoG, the decimated seed of the next octave,
+// the gradient field of slices 1 - 3 and the extrema mask of scales 1 - 3, with block barriers
+// where the launches were. Every plane is still written to global memory (refinement,
+// orientation, descriptor and the debug taps read them). Arithmetic is expression-for-expression
+// that of blurKernel / gradientKernel / extremaMaskSmallKernel: planes and candidates stay
+// bit-identical. One SM has 1 / 148 of the machine, so only planes small enough that their launch
+// chain (not their arithmetic) is what costs are taken: <= kTailMaxPixels.
+struct TailArgs {
+    OctaveDev oct[kOctaves];
+    int oStart;                 // first tail octave; its slice 0 was seeded by the previous octave's blur
+    float softThreshold;
+    uint32_t* mask;
+    int blocksPerFrame;
+    int w0, h0;                 // size of octave oStart (the largest tail plane): sizes the shared-memory planes
+    Taps taps[kGaussians - 1];
+};
+
+constexpr int kTailThreads = 1024;
+constexpr int kTailPad = 16;          // halo columns / rows kept around the planes (>= the largest radius, 13)
+constexpr int kTailMaxPixels = 2600;
+
+template <int NT>
+__device__ __forceinline__ void tailBlurScale(const Taps& taps, float* A, float* B, float* T, float* Ds, int w, int h,
+                                              float* __restrict__ Gout, float* __restrict__ Dout, int pitch) {
+    constexpr int R = NT / 2;
+    const int tid = threadIdx.x;
+    const int wE = w + 2 * kTailPad;
+    // mirrored halo columns of the input rows (Common.hpp:15-22)
+    for (int p = tid; p < h * 2 * R; p += kTailThreads) {
+        const int y = p / (2 * R), k = p - y * (2 * R);
+        const int x = k < R ? k - R : w + (k - R);
+        A[y * wE + kTailPad + x] = A[y * wE + kTailPad + symmetrized(x, w)];
+    }
+    __syncthreads();
+    // X pass into rows kTailPad .. kTailPad + h of T
+    for (int p = tid; p < w * h; p += kTailThreads) {
+        const int y = p / w, x = p - y * w;
+        const float* row = A + y * wE + kTailPad + x - R;
+        float sum = 0.0f;
+#pragma unroll
+        for (int i = 0; i < NT; i++) sum = fmaf(taps.w[i], row[i], sum);
+        T[(y + kTailPad) * w + x] = sum;
+    }
+    __syncthreads();
+    // mirrored halo rows of the X-pass plane
+    for (int p = tid; p < 2 * R * w; p += kTailThreads) {
+        const int k = p / w, x = p - k * w;
+        const int y = k < R ? k - R : h + (k - R);
+        T[(y + kTailPad) * w + x] = T[(symmetrized(y, h) + kTailPad) * w + x];
+    }
+    __syncthreads();
+    // Y pass, DoG, stores
+    for (int p = tid; p < w * h; p += kTailThreads) {
+        const int y = p / w, x = p - y * w;
+        const float* col = T + (y + kTailPad - R) * w + x;
+        float sum = 0.0f;
+#pragma unroll
+        for (int i = 0; i < NT; i++) sum = fmaf(taps.w[i], col[i * w], sum);
+        const float d = sum - A[y * wE + kTailPad + x];
+        B[y * wE + kTailPad + x] = sum;
+        Ds[p] = d;
+        Gout[(size_t)y * pitch + x] = sum;
+        Dout[(size_t)y * pitch + x] = d;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kTailThreads, 1) tailOctavesKernel(const __grid_constant__ TailArgs a) {
+    extern __shared__ __align__(16) float tsm[];
+    const int PA = a.h0 * (a.w0 + 2 * kTailPad);      // Gaussian planes: rows extended by the halo
+    const int PT = (a.h0 + 2 * kTailPad) * a.w0;      // X-pass plane: extended by halo rows
+    const int PD = a.w0 * a.h0;
+    float* A = tsm;                  // Gaussian slice s
+    float* B = tsm + PA;             // Gaussian slice s + 1
+    float* T = tsm + 2 * PA;
+    float* Dr = tsm + 2 * PA + PT;   // DoG ring: slice s at Dr + (s % 3) * PD
+    const int tid = threadIdx.x, lane = tid & 31, f = blockIdx.x;
+    pdlPrologue();
+    for (int oc = a.oStart; oc < kOctaves; oc++) {
+        const OctaveDev& o = a.oct[oc];
+        const int w = o.w, h = o.h, n = w * h;
+        if (w < 1 || h < 1) break;
+        const int wE = w + 2 * kTailPad;
+        float* __restrict__ G = o.G + (size_t)f * kGaussians * o.plane;
+        float* __restrict__ D = o.D + (size_t)f * kDogs * o.plane;
+        // slice 0: seeded by the previous octave's blur (first tail octave) or by this CTA below
+        for (int p = tid; p < n; p += kTailThreads) {
+            const int y = p / w, x = p - y * w;
+            A[y * wE + kTailPad + x] = __ldcg(G + (size_t)y * o.pitch + x);
+        }
+        __syncthreads();
+        for (int s = 0; s < kGaussians - 1; s++) {
+            float* Ds = Dr + (s % 3) * PD;
+            float* Gout = G + (size_t)(s + 1) * o.plane;
+            float* Dout = D + (size_t)s * o.plane;
+            switch (s) {   // the fixed schedule of DifferenceOfGaussians.swift:91-110: 11, 15, 17, 21, 27 taps
+                case 0: tailBlurScale<11>(a.taps[0], A, B, T, Ds, w, h, Gout, Dout, o.pitch); break;
+                case 1: tailBlurScale<15>(a.taps[1], A, B, T, Ds, w, h, Gout, Dout, o.pitch); break;
+                case 2: tailBlurScale<17>(a.taps[2], A, B, T, Ds, w, h, Gout, Dout, o.pitch); break;
+                case 3: tailBlurScale<21>(a.taps[3], A, B, T, Ds, w, h, Gout, Dout, o.pitch); break;
+                default: tailBlurScale<27>(a.taps[4], A, B, T, Ds, w, h, Gout, Dout, o.pitch); break;
+            }
+            // gradient field of Gaussian slice s + 1 in 1..3 (SIFTGradient.metal:15-39; clamp = the
+            // mirror for one pixel, as gradientKernel)
+            if (s + 1 <= kScales) {
+                float2* __restrict__ grad = o.grad + ((size_t)f * kScales + s) * o.plane;
+                for (int p = tid; p < n; p += kTailThreads) {
+                    const int y = p / w, x = p - y * w;
+                    const float* row = B + y * wE + kTailPad;
+                    const float cpx = row[min(x + 1, w - 1)], cmx = row[max(x - 1, 0)];
+                    const float dn = B[min(y + 1, h - 1) * wE + kTailPad + x], up = B[max(y - 1, 0) * wE + kTailPad + x];
+                    const float tx = (cpx - cmx) * 0.5f;
+                    const float ty = (dn - up) * 0.5f;
+                    grad[(size_t)y * o.pitch + x] = make_float2(dm_atan2f(tx, ty), sqrtf((tx * tx) + (ty * ty)));
+                }
+            }
+            // decimated seed of the next octave from slice 3 (NearestNeighborDownScale.metal:15-22):
+            // to global memory (its plane is a result like any other); re-read, L2-hot, when this
+            // octave is done
+            if (s + 1 == kScales && oc + 1 < kOctaves && a.oct[oc + 1].w >= 1 && a.oct[oc + 1].h >= 1) {
+                const OctaveDev& nx = a.oct[oc + 1];
+                float* __restrict__ G0 = nx.G + (size_t)f * kGaussians * nx.plane;
+                for (int p = tid; p < nx.w * nx.h; p += kTailThreads) {
+                    const int y = p / nx.w, x = p - y * nx.w;
+                    G0[(size_t)y * nx.pitch + x] = B[(2 * y) * wE + kTailPad + 2 * x];
+                }
+            }
+            // extrema mask of scale sc = s - 1 in 1..3 from DoG slices sc - 1, sc, sc + 1 = s
+            // (SIFTExtrema.metal:62-110: neighbours 1..25, neighbour 0 = (-1, -1, -1) skipped; the
+            // 0.8 C_DoG pre-threshold of SIFTInterpolate.metal:208 fused in, as extremaMaskSmallKernel)
+            const int sc = s - 1;
+            if (sc >= 1 && sc <= kScales && w >= 3 && h >= 3) {
+                const float* Dm = Dr + ((sc - 1) % 3) * PD;
+                const float* Dc = Dr + (sc % 3) * PD;
+                const float* Dp = Dr + ((sc + 1) % 3) * PD;
+                uint32_t* __restrict__ m = a.mask + ((size_t)f * a.blocksPerFrame + o.maskBlockStart) * (size_t)kScanChunk;
+                const int units = h * o.maskRowWords;   // one warp per (row, mask word)
+                for (int u = tid >> 5; u < units; u += kTailThreads / 32) {
+                    const int y = u / o.maskRowWords, xw = u - y * o.maskRowWords;
+                    const int x = xw * 32 + lane;
+                    bool cand = false;
+                    if (x >= 1 && x <= w - 2 && y >= 1 && y <= h - 2) {
+                        const int c = y * w + x;
+                        const float v = Dc[c];
+                        if (!(fabsf(v) <= a.softThreshold)) {
+                            float mn = +1000.0f, mx = -1000.0f;
+#pragma unroll
+                            for (int ds = -1; ds <= 1; ds++) {
+                                const float* pl = ds < 0 ? Dm : (ds == 0 ? Dc : Dp);
+#pragma unroll
+                                for (int dy = -1; dy <= 1; dy++) {
+#pragma unroll
+                                    for (int dx = -1; dx <= 1; dx++) {
+                                        if (ds == 0 && dy == 0 && dx == 0) continue;       // the centre
+                                        if (ds == -1 && dy == -1 && dx == -1) continue;    // neighbour 0
+                                        const float nv = pl[c + dy * w + dx];
+                                        mn = fminf(mn, nv);
+                                        mx = fmaxf(mx, nv);
+                                    }
+                                }
+                            }
+                            cand = (v < mn) || (v > mx);
+                        }
+                    }
+                    const uint32_t word = __ballot_sync(0xffffffffu, cand);
+                    if (lane == 0) m[((size_t)(sc - 1) * h + y) * o.maskRowWords + xw] = word;
+                }
+            }
+            __syncthreads();
+            float* t = A; A = B; B = t;   // slice s + 1 becomes the input of the next scale
+        }
+        __syncthreads();   // the seed of the next octave (global stores of this CTA) is read back above
+    }
+}
+
+// First octave the tail kernel takes: the largest one of at most kTailMaxPixels pixels, never
+// octave 0; kOctaves = none.
+int tailStartOctave(const EngineParams& P) {
+    static const bool enabled = !(getenv("SIFTCUDA_TAIL") && atoi(getenv("SIFTCUDA_TAIL")) == 0);   // tuning switch
+    if (!enabled) return kOctaves;
+    static const int maxPixels = getenv("SIFTCUDA_TAIL_PIXELS") ? atoi(getenv("SIFTCUDA_TAIL_PIXELS")) : kTailMaxPixels;
+    for (int o = 1; o < kOctaves; o++) {
+        const long w = P.oct[o].w, h = P.oct[o].h;
+        const long floats = 2 * h * (w + 2 * kTailPad) + (h + 2 * kTailPad) * w + 3 * w * h;
+        if (w >= 1 && h >= 1 && w * h <= maxPixels && floats * 4 <= 200 * 1024) return o;
+    }
+    return kOctaves;
+}
+
+cudaError_t launchTailOctaves(const EngineParams& P, int oStart, const Taps* taps, const int* ntaps, uint32_t* mask,
+                              int frames, cudaStream_t st, int priority) {
+    if (oStart >= kOctaves) return cudaSuccess;
+    TailArgs a{};
+    for (int o = 0; o < kOctaves; o++) a.oct[o] = P.oct[o];
+    a.oStart = oStart;
+    a.softThreshold = P.dogThreshold * 0.8f;
+    a.mask = mask;
+    a.blocksPerFrame = P.blocksPerFrame;
+    a.w0 = P.oct[oStart].w;
+    a.h0 = P.oct[oStart].h;
+    for (int s = 0; s < kGaussians - 1; s++) {
+        if (ntaps[s] != (s == 0 ? 11 : s == 1 ? 15 : s == 2 ? 17 : s == 3 ? 21 : 27)) return cudaErrorInvalidValue;
+        a.taps[s] = taps[s];
+    }
+    const int smemBytes = (2 * a.h0 * (a.w0 + 2 * kTailPad) + (a.h0 + 2 * kTailPad) * a.w0 + 3 * a.w0 * a.h0) * (int)sizeof(float);
+    static std::atomic<unsigned long long> configured{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!((configured.load(std::memory_order_acquire) >> (dev & 63)) & 1ull)) {
+        SIFT_CUDA_TRY(cudaFuncSetAttribute(tailOctavesKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        configured.fetch_or(1ull << (dev & 63), std::memory_order_release);
+    }
+    return launchKernel(tailOctavesKernel, dim3((unsigned)frames), dim3(kTailThreads), (size_t)smemBytes, st, false, priority, a);
+}
+
 }  // namespace sift
+
