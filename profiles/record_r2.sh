@@ -7,7 +7,7 @@ python bench.py > $O/bench_1080p.json 2> $O/bench_1080p.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv python bench.py --steps 2 --quick > $O/ncu_launch.log 2>&1
 # full-plane blur launches (row bands off so that one launch = one scale of the whole plane)
 SIFTCUDA_BANDS=1 ncu --set full --clock-control none --import-source on -k regex:blurKernel -s 1 -c 5 -o $O/prof_blur python bench.py --steps 2 --quick > $O/ncu_blur.log 2>&1
-for k in descriptorKernel orientationKernel extremaMaskKernel gradientKernel grayUpsample2xKernel; do
+for k in descriptorKernel orientationKernel extremaMaskTmaKernel tailOctavesKernel gradientKernel grayUpsample2xKernel; do
   ncu --set full --clock-control none --import-source on -k regex:$k -c 1 -o $O/prof_$k python bench.py --steps 2 --quick > $O/ncu_$k.log 2>&1
 done
 ncu --set full --clock-control none --import-source on -k regex:matchKernel -c 1 -o $O/prof_matchKernel python profiles/match_bench.py 20000 > $O/ncu_match.log 2>&1

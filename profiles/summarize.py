@@ -37,8 +37,8 @@ KEYS = [("time µs", "gpu__time_duration.sum"), ("DRAM read MB", "dram__bytes_re
 P("## ncu --set full, per launch\n")
 P("| kernel | " + " | ".join(k for k, _ in KEYS) + " |\n|---|" + "---|" * len(KEYS))
 blur_traffic = []
-for rep in ("prof_grayUpsample2xKernel", "prof_blur", "prof_gradientKernel", "prof_extremaMaskKernel", "prof_orientationKernel",
-            "prof_descriptorKernel", "prof_matchKernel"):
+for rep in ("prof_grayUpsample2xKernel", "prof_blur", "prof_gradientKernel", "prof_extremaMaskTmaKernel", "prof_extremaMaskKernel",
+            "prof_tailOctavesKernel", "prof_orientationKernel", "prof_descriptorKernel", "prof_matchKernel"):
     path = f"{g}/{rep}.ncu-rep"
     if not os.path.exists(path):
         continue
