@@ -167,9 +167,16 @@ def make_frames(w, h, n, first_index=0, gray=False):
     from siftmetal_b200.synth import pink_noise_bgra, pink_noise_gray
 
     gen = pink_noise_gray if gray else pink_noise_bgra
-    uniq = min(n, 8)   # distinct frames; larger batches cycle through them (generation is FFT-bound)
-    base = [gen(w, h, first_index + i) for i in range(uniq)]
-    return [base[i % uniq] for i in range(n)]
+    # 8 distinct frames; global frame g of a batch is frame g % 8 whatever the number of shards,
+    # so a sharded batch has the same content at every N (generation is FFT-bound)
+    base = {}
+    out = []
+    for i in range(n):
+        j = (first_index + i) % 8
+        if j not in base:
+            base[j] = gen(w, h, j)
+        out.append(base[j])
+    return out
 
 
 def load_oracle():
