@@ -49,6 +49,7 @@ struct Slot {
     uint8_t* dInput = nullptr;          // device input arena (max_batch frames)
     bool allocated = false;
     ResultColumns host{};               // pinned host memory, device-addressable (UVA)
+    ResultColumns dev{};                // the slot's result columns in HBM (slot 0: the context's)
     void* hostBlock = nullptr;          // start of the block the columns are carved from
     bool hostBlockExternal = false;     // caller memory (sift_bind_result_memory), not ours to free
     Counters* hCounters = nullptr;      // pinned
@@ -56,6 +57,7 @@ struct Slot {
     cudaEvent_t evUploaded = nullptr, evStart = nullptr, evEnd = nullptr;
     int frames = 0;
     bool pending = false, described = false, hostOut = false, graphReplay = false, staged = false;
+    bool copyOut = false;               // the columns reach host memory by the copy engine at sift_wait
     int launches = 0;
     std::vector<int32_t> kpCounts, descCounts, candCounts;
     int64_t nKp = 0, nDesc = 0;
@@ -66,7 +68,7 @@ struct GraphEntry {
     int slot = 0, frames = 0, pitch = 0;
     const void* input = nullptr;
     int64_t frameStride = 0;
-    bool describe = false, hostOut = false;
+    bool describe = false, hostOut = false, copyOut = false;
     int seen = 0;                       // calls with this key so far (the first one runs eagerly)
     cudaGraphExec_t exec = nullptr;
     int launches = 0;
@@ -82,6 +84,16 @@ struct SiftContext {
     int bytesPerPixel = 4;
     cudaStream_t stream = nullptr;
     cudaStream_t copyStream = nullptr;
+    // Result delivery. Default: the scatter / descriptor kernels store the columns straight into
+    // the slot's host memory (costs a 1080p call 24 µs against leaving them in HBM). Alternative
+    // (SIFTCUDA_RESULT_COPY, tuning): the kernels write the slot's HBM columns and sift_wait moves
+    // exactly the filled part with the copy engine on this stream, under the kernels of the next
+    // submitted call — measured level with the direct stores launch by launch (0.909 ms per call
+    // either way) and 11 µs ahead under graph replay; a copy-out kernel instead of the copy engine
+    // was slower than both (SM stores at PCIe rate back up into the next call's kernels). See
+    // profiles/r2/EXPERIMENTS.md.
+    cudaStream_t downStream = nullptr;
+    int resultCopy = 0;            // SIFTCUDA_RESULT_COPY (tuning): 0 never, 1 pipelined calls, 2 every host call
     // octave o >= 1 runs its blur chain + gradient + extrema mask on its own stream as soon as
     // octave o-1 has produced Gaussian slice 3 (fork / join around the main stream)
     cudaStream_t octStream[kOctaves]{};
@@ -255,6 +267,13 @@ int ensureSlot(SiftContext* c, int s) {
     cudaError_t e = cudaSuccess;
     auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
     A(devAlloc(c, &S.dInput, (size_t)c->B * frameBytes));
+    if (s == 0) {
+        S.dev = c->dev;
+    } else {
+        char* dblock = nullptr;
+        A(devAlloc(c, &dblock, columnsBytes((size_t)c->capKp, (size_t)c->capDesc)));
+        if (e == cudaSuccess) S.dev = carveColumns(dblock, (size_t)c->capKp, (size_t)c->capDesc);
+    }
     void* block = nullptr;
     A(cudaMallocHost(&block, columnsBytes((size_t)c->capKp, (size_t)c->capDesc)));
     if (e == cudaSuccess) {
@@ -300,6 +319,7 @@ void destroy(SiftContext* c) {
     // drain every stream of the context (an upload may still be in flight on the copy stream)
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copyStream) cudaStreamSynchronize(c->copyStream);
+    if (c->downStream) cudaStreamSynchronize(c->downStream);
     for (int o = 1; o < kOctaves; o++)
         if (c->octStream[o]) cudaStreamSynchronize(c->octStream[o]);
     for (int b = 1; b < SiftContext::kMaxBands; b++)
@@ -333,6 +353,7 @@ void destroy(SiftContext* c) {
     }
     if (c->evBandFork) cudaEventDestroy(c->evBandFork);
     if (c->copyStream) cudaStreamDestroy(c->copyStream);
+    if (c->downStream) cudaStreamDestroy(c->downStream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -563,6 +584,8 @@ int sift_create(const SiftConfig* cfg, int device, SiftContext** out) {
     c->octStream[0] = c->stream;
     A(cudaEventCreateWithFlags(&c->evBandFork, cudaEventDisableTiming));
     A(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
+    A(cudaStreamCreateWithPriority(&c->downStream, cudaStreamNonBlocking, prioHigh));
+    if (const char* rc = getenv("SIFTCUDA_RESULT_COPY")) c->resultCopy = atoi(rc);
     for (int b = 1; b < SiftContext::kMaxBands; b++) {
         A(cudaStreamCreateWithFlags(&c->bandStream[b], cudaStreamNonBlocking));
         A(cudaEventCreateWithFlags(&c->evBandSeeded[b], cudaEventDisableTiming));
@@ -698,8 +721,31 @@ struct RunArgs {
     int frames = 0;
     bool withDescribe = true;
     bool hostOut = false;        // keypoint / descriptor columns go to the slot's pinned arrays
+    bool copyOut = false;        // ... through the slot's HBM columns and the copy engine at sift_wait
     Slot* slot = nullptr;
 };
+
+// Exactly the filled part of the slot's device columns → its host columns (pinned or registered
+// memory), by the copy engine on `st`.
+int enqueueColumnDownload(SiftContext* c, Slot& S, cudaStream_t st) {
+    const size_t nk = (size_t)S.nKp, nd = (size_t)S.nDesc;
+    const ResultColumns &d = S.dev, &h = S.host;
+    if (nk) {
+        CTX_TRY(c, cudaMemcpyAsync(h.kp.absX, d.kp.absX, nk * 4, cudaMemcpyDeviceToHost, st));
+        CTX_TRY(c, cudaMemcpyAsync(h.kp.absY, d.kp.absY, nk * 4, cudaMemcpyDeviceToHost, st));
+        CTX_TRY(c, cudaMemcpyAsync(h.kp.sigma, d.kp.sigma, nk * 4, cudaMemcpyDeviceToHost, st));
+        CTX_TRY(c, cudaMemcpyAsync(h.kp.value, d.kp.value, nk * 4, cudaMemcpyDeviceToHost, st));
+        CTX_TRY(c, cudaMemcpyAsync(h.kp.subScale, d.kp.subScale, nk * 4, cudaMemcpyDeviceToHost, st));
+        CTX_TRY(c, cudaMemcpyAsync(h.kp.scaledXY, d.kp.scaledXY, nk * sizeof(short2), cudaMemcpyDeviceToHost, st));
+        CTX_TRY(c, cudaMemcpyAsync(h.kp.octaveScale, d.kp.octaveScale, nk * sizeof(uchar2), cudaMemcpyDeviceToHost, st));
+    }
+    if (nd) {
+        CTX_TRY(c, cudaMemcpyAsync(h.desc.features, d.desc.features, nd * 128, cudaMemcpyDeviceToHost, st));
+        CTX_TRY(c, cudaMemcpyAsync(h.desc.theta, d.desc.theta, nd * 4, cudaMemcpyDeviceToHost, st));
+        CTX_TRY(c, cudaMemcpyAsync(h.desc.keypoint, d.desc.keypoint, nd * 4, cudaMemcpyDeviceToHost, st));
+    }
+    return SIFT_OK;
+}
 
 // getDescriptors (SIFT.swift:207-238) over the keypoints in c->dKps.
 int enqueueDescribe(SiftContext* c, const RunArgs& r, int nSegs, bool T) {
@@ -707,8 +753,8 @@ int enqueueDescribe(SiftContext* c, const RunArgs& r, int nSegs, bool T) {
     NvtxRange range("getDescriptors(orientations) + getDescriptors(descriptors)");
     const DescriptorColumnsDev none{};
     CTX_TRY(c, launchDescribe(c->P, c->dKps, c->dKpSeg, c->capKp, c->dSegStarts + (c->nSegs + 1), c->dNOri, c->dOriTmp,
-                              c->dOriOffset, c->dDescKp, c->dBlockSums, c->dev.desc,
-                              r.hostOut ? r.slot->host.desc : none, c->capDesc, c->dSegStarts + 2 * (c->nSegs + 1),
+                              c->dOriOffset, c->dDescKp, c->dBlockSums, r.slot->dev.desc,
+                              (r.hostOut && !r.copyOut) ? r.slot->host.desc : none, c->capDesc, c->dSegStarts + 2 * (c->nSegs + 1),
                               nSegs, c->dCounters, c->smCount, st, T ? c->ev[5] : nullptr));
     c->launches += 5;
     if (T) CTX_TRY(c, cudaEventRecord(c->ev[6], st));
@@ -868,7 +914,7 @@ int enqueuePipeline(SiftContext* c, const RunArgs& r, bool T) {
         NvtxRange range("interpolateKeypoints");
         CTX_TRY(c, launchRefine(c->P, c->dCands, c->capCand, c->dKpTmp, c->dFlagWords, c->dBlockSums, c->dKps,
                                 c->dKpSeg, c->capKp, c->dSegStarts, c->dSegStarts + (c->nSegs + 1), nSegs,
-                                c->dCounters, r.hostOut ? r.slot->host.kp : c->dev.kp, st));
+                                c->dCounters, (r.hostOut && !r.copyOut) ? r.slot->host.kp : r.slot->dev.kp, st));
         c->launches += 3;
         if (T) CTX_TRY(c, cudaEventRecord(c->ev[4], st));
     }
@@ -882,7 +928,8 @@ int enqueuePipeline(SiftContext* c, const RunArgs& r, bool T) {
 GraphEntry* findGraph(SiftContext* c, int slot, const RunArgs& r) {
     for (auto& g : c->graphs)
         if (g.slot == slot && g.frames == r.frames && g.input == (const void*)r.input && g.pitch == r.pitch &&
-            g.frameStride == r.frameStride && g.describe == r.withDescribe && g.hostOut == r.hostOut)
+            g.frameStride == r.frameStride && g.describe == r.withDescribe && g.hostOut == r.hostOut &&
+            g.copyOut == r.copyOut)
             return &g;
     if (c->graphs.size() >= 16) {   // evict the least recently used entry
         size_t victim = 0;
@@ -893,7 +940,7 @@ GraphEntry* findGraph(SiftContext* c, int slot, const RunArgs& r) {
     }
     GraphEntry g;
     g.slot = slot; g.frames = r.frames; g.input = r.input; g.pitch = r.pitch; g.frameStride = r.frameStride;
-    g.describe = r.withDescribe; g.hostOut = r.hostOut;
+    g.describe = r.withDescribe; g.hostOut = r.hostOut; g.copyOut = r.copyOut;
     c->graphs.push_back(g);
     return &c->graphs.back();
 }
@@ -910,6 +957,7 @@ int runSlot(SiftContext* c, int slotIndex, RunArgs r) {
     S.described = r.withDescribe;
     S.hostOut = r.hostOut;
     S.graphReplay = false;
+    S.copyOut = r.copyOut;
     CTX_TRY(c, cudaEventRecord(S.evStart, st));
     GraphEntry* g = (c->graphsEnabled && !T) ? findGraph(c, slotIndex, r) : nullptr;
     if (g) {
@@ -967,6 +1015,13 @@ int finishSlot(SiftContext* c, Slot& S) {
     }
     S.nKp = std::min(S.hCounters->nKeypoints, c->capKp);
     S.nDesc = S.described ? std::min(S.hCounters->nDescriptors, c->capDesc) : 0;
+    if (S.copyOut) {
+        // the counts are known now: the copy engine moves the columns while the kernels of the next
+        // submitted call run (a slot's device columns are its own, nothing overwrites them)
+        const int rc = enqueueColumnDownload(c, S, c->downStream);
+        if (rc != SIFT_OK) return rc;
+        CTX_TRY(c, cudaStreamSynchronize(c->downStream));
+    }
     SiftTimings& t = c->timings;
     memset(&t, 0, sizeof t);
     t.kernel_launches = S.launches;
@@ -1053,16 +1108,21 @@ int submitHost(SiftContext* c, const void* const* images, int n, int pitchBytes,
     r = ensureSlot(c, s);
     if (r != SIFT_OK) return r;
     Slot& S = c->slot[s];
-    r = enqueueUpload(c, S, images, n, pitchBytes);
-    if (r != SIFT_OK) return r;
-    CTX_TRY(c, cudaStreamWaitEvent(c->stream, S.evUploaded, 0));
+    // tuning only: 1 = results stay in HBM (nothing delivered), 2 = no upload (stale input)
+    static const int dbgE2E = getenv("SIFTCUDA_DEBUG_E2E") ? atoi(getenv("SIFTCUDA_DEBUG_E2E")) : 0;
+    if (!(dbgE2E & 2)) {
+        r = enqueueUpload(c, S, images, n, pitchBytes);
+        if (r != SIFT_OK) return r;
+        CTX_TRY(c, cudaStreamWaitEvent(c->stream, S.evUploaded, 0));
+    }
     RunArgs a;
     a.input = S.dInput;
     a.pitch = c->cfg.width * c->bytesPerPixel;
     a.frameStride = (int64_t)a.pitch * c->cfg.height;
     a.frames = n;
     a.withDescribe = withDescribe;
-    a.hostOut = true;
+    a.hostOut = !(dbgE2E & 1);
+    a.copyOut = a.hostOut && (c->resultCopy == 2 || (c->resultCopy == 1 && !synchronous));
     r = runSlot(c, s, a);
     if (r != SIFT_OK) return r;
     S.pending = true;
@@ -1169,21 +1229,8 @@ int sift_batch_download(SiftContext* c, SiftBatchResult* out) {
     if (S.staged) {
         // device columns → the slot's pinned columns
         cudaStream_t st = c->stream;
-        const size_t nk = (size_t)S.nKp, nd = (size_t)S.nDesc;
-        if (nk) {
-            CTX_TRY(c, cudaMemcpyAsync(S.host.kp.absX, c->dev.kp.absX, nk * 4, cudaMemcpyDeviceToHost, st));
-            CTX_TRY(c, cudaMemcpyAsync(S.host.kp.absY, c->dev.kp.absY, nk * 4, cudaMemcpyDeviceToHost, st));
-            CTX_TRY(c, cudaMemcpyAsync(S.host.kp.sigma, c->dev.kp.sigma, nk * 4, cudaMemcpyDeviceToHost, st));
-            CTX_TRY(c, cudaMemcpyAsync(S.host.kp.value, c->dev.kp.value, nk * 4, cudaMemcpyDeviceToHost, st));
-            CTX_TRY(c, cudaMemcpyAsync(S.host.kp.subScale, c->dev.kp.subScale, nk * 4, cudaMemcpyDeviceToHost, st));
-            CTX_TRY(c, cudaMemcpyAsync(S.host.kp.scaledXY, c->dev.kp.scaledXY, nk * sizeof(short2), cudaMemcpyDeviceToHost, st));
-            CTX_TRY(c, cudaMemcpyAsync(S.host.kp.octaveScale, c->dev.kp.octaveScale, nk * sizeof(uchar2), cudaMemcpyDeviceToHost, st));
-        }
-        if (nd) {
-            CTX_TRY(c, cudaMemcpyAsync(S.host.desc.features, c->dev.desc.features, nd * 128, cudaMemcpyDeviceToHost, st));
-            CTX_TRY(c, cudaMemcpyAsync(S.host.desc.theta, c->dev.desc.theta, nd * 4, cudaMemcpyDeviceToHost, st));
-            CTX_TRY(c, cudaMemcpyAsync(S.host.desc.keypoint, c->dev.desc.keypoint, nd * 4, cudaMemcpyDeviceToHost, st));
-        }
+        const int rc = enqueueColumnDownload(c, S, st);
+        if (rc != SIFT_OK) return rc;
         CTX_TRY(c, cudaStreamSynchronize(st));
     }
     fillResult(c, S, out);
@@ -1314,6 +1361,7 @@ int sift_describe(SiftContext* c, const SiftKeypoint* kps, const int32_t counts[
     S.frames = 1;
     S.described = true;
     S.hostOut = true;
+    S.copyOut = false;
     S.staged = false;
     S.nDesc = nDesc;
     for (int o = 0; o < kOctaves; o++) S.descCounts[o] = descCounts[o];

@@ -403,12 +403,14 @@ def test_config2_vga256_batch_against_oracle():
 
 
 @pytest.mark.parametrize("switch", ["SIFTCUDA_GRAPH=1", "SIFTCUDA_BANDS=1", "SIFTCUDA_BANDS=3", "SIFTCUDA_PDL=0",
-                                    "SIFTCUDA_BLUR_TMA=0", "SIFTCUDA_EXTREMA_TMA=0", "SIFTCUDA_TAIL=0"])
+                                    "SIFTCUDA_BLUR_TMA=0", "SIFTCUDA_EXTREMA_TMA=0", "SIFTCUDA_TAIL=0",
+                                    "SIFTCUDA_RESULT_COPY=2"])
 def test_tuning_switches_do_not_change_results(switch):
     """Alternative schedules (CUDA-graph replay instead of stream launches; no row bands; three row
     bands; no programmatic dependent launch; cp.async instead of TMA tile loads; the register-march
     extrema kernel instead of the TMA-fed one; the deepest octave launch by launch instead of in the
-    one-CTA tail kernel) must give the same
+    one-CTA tail kernel; result columns through HBM and the copy-out kernel instead of direct
+    stores to host memory) must give the same
     result arrays as the default, call after call (graph: first call eager, second captured, third replayed)."""
     import os
     import subprocess
