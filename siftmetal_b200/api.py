@@ -395,6 +395,12 @@ class Engine:
     def pending(self):
         return int(self.L.sift_pending(self.ctx))
 
+    def device_bytes(self):
+        """Device memory the context holds now (grows when the second pipeline / slot is created)."""
+        info = SiftInfo()
+        self.L.sift_get_info(self.ctx, C.byref(info))
+        return int(info.device_bytes)
+
     def next_slot(self):
         return int(self.L.sift_next_slot(self.ctx))
 

@@ -146,6 +146,16 @@ struct SiftContext {
     ResultColumns dev{};        // device result columns (staged path, device-side matching)
 
     Slot slot[2];
+    // Pipelined calls alternate between two lanes. Small contexts (twinMode) give lane 1 a whole
+    // second pipeline — its own scratch planes, streams and slot, created at the first overlapping
+    // submit — so that the kernels of two consecutive calls run beside each other instead of in
+    // stream order: the descriptor stage of frame i (14 warps per SM) and the launch-bound
+    // compaction chain leave SMs idle that the pyramid of frame i + 1 fills. Large contexts keep
+    // both lanes as slots of the one pipeline (a batch fills the machine by itself, and the
+    // scratch memory is what bounds the batch).
+    SiftContext* twin = nullptr;
+    bool twinMode = false, isTwin = false;
+    SiftContext* lastOwner = nullptr;   // context holding the last completed call's slot (this or twin)
     int head = 0, next = 0, nPending = 0;
     std::vector<std::pair<char*, size_t>> registered;   // caller memory pinned by sift_register_host_memory
     Slot* last = nullptr;       // slot holding the results of the last completed call
@@ -315,6 +325,8 @@ void destroyMatcher(SiftContext* c);
 
 void destroy(SiftContext* c) {
     if (!c) return;
+    if (c->twin) destroy(c->twin);
+    c->twin = nullptr;
     cudaSetDevice(c->device);
     // drain every stream of the context (an upload may still be in flight on the copy stream)
     if (c->stream) cudaStreamSynchronize(c->stream);
@@ -398,7 +410,9 @@ const char* sift_status_string(int status) {
 
 const char* sift_last_error_string(const SiftContext* c) { return c ? c->lastError.c_str() : ""; }
 
-int sift_create(const SiftConfig* cfg, int device, SiftContext** out) {
+}  // extern "C"
+
+static int createContext(const SiftConfig* cfg, int device, SiftContext** out, bool isTwin) {
     if (!cfg || !out) return SIFT_ERR_INVALID_ARGUMENT;
     *out = nullptr;
     if (cfg->width < 8 || cfg->height < 8 || cfg->width > 16384 || cfg->height > 16384 ||
@@ -616,9 +630,40 @@ int sift_create(const SiftConfig* cfg, int device, SiftContext** out) {
         return rs;
     }
     I.device_bytes = c->deviceBytes;
+    c->isTwin = isTwin;
+    // SIFTCUDA_TWIN=0: both lanes in the one pipeline (tuning); SIFTCUDA_TWIN_MB: the size limit
+    static const bool twinEnabled = !(getenv("SIFTCUDA_TWIN") && atoi(getenv("SIFTCUDA_TWIN")) == 0);
+    static const long twinLimitMb = getenv("SIFTCUDA_TWIN_MB") ? atol(getenv("SIFTCUDA_TWIN_MB")) : 6144;
+    c->twinMode = !isTwin && twinEnabled && c->deviceBytes <= (int64_t)twinLimitMb * (1 << 20);
     *out = c;
     return SIFT_OK;
 }
+
+// The second pipeline of a small context (lane 1 of the pipelined calls).
+static int ensureTwin(SiftContext* c) {
+    if (c->twin) return SIFT_OK;
+    SiftContext* t = nullptr;
+    const int r = createContext(&c->cfg, c->device, &t, true);
+    if (r != SIFT_OK) return fail(c, r, "second pipeline (lane 1) could not be created");
+    t->graphsEnabled = c->graphsEnabled;
+    t->stageTiming = c->stageTiming;
+    c->twin = t;
+    c->info.device_bytes = c->deviceBytes + t->deviceBytes;
+    return SIFT_OK;
+}
+struct LaneRef {
+    SiftContext* x;
+    int s;
+};
+// Lane (0 / 1, what the ABI calls a slot) → the pipeline and slot behind it.
+static LaneRef laneOf(SiftContext* c, int lane) {
+    if (c->twinMode && lane == 1) return {c->twin, 0};
+    return {c, lane};
+}
+
+extern "C" {
+
+int sift_create(const SiftConfig* cfg, int device, SiftContext** out) { return createContext(cfg, device, out, false); }
 
 void sift_destroy(SiftContext* c) { destroy(c); }
 
@@ -631,12 +676,14 @@ int sift_get_info(const SiftContext* c, SiftInfo* out) {
 int sift_set_stage_timing(SiftContext* c, int32_t enabled) {
     if (!c) return SIFT_ERR_INVALID_ARGUMENT;
     c->stageTiming = enabled != 0;
+    if (c->twin) c->twin->stageTiming = c->stageTiming;
     return SIFT_OK;
 }
 
 int sift_set_graph_replay(SiftContext* c, int32_t enabled) {
     if (!c) return SIFT_ERR_INVALID_ARGUMENT;
     c->graphsEnabled = enabled != 0;
+    if (c->twin) c->twin->graphsEnabled = c->graphsEnabled;
     return SIFT_OK;
 }
 
@@ -680,7 +727,6 @@ int sift_register_host_memory(SiftContext* c, void* base, int64_t bytes) {
 
 int sift_bind_result_memory(SiftContext* c, int32_t slot, void* base, int64_t bytes) {
     if (!c || slot < 0 || slot > 1 || !base || ((uintptr_t)base & 255)) return SIFT_ERR_INVALID_ARGUMENT;
-    if (c->slot[slot].pending) return fail(c, SIFT_ERR_BUSY, "sift_bind_result_memory: the slot has a call in flight");
     const size_t need = columnsBytes((size_t)c->capKp, (size_t)c->capDesc);
     if (bytes < (int64_t)need)
         return fail(c, SIFT_ERR_INVALID_ARGUMENT, "sift_bind_result_memory: block smaller than sift_result_layout().bytes");
@@ -690,23 +736,33 @@ int sift_bind_result_memory(SiftContext* c, int32_t slot, void* base, int64_t by
     if (!inside)
         return fail(c, SIFT_ERR_INVALID_ARGUMENT, "sift_bind_result_memory: not inside memory given to sift_register_host_memory");
     CTX_TRY(c, cudaSetDevice(c->device));
-    const int r = ensureSlot(c, slot);
-    if (r != SIFT_OK) return r;
-    Slot& S = c->slot[slot];
+    if (c->twinMode && slot == 1) {
+        const int rt = ensureTwin(c);
+        if (rt != SIFT_OK) return rt;
+    }
+    const LaneRef L = laneOf(c, slot);
+    SiftContext* x = L.x;
+    if (x->slot[L.s].pending) return fail(c, SIFT_ERR_BUSY, "sift_bind_result_memory: the slot has a call in flight");
+    const int r = ensureSlot(x, L.s);
+    if (r != SIFT_OK) {
+        if (x != c) c->lastError = x->lastError;
+        return r;
+    }
+    Slot& S = x->slot[L.s];
     if (S.hostBlock && !S.hostBlockExternal) cudaFreeHost(S.hostBlock);
     S.hostBlock = base;
     S.hostBlockExternal = true;
     S.host = carveColumns(base, (size_t)c->capKp, (size_t)c->capDesc);
     // recorded graphs of this slot carry the old pointers
-    for (size_t i = 0; i < c->graphs.size();) {
-        if (c->graphs[i].slot == slot) {
-            if (c->graphs[i].exec) cudaGraphExecDestroy(c->graphs[i].exec);
-            c->graphs.erase(c->graphs.begin() + (long)i);
+    for (size_t i = 0; i < x->graphs.size();) {
+        if (x->graphs[i].slot == L.s) {
+            if (x->graphs[i].exec) cudaGraphExecDestroy(x->graphs[i].exec);
+            x->graphs.erase(x->graphs.begin() + (long)i);
         } else {
             i++;
         }
     }
-    if (c->last == &S) { c->last = nullptr; c->executed = false; }
+    if (x->last == &S) { x->last = nullptr; x->executed = false; }
     return SIFT_OK;
 }
 
@@ -1048,6 +1104,7 @@ int finishSlot(SiftContext* c, Slot& S) {
         S.status = fail(c, SIFT_ERR_CAPACITY, buf);
     }
     c->last = &S;
+    c->lastOwner = c;
     c->executed = true;
     return S.status;
 }
@@ -1095,54 +1152,85 @@ int checkImages(SiftContext* c, const void* const* images, int n, int pitchBytes
     return SIFT_OK;
 }
 
+// Upload + pipeline of one call on slot s of pipeline x.
+int submitOn(SiftContext* x, int s, const void* const* images, int n, int pitchBytes, bool withDescribe,
+             bool synchronous) {
+    int r = ensureSlot(x, s);
+    if (r != SIFT_OK) return r;
+    Slot& S = x->slot[s];
+    // tuning only: 1 = results stay in HBM (nothing delivered), 2 = no upload (stale input)
+    static const int dbgE2E = getenv("SIFTCUDA_DEBUG_E2E") ? atoi(getenv("SIFTCUDA_DEBUG_E2E")) : 0;
+    if (!(dbgE2E & 2)) {
+        r = enqueueUpload(x, S, images, n, pitchBytes);
+        if (r != SIFT_OK) return r;
+        CTX_TRY(x, cudaStreamWaitEvent(x->stream, S.evUploaded, 0));
+    }
+    RunArgs a;
+    a.input = S.dInput;
+    a.pitch = x->cfg.width * x->bytesPerPixel;
+    a.frameStride = (int64_t)a.pitch * x->cfg.height;
+    a.frames = n;
+    a.withDescribe = withDescribe;
+    a.hostOut = !(dbgE2E & 1);
+    a.copyOut = a.hostOut && (x->resultCopy == 2 || (x->resultCopy == 1 && !synchronous));
+    r = runSlot(x, s, a);
+    if (r != SIFT_OK) return r;
+    S.pending = true;
+    S.staged = false;
+    x->curInput = nullptr;
+    return SIFT_OK;
+}
+
 int submitHost(SiftContext* c, const void* const* images, int n, int pitchBytes, bool withDescribe, bool synchronous) {
     int r = checkImages(c, images, n, pitchBytes, "submit: bad arguments");
     if (r != SIFT_OK) return r;
     if (c->nPending >= 2) return fail(c, SIFT_ERR_BUSY, "both in-flight slots are taken: call sift_wait first");
     CTX_TRY(c, cudaSetDevice(c->device));
-    // synchronous callers only ever use slot 0 (slot 1 is allocated by the first overlapping
-    // submit); pipelined callers alternate, so a result stays valid across the next submit
+    // synchronous callers only ever use lane 0 (lane 1 — the second pipeline of a small context,
+    // slot 1 of a large one — is allocated by the first overlapping submit); pipelined callers
+    // alternate, so a result stays valid across the next submit
     if (synchronous) c->next = 0;
     if (c->nPending == 0) c->head = c->next;
-    const int s = c->next;
-    r = ensureSlot(c, s);
-    if (r != SIFT_OK) return r;
-    Slot& S = c->slot[s];
-    // tuning only: 1 = results stay in HBM (nothing delivered), 2 = no upload (stale input)
-    static const int dbgE2E = getenv("SIFTCUDA_DEBUG_E2E") ? atoi(getenv("SIFTCUDA_DEBUG_E2E")) : 0;
-    if (!(dbgE2E & 2)) {
-        r = enqueueUpload(c, S, images, n, pitchBytes);
+    const int lane = c->next;
+    if (c->twinMode && lane == 1) {
+        r = ensureTwin(c);
         if (r != SIFT_OK) return r;
-        CTX_TRY(c, cudaStreamWaitEvent(c->stream, S.evUploaded, 0));
     }
-    RunArgs a;
-    a.input = S.dInput;
-    a.pitch = c->cfg.width * c->bytesPerPixel;
-    a.frameStride = (int64_t)a.pitch * c->cfg.height;
-    a.frames = n;
-    a.withDescribe = withDescribe;
-    a.hostOut = !(dbgE2E & 1);
-    a.copyOut = a.hostOut && (c->resultCopy == 2 || (c->resultCopy == 1 && !synchronous));
-    r = runSlot(c, s, a);
-    if (r != SIFT_OK) return r;
-    S.pending = true;
-    S.staged = false;
+    const LaneRef L = laneOf(c, lane);
+    r = submitOn(L.x, L.s, images, n, pitchBytes, withDescribe, synchronous);
+    if (r != SIFT_OK) {
+        if (L.x != c) c->lastError = L.x->lastError;
+        return r;
+    }
     c->nPending++;
     c->next ^= 1;
-    c->curInput = nullptr;
     return SIFT_OK;
 }
 
 int waitOldest(SiftContext* c, SiftBatchResult* out) {
     if (c->nPending < 1) return fail(c, SIFT_ERR_BUSY, "sift_wait: nothing submitted");
     CTX_TRY(c, cudaSetDevice(c->device));
-    Slot& S = c->slot[c->head];
-    const int r = finishSlot(c, S);
+    const int lane = c->head;
+    const LaneRef L = laneOf(c, lane);
+    Slot& S = L.x->slot[L.s];
+    const int r = finishSlot(L.x, S);
     S.pending = false;
     c->nPending--;
     c->head ^= 1;
+    c->lastOwner = L.x;
+    if (L.x != c) {
+        // the planes of this call live in the second pipeline: the debug taps and the staged
+        // download of the first one have nothing current to show
+        c->timings = L.x->timings;
+        c->lastError = L.x->lastError;
+        c->last = nullptr;
+        c->executed = false;
+    }
     if (r != SIFT_OK && r != SIFT_ERR_CAPACITY) return r;
-    if (out) fillResult(c, S, out);
+    if (out) {
+        fillResult(L.x, S, out);
+        out->slot = lane;
+    }
     return r;
 }
 

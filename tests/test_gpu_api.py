@@ -118,6 +118,74 @@ def test_pipelined_copy_out_under_load():
         del os.environ["SIFTCUDA_RESULT_COPY"]
 
 
+def test_second_pipeline_of_small_contexts():
+    """A small context runs lane 1 of the pipelined calls on a second pipeline of its own (scratch
+    planes, streams, slot), created by the first overlapping submit, so that consecutive calls
+    overlap on the device. Same results as the synchronous call and as the one-pipeline form
+    (SIFTCUDA_TWIN=0, other process); device matching follows the lane the last call ran on."""
+    import os
+    import subprocess
+    import sys
+
+    from siftmetal_b200 import Engine
+    from siftmetal_b200.synth import pink_noise_bgra
+
+    w, h = 960, 540
+    imgs = [pink_noise_bgra(w, h, 40 + i) for i in range(3)]
+    eng = Engine(w, h, max_batch=2)
+    ref = [eng.detect_and_describe([imgs[i], imgs[(i + 1) % 3]]) for i in range(3)]
+    bytes_one = eng.device_bytes()
+    got, inflight = [], 0
+    for i in range(9):
+        if inflight == 2:
+            got.append(eng.wait())
+            inflight -= 1
+        eng.submit([imgs[i % 3], imgs[(i + 1) % 3]])
+        inflight += 1
+    while inflight:
+        got.append(eng.wait())
+        inflight -= 1
+    slots = [r.slot for r in got]
+    assert all(a != b for a, b in zip(slots, slots[1:])) and set(slots) == {0, 1}    # lanes alternate
+    for i, r in enumerate(got):
+        assert _same(r, ref[i % 3]), i
+    assert eng.device_bytes() > 1.9 * bytes_one            # the second pipeline exists now
+
+    def check_device_match(r):
+        m_dev = eng.match_frames(0, 1)
+        d = r.descriptors
+        k = int(r.descriptor_counts[0].sum())
+        assert np.array_equal(m_dev, eng.match(d["features"][:k], d["features"][k:]))
+
+    # device matching reads the descriptor column of the lane the last completed call ran on
+    eng.submit([imgs[0], imgs[1]])
+    eng.submit([imgs[1], imgs[2]])
+    eng.wait()
+    rb = eng.wait()
+    check_device_match(rb)
+    eng.submit([imgs[2], imgs[0]])
+    rc = eng.wait()
+    assert rc.slot != rb.slot
+    check_device_match(rc)
+    eng.close()
+
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, '.');"
+        "from siftmetal_b200 import Engine; from siftmetal_b200.synth import pink_noise_bgra;"
+        "imgs = [pink_noise_bgra(960, 540, 40 + i) for i in range(3)]; e = Engine(960, 540, max_batch=2);"
+        "b0 = e.device_bytes();"
+        "e.submit([imgs[0], imgs[1]]); e.submit([imgs[1], imgs[2]]); a = e.wait(); b = e.wait();"
+        "assert e.device_bytes() < 1.5 * b0;"
+        "np.savez(sys.argv[1], k0=a.keypoints, d0=a.descriptors, k1=b.keypoints, d1=b.descriptors)"
+    )
+    path = "/tmp/sift_twin_0.npz"
+    subprocess.run([sys.executable, "-c", code, path], check=True, env={**os.environ, "SIFTCUDA_TWIN": "0"},
+                   cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    v = np.load(path)
+    assert np.array_equal(v["k0"], ref[0].keypoints) and np.array_equal(v["d0"], ref[0].descriptors)
+    assert np.array_equal(v["k1"], ref[1].keypoints) and np.array_equal(v["d1"], ref[1].descriptors)
+
+
 def test_graph_replay_equals_launch_by_launch():
     """First call of a shape runs launch by launch, the second records the CUDA graph, later ones
     replay it: identical results; per-stage timing (opt-in) forces the eager path."""
