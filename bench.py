@@ -16,7 +16,9 @@ Default workload = BASELINE.json configs[1]: a single 1920×1080 frame per step 
              in flight) with HOST (pinned) frames: every step's H2D of its frames and the arrival of
              its keypoint + descriptor columns in host memory are inside the wall-clock timed region
              (the kernels store the result columns straight into pinned memory; the upload of step
-             i + 1 crosses PCIe under the kernels of step i). For a sharded workload on N > 1 GPUs
+             i + 1 crosses PCIe under the kernels of step i; a small context — the single-frame
+             workloads — runs the two calls in flight on two pipelines of its own, so their kernels
+             also overlap on the device, which the one-step-at-a-time `value` does not). For a sharded workload on N > 1 GPUs
              the host gather (every rank's result columns visible to rank 0 in frame order: the
              slots are bound to shared-memory segments, one barrier per call) is inside the region too. `sync_call` is the same through the
              synchronous sift_detect_and_describe_batch (no overlap between calls).
@@ -506,7 +508,8 @@ def main():
                     "d2h_bytes_per_step": int(nk_total // max(e2e_steps, 1)) * 26 + int(nd_total // max(e2e_steps, 1)) * 136
                                           + len(chunks) * (24 + 3 * 4 * (7 * chunk + 1)),
                     "steps": e2e_steps,
-                    "timing": "wall clock around sift_submit / sift_wait with two calls in flight, pinned host frames, "
+                    "timing": "wall clock around sift_submit / sift_wait with two calls in flight (on two pipelines of "
+                              "the context when it is small: see sift_get_info device_bytes), pinned host frames, "
                               "result columns in pinned host memory" + (", every call's shards visible on rank 0 in frame order "
                                                                         "(kernels store into shared-memory segments)"
                                                                         if gathered is not None else ""),
