@@ -644,7 +644,12 @@ static int ensureTwin(SiftContext* c) {
     if (c->twin) return SIFT_OK;
     SiftContext* t = nullptr;
     const int r = createContext(&c->cfg, c->device, &t, true);
-    if (r != SIFT_OK) return fail(c, r, "second pipeline (lane 1) could not be created");
+    if (r != SIFT_OK) {
+        // no room (or no luck): lane 1 becomes slot 1 of the one pipeline, as in a large context
+        cudaGetLastError();
+        c->twinMode = false;
+        return SIFT_OK;
+    }
     t->graphsEnabled = c->graphsEnabled;
     t->stageTiming = c->stageTiming;
     c->twin = t;
