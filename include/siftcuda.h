@@ -256,7 +256,7 @@ int sift_detect_and_describe_batch(SiftContext* context, const void* const* imag
  * call i+1 crosses PCIe under the kernels of call i and the results of call i (written into the
  * slot's pinned arrays by the kernels themselves) are complete when its last kernel retires.
  * The host frames must stay valid and unmodified until the matching sift_wait returns.
- * A small context (<= 6 GB of device memory, e.g. single 1080p / 4K frames) gives slot 1 a second
+ * A small context (<= 6 GB of device memory and max_batch <= 8, e.g. single 1080p / 4K frames) gives slot 1 a second
  * pipeline of its own (scratch planes, streams), created by the first overlapping submit: the
  * kernels of two calls in flight then run beside each other on the device, and sift_get_info()
  * reports the doubled device_bytes. After a call that ran on slot 1 the debug taps and

@@ -150,7 +150,8 @@ struct SiftContext {
     // second pipeline — its own scratch planes, streams and slot, created at the first overlapping
     // submit — so that the kernels of two consecutive calls run beside each other instead of in
     // stream order: the descriptor stage of frame i (14 warps per SM) and the launch-bound
-    // compaction chain leave SMs idle that the pyramid of frame i + 1 fills. Large contexts keep
+    // compaction chain leave SMs idle that the pyramid of frame i + 1 fills. Large contexts (more
+    // than 8 frames per call or more than 6 GB) keep
     // both lanes as slots of the one pipeline (a batch fills the machine by itself, and the
     // scratch memory is what bounds the batch).
     SiftContext* twin = nullptr;
@@ -634,7 +635,8 @@ static int createContext(const SiftConfig* cfg, int device, SiftContext** out, b
     // SIFTCUDA_TWIN=0: both lanes in the one pipeline (tuning); SIFTCUDA_TWIN_MB: the size limit
     static const bool twinEnabled = !(getenv("SIFTCUDA_TWIN") && atoi(getenv("SIFTCUDA_TWIN")) == 0);
     static const long twinLimitMb = getenv("SIFTCUDA_TWIN_MB") ? atol(getenv("SIFTCUDA_TWIN_MB")) : 6144;
-    c->twinMode = !isTwin && twinEnabled && c->deviceBytes <= (int64_t)twinLimitMb * (1 << 20);
+    // batches of more than 8 frames fill the machine by themselves (and were measured that way)
+    c->twinMode = !isTwin && twinEnabled && c->B <= 8 && c->deviceBytes <= (int64_t)twinLimitMb * (1 << 20);
     *out = c;
     return SIFT_OK;
 }
